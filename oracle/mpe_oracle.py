@@ -1,0 +1,334 @@
+"""TEST INFRASTRUCTURE ONLY -- CPU oracle for gym-formation's MPE step path (numpy, float64).
+
+Closed-form restatement of the reference algorithm (jc-bao/gym-formation, all citations
+relative to /root/reference):
+
+  * ``MultiAgentEnv.step / _set_action / _get_done``   formation_gym/environment.py:113-142,172-236
+  * ``World.step`` and helpers                          formation_gym/core.py:206-322 (+325-362 walls)
+  * hd scenario ``observation/reward/reset_world``      formation_gym/envs/formation_hd_env.py:38-95,119-121
+  * basic scenario ``observation/reward/reset_world``   formation_gym/envs/basic_formation_env.py:29-65,89-91
+
+Third-party arithmetic restated here (the reference pins no versions --
+``setup.py:4-17`` has no install_requires; this container has numpy 2.3.5 / scipy 1.18.1):
+  * ``scipy.spatial.distance.directed_hausdorff(u, v)[0]`` == sqrt(max_i min_j |u_i - v_j|^2)
+    (call site formation_hd_env.py:66) -- restated as a brute-force max-min.
+  * ``np.logaddexp(0, t)`` (core.py:310) == stable softplus; numpy's own ufunc is called here,
+    the C twin (oracle/mpe_oracle.c) spells it out.
+
+PINNING: the reference ships no tests, golden vectors or fixtures for this path,
+so this oracle is pinned against OUTPUTS OF THE UNMODIFIED REFERENCE RUN IN THE BUILD CONTAINER:
+``tests/golden/make_golden.py`` (committed) drives /root/reference through oracle/ref_harness.py
+and freezes (state, action) -> (pos, vel, obs, rewards, done) into ``tests/golden/*.npz``;
+``tests/test_oracle_golden.py`` checks every function below against those files.
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s cpu_baseline / --impl reference
+legs may import this module, and only as the checker / the timed CPU baseline.  The product
+package must never import it.
+
+All arrays are batched: pos/vel/act ``[E,N,2]``, ideal_shape ``[E,N,2]``, ideal_vel ``[E,2]``,
+landmarks ``[E,L,2]``.  Accumulation order inside an env follows the reference (pairs a<b in
+entity order, core.py:242-254) so float64 results are reproducible to the last bit or two.
+"""
+from dataclasses import dataclass, field
+from typing import Optional, Sequence
+
+import numpy as np
+
+
+@dataclass
+class WorldParams:
+    """World/Agent constants (core.py:45-110,112-139) as one flat record."""
+    dt: float = 0.1                  # core.py:125
+    damping: float = 0.25            # core.py:127
+    contact_force: float = 1e2       # core.py:129
+    contact_margin: float = 1e-3     # core.py:130
+    sensitivity: float = 5.0         # environment.py:218
+    agent_size: float = 0.03         # formation_hd_env.py:26 (basic: 0.1, basic_formation_env.py:18)
+    mass: float = 1.0                # core.py:69,73-75
+    accel: Optional[float] = None    # core.py:65   (scales the action twice when set: Q20)
+    max_speed: Optional[float] = None  # core.py:64
+    u_noise: Optional[float] = None  # core.py:97
+    collide: bool = True             # formation_hd_env.py:24
+    world_length: int = 100          # formation_hd_env.py:13,16 (basic: 50, core.py:113)
+    # optional per-agent overrides [N] (heterogeneous mass/size/accel/max_speed)
+    agent_mass: Optional[Sequence[float]] = None
+    agent_sizes: Optional[Sequence[float]] = None
+    agent_accel: Optional[Sequence[float]] = None
+    agent_max_speed: Optional[Sequence[float]] = None
+    walls: list = field(default_factory=list)   # (orient 'H'|'V', axis_pos, end0, end1, width, hard)
+
+    def per_agent(self, n):
+        mass = np.full(n, self.mass, np.float64) if self.agent_mass is None \
+            else np.asarray(self.agent_mass, np.float64)
+        size = np.full(n, self.agent_size, np.float64) if self.agent_sizes is None \
+            else np.asarray(self.agent_sizes, np.float64)
+        if self.agent_accel is not None:
+            accel = np.asarray(self.agent_accel, np.float64)
+        elif self.accel is not None:
+            accel = np.full(n, self.accel, np.float64)
+        else:
+            accel = None
+        if self.agent_max_speed is not None:
+            vmax = np.asarray(self.agent_max_speed, np.float64)
+        elif self.max_speed is not None:
+            vmax = np.full(n, self.max_speed, np.float64)
+        else:
+            vmax = None
+        return mass, size, accel, vmax
+
+
+HD_PARAMS = WorldParams(agent_size=0.03, world_length=100)
+BASIC_PARAMS = WorldParams(agent_size=0.1, world_length=50)
+
+
+def _two_prod(a, b):
+    """Error-free product (Dekker/Veltkamp): a*b == p + e exactly."""
+    p = a * b
+    c = 134217729.0
+    ah = a * c
+    ah = ah - (ah - a)
+    al = a - ah
+    bh = b * c
+    bh = bh - (bh - b)
+    bl = b - bh
+    e = ((ah * bh - p) + ah * bl + al * bh) + al * bl
+    return p, e
+
+
+def norm2(x0, x1):
+    """``np.linalg.norm([x0, x1])`` as the reference evaluates it (core.py:305,
+    formation_hd_env.py:69,120, basic_formation_env.py:46,90): for a 1-D vector numpy computes
+    ``sqrt(dot(x, x))`` and the BLAS ddot of the numpy build the golden files were generated with
+    contracts the 2-term sum into ``fma(x1, x1, x0*x0)``.  Emulated here with error-free
+    transformations (verified equal to np.linalg.norm on 6e5 random vectors, 0 mismatches); the
+    difference from the plain ``sqrt(x0*x0 + x1*x1)`` is at most 1 ulp, which only matters for
+    bit-level agreement of long stiff-contact trajectories."""
+    with np.errstate(all='ignore'):
+        a = x0 * x0
+        p, e = _two_prod(x1, x1)
+        s = a + p
+        bb = s - a
+        t = (a - (s - bb)) + (p - bb)
+        r = np.sqrt(s + (t + e))
+    # inf/nan inputs: fall back to the plain formula (error terms are nan there)
+    plain = np.sqrt(x0 * x0 + x1 * x1)
+    return np.where(np.isfinite(r), r, plain)
+
+
+# ------------------------------------------------------------------------------------------
+# World.step  (core.py:206-225)
+# ------------------------------------------------------------------------------------------
+def wall_force(p, size, wall, prm):
+    """get_wall_collision_force (core.py:325-362) for a batch of positions p [E,2]."""
+    orient, axis_pos, e0, e1, width, _hard = wall
+    prll, perp = (0, 1) if orient == 'H' else (1, 0)
+    x = p[:, prll]
+    beyond = (x < e0 - size) | (x > e1 + size)
+    partial = ((x < e0) | (x > e1)) & ~beyond
+    past = np.where(x < e0, x - e0, x - e1)
+    past = np.where(partial, past, 0.0)
+    theta = np.arcsin(past / size)
+    dist_min = np.where(partial, np.cos(theta) * size + 0.5 * width, size + 0.5 * width)
+    delta = p[:, perp] - axis_pos
+    dist = np.abs(delta)
+    k = prm.contact_margin
+    with np.errstate(all='ignore'):
+        pen = np.logaddexp(0, -(dist - dist_min) / k) * k
+        fmag = prm.contact_force * delta / dist * pen
+    f = np.zeros_like(p)
+    f[:, perp] = np.cos(theta) * fmag
+    f[:, prll] = np.sin(theta) * np.abs(fmag)
+    f[beyond] = 0.0
+    return f
+
+
+def world_step(pos, vel, act, prm=HD_PARAMS, noise=None):
+    """One ``World.step`` after ``_set_action``.  Returns new (pos, vel); inputs untouched.
+
+    environment.py:216-221 (u = a * sensitivity), core.py:228-237 (action force),
+    core.py:240-262 + 289-322 (pairwise contact force from the OLD positions),
+    core.py:264-277 (damping, F/m*dt, max_speed clamp, p += v*dt)."""
+    pos = np.asarray(pos, np.float64)
+    vel = np.asarray(vel, np.float64)
+    act = np.asarray(act, np.float64)
+    E, N, _ = pos.shape
+    mass, size, accel, vmax = prm.per_agent(N)
+    sens = np.full(N, prm.sensitivity) if accel is None else accel        # environment.py:218-220
+    gain = mass if accel is None else mass * accel                         # core.py:235-236
+    u = act * sens[None, :, None]
+    F = gain[None, :, None] * u + (0.0 if noise is None else noise)        # core.py:232-236
+    F = np.array(F, np.float64)
+    if prm.collide:
+        k = prm.contact_margin
+        with np.errstate(all='ignore'):      # coincident agents -> 0/0 -> NaN, as the reference
+            for a in range(N):
+                for b in range(a + 1, N):
+                    delta = pos[:, a] - pos[:, b]                          # core.py:304
+                    dist = norm2(delta[:, 0], delta[:, 1])                      # core.py:305
+                    dist_min = size[a] + size[b]                           # core.py:307
+                    pen = np.logaddexp(0, -(dist - dist_min) / k) * k      # core.py:310
+                    force = prm.contact_force * delta / dist[:, None] * pen[:, None]  # :312
+                    ratio = mass[b] / mass[a]                              # core.py:316
+                    F[:, a] = ratio * force + F[:, a]                      # core.py:250,317
+                    F[:, b] = -(1 / ratio) * force + F[:, b]               # core.py:254,318
+    for w in prm.walls:                                                    # core.py:255-261
+        for a in range(N):
+            F[:, a] = F[:, a] + wall_force(pos[:, a], size[a], w, prm)
+    v = vel * (1 - prm.damping)                                            # core.py:268
+    v = v + (F / mass[None, :, None]) * prm.dt                             # core.py:270
+    if vmax is not None:                                                   # core.py:271-276
+        sp = np.sqrt(np.square(v[..., 0]) + np.square(v[..., 1]))
+        over = sp > vmax[None, :]
+        with np.errstate(all='ignore'):
+            clamped = v / sp[..., None] * vmax[None, :, None]
+        v = np.where(over[..., None], clamped, v)
+    p = pos + v * prm.dt                                                   # core.py:277
+    return p, v
+
+
+# ------------------------------------------------------------------------------------------
+# formation_hd_env scenario hooks
+# ------------------------------------------------------------------------------------------
+def hd_observation(pos, vel, ideal_shape, ideal_vel):
+    """formation_hd_env.py:52-59: [v_i, (p_j - p_i) j!=i ascending, comm zeros 2(N-1),
+    ideal_shape.flatten(), ideal_vel] -> [E,N,6N]."""
+    E, N, _ = pos.shape
+    obs = np.zeros((E, N, 6 * N), np.float64)
+    flat_shape = np.asarray(ideal_shape, np.float64).reshape(E, 2 * N)
+    for i in range(N):
+        obs[:, i, 0:2] = vel[:, i]
+        others = [j for j in range(N) if j != i]
+        rel = pos[:, others] - pos[:, i:i + 1]
+        obs[:, i, 2:2 * N] = rel.reshape(E, 2 * (N - 1))
+        obs[:, i, 4 * N - 2:6 * N - 2] = flat_shape
+        obs[:, i, 6 * N - 2:6 * N] = ideal_vel
+    return obs
+
+
+def hd_landmark_shift(pos, landmarks, times=1):
+    """Side effect of every hd ``observation`` call (formation_hd_env.py:40-44): landmarks are
+    re-centred on the agents' centroid.  Called N times per step/reset by the env facade."""
+    lm = np.array(landmarks, np.float64)
+    for _ in range(times):
+        delta = np.mean(pos, 1) - np.mean(lm, 1)
+        lm = lm + delta[:, None, :]
+    return lm
+
+
+def directed_hausdorff_sq(u, v):
+    """max_i min_j |u_i - v_j|^2 for batches u [E,N,2], v [E,M,2] (scipy's result squared)."""
+    dx = u[:, :, None, 0] - v[:, None, :, 0]
+    dy = u[:, :, None, 1] - v[:, None, :, 1]
+    d2 = dx * dx + dy * dy
+    return d2.min(2).max(1)
+
+
+def hd_reward(pos, vel, ideal_shape, ideal_vel, prm=HD_PARAMS):
+    """formation_hd_env.py:61-75,119-121 -> individual rewards [E,N] (post-step state)."""
+    E, N, _ = pos.shape
+    _, size, _, _ = prm.per_agent(N)
+    C = pos - np.mean(pos, 1)[:, None, :]                                   # :64-65
+    S = np.asarray(ideal_shape, np.float64)
+    form = -np.sqrt(np.maximum(directed_hausdorff_sq(C, S), directed_hausdorff_sq(S, C)))  # :66
+    mean_vel = np.mean(vel, 1)                                              # :68
+    dv = np.asarray(ideal_vel, np.float64) - mean_vel
+    velr = norm2(dv[:, 0], dv[:, 1])                                        # :69
+    base = form - velr
+    rew = np.repeat(base[:, None], N, 1)
+    if prm.collide:                                                         # :71-74
+        for i in range(N):
+            r = rew[:, i].copy()
+            for j in range(N):
+                if j == i:
+                    continue
+                d = pos[:, j] - pos[:, i]
+                dist = norm2(d[:, 0], d[:, 1])
+                r = np.where(dist < (size[i] + size[j]) / 2, r - 1, r)      # :119-121
+            rew[:, i] = r
+    return rew
+
+
+# ------------------------------------------------------------------------------------------
+# basic_formation_env scenario hooks
+# ------------------------------------------------------------------------------------------
+def basic_observation(pos, vel, landmarks):
+    """basic_formation_env.py:29-41: [v_i, p_i, (l_k - p_i) k, (p_j - p_i) j!=i, comm zeros]."""
+    E, N, _ = pos.shape
+    L = landmarks.shape[1]
+    D = 4 + 2 * L + 4 * (N - 1)
+    obs = np.zeros((E, N, D), np.float64)
+    for i in range(N):
+        obs[:, i, 0:2] = vel[:, i]
+        obs[:, i, 2:4] = pos[:, i]
+        obs[:, i, 4:4 + 2 * L] = (landmarks - pos[:, i:i + 1]).reshape(E, 2 * L)
+        others = [j for j in range(N) if j != i]
+        obs[:, i, 4 + 2 * L:4 + 2 * L + 2 * (N - 1)] = \
+            (pos[:, others] - pos[:, i:i + 1]).reshape(E, 2 * (N - 1))
+    return obs
+
+
+def basic_reward(pos, landmarks, prm=BASIC_PARAMS):
+    """basic_formation_env.py:43-52,89-91: -sum_l min_a |p_a - l| - #{a (incl. self): |p_a-p_i| < s_a+s_i}."""
+    E, N, _ = pos.shape
+    L = landmarks.shape[1]
+    _, size, _, _ = prm.per_agent(N)
+    base = np.zeros(E, np.float64)
+    for k in range(L):
+        d = pos - landmarks[:, k:k + 1]
+        dist = norm2(d[..., 0], d[..., 1])
+        base = base - dist.min(1)
+    rew = np.repeat(base[:, None], N, 1)
+    if prm.collide:
+        for i in range(N):
+            r = rew[:, i].copy()
+            for j in range(N):                      # includes j == i (dist 0 < 2s): Q7
+                d = pos[:, j] - pos[:, i]
+                dist = norm2(d[:, 0], d[:, 1])
+                r = np.where(dist < (size[i] + size[j]), r - 1, r)
+            rew[:, i] = r
+    return rew
+
+
+# ------------------------------------------------------------------------------------------
+# MultiAgentEnv.step  (environment.py:113-142)
+# ------------------------------------------------------------------------------------------
+def shared_reward(indiv):
+    """environment.py:136-138: reward = np.sum(reward_n) with reward_n a list of N [r_i]."""
+    return np.array([np.sum(row.reshape(-1, 1)) for row in indiv], np.float64)
+
+
+def hd_env_step(pos, vel, act, ideal_shape, ideal_vel, step, prm=HD_PARAMS, landmarks=None,
+                noise=None):
+    """Full ``env.step`` for formation_hd_env.  ``step`` [E] is current_step BEFORE the call."""
+    p, v = world_step(pos, vel, act, prm, noise)
+    obs = hd_observation(p, v, ideal_shape, ideal_vel)
+    indiv = hd_reward(p, v, ideal_shape, ideal_vel, prm)
+    new_step = np.asarray(step) + 1                                         # environment.py:114
+    done = new_step >= prm.world_length                                     # :172-177
+    out = dict(pos=p, vel=v, obs=obs, indiv=indiv, reward=shared_reward(indiv),
+               done=done, step=new_step)
+    if landmarks is not None:
+        out['landmarks'] = hd_landmark_shift(p, landmarks, times=p.shape[1])
+    return out
+
+
+def basic_env_step(pos, vel, act, landmarks, step, prm=BASIC_PARAMS, noise=None):
+    p, v = world_step(pos, vel, act, prm, noise)
+    obs = basic_observation(p, v, landmarks)
+    indiv = basic_reward(p, landmarks, prm)
+    new_step = np.asarray(step) + 1
+    done = new_step >= prm.world_length
+    return dict(pos=p, vel=v, obs=obs, indiv=indiv, reward=shared_reward(indiv),
+                done=done, step=new_step)
+
+
+# ------------------------------------------------------------------------------------------
+# reset (formation_hd_env.py:77-95, basic_formation_env.py:54-65) from given uniforms
+# ------------------------------------------------------------------------------------------
+def hd_reset_from_uniform(u_pos, u_lm, u_vel):
+    """u_* are U(-1,1) draws in the reference's order (agents, landmarks, ideal_vel).
+    Returns pos, vel, landmarks, ideal_shape (centred, :93), ideal_vel."""
+    pos = np.array(u_pos, np.float64)
+    lm = np.array(u_lm, np.float64)
+    shape = lm - np.mean(lm, 1)[:, None, :]
+    return pos, np.zeros_like(pos), lm, shape, np.array(u_vel, np.float64)
