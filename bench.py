@@ -1,0 +1,380 @@
+#!/usr/bin/env python
+"""bench.py -- agent-steps/sec of the gym-formation MPE step path on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's CUDA path
+    python bench.py --impl reference [--gpus N] --steps K --warmup W   # CPU reference arm
+
+One "step" = one env step (MultiAgentEnv.step semantics) of EVERY env of the batch: the random
+policy kernel (fg_random_actions: act ~ U(-1,1), test.py:20) followed by the fused step kernel
+(fg_step_fused: _set_action + World.step + observation + reward + done + auto-reset).  Workload
+(config.workload): formation_hd_env, 9 agents, 131072 envs per GPU (= the north star's 1M envs on
+8 GPUs), episode_length 25, fp32.  A step moves 131072 * 2437 B = 319 MB > the 126 MB L2, so
+every timed iteration streams from/to HBM (no L2 flush needed).
+
+Printed JSON keys beyond the base contract: `roofline` (fused step kernel vs measured HBM peak),
+`cpu_baseline` (oracle port on the host cores, N=1 only), `e2e` (same metric through the public
+API with pinned HOST buffers: H2D of the actions and D2H of obs/reward/done inside the timed
+region), `clocks`, `gpu_launches`, `also` (other BASELINE configs, informational).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (os.path.join(ROOT, "gym-formation_b200"), ROOT):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+METRIC = "agent-steps/sec (formation_hd_env, random policy)"
+UNIT = "agent-steps/s"
+FALLBACK_HBM_GBS = 6650.0          # /opt/skills/guides/B200_PROFILING.md fallback
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=25)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--scenario", default="formation_hd_env")
+    ap.add_argument("--agents", type=int, default=9)
+    ap.add_argument("--envs-per-gpu", type=int, default=131072)
+    ap.add_argument("--episode-length", type=int, default=25)
+    ap.add_argument("--dtype", default="f32", choices=["f32", "f64"])
+    ap.add_argument("--no-obs", action="store_true", help="state+reward only (B_state accounting)")
+    ap.add_argument("--e2e-steps", type=int, default=10)
+    ap.add_argument("--cpu-seconds", type=float, default=3.0)
+    ap.add_argument("--no-also", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def hbm_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons DURING the timed region (profiling recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return None
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for nm, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                pass
+        if not sm:
+            return None
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+def run_reference(a):
+    """CPU reference arm: the reference's per-env numpy loop (oracle/ref_loop_port.py -- the
+    unmodified reference cannot travel to the GPU box) on all host cores, one env per process
+    like the reference's SubprocVecEnv.  A 'step' = one env step of that batch of P envs."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    import numpy as np
+    from oracle import ref_loop_port as rp
+
+    procs = os.cpu_count() or 1
+    N, K, W = a.agents, a.steps, a.warmup
+    # keep the whole run within a few minutes whatever K is
+    per_step = {3: 0.004, 9: 0.015, 27: 0.07}.get(N, 0.01 * N)
+    K_eff = max(1, min(K, int(120.0 / per_step)))
+
+    def worker(q, seed):
+        np.random.seed(seed)
+        env = rp.RefLoopEnv(a.scenario, N, a.episode_length)
+        acts = lambda: [np.random.uniform(-1, 1, 2) for _ in range(N)]  # noqa: E731
+        for _ in range(min(W, 10)):
+            env.step(acts())
+        t0 = time.perf_counter()
+        for _ in range(K_eff):
+            _, _, done_n, _ = env.step(acts())
+            if all(done_n):
+                env.reset()
+        q.put(time.perf_counter() - t0)
+
+    ctx = mp.get_context("fork")
+    q = ctx.Queue()
+    ps = [ctx.Process(target=worker, args=(q, 100 + k)) for k in range(procs)]
+    t0 = time.perf_counter()
+    for p in ps:
+        p.start()
+    times = [q.get() for _ in ps]
+    for p in ps:
+        p.join()
+    wall = max(times)
+    value = procs * N * K_eff / wall
+    sample = ("%d envs (one per host core, %d processes) x %d env-steps of %s N=%d, episode_length %d; "
+              "per-env Python/numpy loop port of the reference (oracle/ref_loop_port.py, scipy "
+              "directed_hausdorff=%s)" % (procs, procs, K_eff, a.scenario, N, a.episode_length, rp.HAVE_SCIPY))
+    out = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus,
+        "steps": K_eff, "warmup": min(W, 10), "ms_per_step": wall / K_eff * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic", "config": workload_config(a, procs, "cpu"),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": procs, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(out), flush=True)
+
+
+def workload_config(a, envs_per_unit, where):
+    return {"workload": "%s N=%d, %d envs per %s, episode_length %d, random policy U(-1,1), auto-reset"
+                        % (a.scenario, a.agents, envs_per_unit, "GPU" if where == "gpu" else "run",
+                           a.episode_length),
+            "scenario": a.scenario, "agents": a.agents, "envs_per_gpu": envs_per_unit if where == "gpu" else None,
+            "episode_length": a.episode_length, "obs": not a.no_obs,
+            "l2": "inputs larger than L2 (step traffic > 126 MB), no flush" if where == "gpu" else None}
+
+
+def run_b200(a):
+    import torch
+    import torch.distributed as dist
+    import formation_gym
+    from formation_gym import distributed as fgd
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the step path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=device)
+    dtype = torch.float32 if a.dtype == "f32" else torch.float64
+    E, N, K, W = a.envs_per_gpu, a.agents, a.steps, max(a.warmup, 3)
+    lo, hi = fgd.shard_range(E * world, rank, world)              # contiguous env range of this rank
+    env = formation_gym.make_batched_env(a.scenario, hi - lo, N, a.episode_length, device=device,
+                                         dtype=dtype, seed=0, auto_reset=True, env_offset=lo,
+                                         write_obs=not a.no_obs)
+    env.reset()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    def one_step():
+        env.sample_actions()
+        return env.step(env.actions)
+
+    for _ in range(W):
+        one_step()
+    torch.cuda.synchronize()
+
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ka = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    kb = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+        time.sleep(0.3)
+    launches0 = env.launches
+    barrier(); torch.cuda.synchronize()
+    ev0.record()
+    for k in range(K):
+        env.sample_actions()
+        ka[k].record()
+        env.step(env.actions)
+        kb[k].record()
+    ev1.record()
+    torch.cuda.synchronize(); barrier()
+    launches = env.launches - launches0
+    ms = ev0.elapsed_time(ev1)
+    # keep the sampler alive a little if the region was short, so it has samples under load
+    clocks = None
+    if sampler:
+        t_extra = time.time()
+        while len(sampler.rows) < 3 and time.time() - t_extra < 1.0:
+            one_step()
+        torch.cuda.synchronize()
+        clocks = sampler.stop()
+    t = torch.tensor([ms], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    kernel_ms = statistics.mean(x.elapsed_time(y) for x, y in zip(ka, kb))
+    total_agents = (hi - lo) * world * N
+    value = total_agents * K / (ms * 1e-3)
+
+    # episode statistics: the ONLY collective of the design (NCCL all-reduce of 4 doubles)
+    stats = fgd.all_reduce_stats(env.stats.clone())
+    ep = {"episodes": float(stats[0]), "return_mean": float(stats[1] / stats[0]) if float(stats[0]) else None}
+
+    # ---------------- e2e: public API with pinned HOST buffers ----------------
+    e2e = None
+    if env.obs is not None:
+        Ke = max(1, a.e2e_steps)
+        act_h = torch.empty(hi - lo, N, 2, dtype=dtype).uniform_(-1, 1).pin_memory()
+        obs_h = torch.empty(env.obs.shape, dtype=dtype).pin_memory()
+        rew_h = torch.empty(env.reward.shape, dtype=dtype).pin_memory()
+        done_h = torch.empty(env.done.shape, dtype=torch.bool).pin_memory()
+        act_d = torch.empty_like(env.actions)
+
+        def e2e_step():
+            act_d.copy_(act_h, non_blocking=True)                 # H2D of this step's inputs
+            obs, rew, done, _ = env.step(act_d)
+            obs_h.copy_(obs, non_blocking=True)                   # D2H of what env.step returns
+            rew_h.copy_(rew, non_blocking=True)
+            done_h.copy_(done, non_blocking=True)
+            torch.cuda.synchronize()                              # the host caller needs the result
+
+        for _ in range(2):
+            e2e_step()
+        barrier(); torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(Ke):
+            e2e_step()
+        torch.cuda.synchronize()
+        dt_e = time.perf_counter() - t0
+        barrier()
+        te = torch.tensor([dt_e], dtype=torch.float64, device=device)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e = {"value": total_agents * Ke / float(te.item()), "unit": UNIT,
+               "h2d_bytes_per_step": act_h.numel() * act_h.element_size() * world,
+               "d2h_bytes_per_step": (obs_h.numel() * obs_h.element_size() + rew_h.numel() * rew_h.element_size()
+                                      + done_h.numel()) * world,
+               "steps": Ke, "note": "H2D actions + fused step + D2H obs/reward/done per step, pinned host "
+                                    "buffers, host sync every step (PCIe-bound: obs is 24N^2 B per env)"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = hbm_peak()
+    bytes_step = env.bytes_per_env_step() * (hi - lo)
+    achieved = bytes_step / (kernel_ms * 1e-3) / 1e9
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            tj = json.load(f)
+        key = "%s_N%d_E%d_%s" % (a.scenario, N, hi - lo, a.dtype)
+        traffic = tj.get(key, {}).get("dram_bytes_per_launch")
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "kernel": "fg::k_step<%s,hd,phys,obsrew> (fg_step_fused)" % a.dtype,
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "peak_source": peak_src, "kernel_ms": kernel_ms,
+                "algorithmic_bytes_per_env_step": env.bytes_per_env_step(),
+                "share_of_step": kernel_ms * K / ms}
+
+    cpu_baseline = None
+    if world == 1 and not a.no_cpu_baseline:
+        from oracle import ref_loop_port as rp
+        r = rp.time_port(a.scenario, N, a.episode_length, seconds=a.cpu_seconds)
+        cpu_baseline = {"value": r["agent_steps_per_s"], "unit": UNIT, "cores": r["procs"], "kind": "port",
+                        "sample": "%d processes x %.1f s of per-env stepping (%d env-steps total) of %s N=%d, "
+                                  "episode_length %d; oracle/ref_loop_port.py (reference-structured numpy loop, "
+                                  "scipy=%s)" % (r["procs"], a.cpu_seconds, r["env_steps"], a.scenario, N,
+                                                 a.episode_length, r["scipy"])}
+
+    also = None
+    if world == 1 and not a.no_also:
+        also = also_configs(formation_gym, torch, device, dtype, peak)
+
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": a.dtype, "data": "synthetic", "config": workload_config(a, hi - lo, "gpu"),
+        "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "clocks": clocks,
+        "gpu_launches": launches, "episode_stats": ep, "also": also,
+    }
+    print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def also_configs(formation_gym, torch, device, dtype, peak):
+    """Other BASELINE.json configs, measured briefly (informational; not the headline line)."""
+    res = []
+    for name, scen, N, E, steps, mode in (
+            ("configs[1] hd N=9 E=4096 (launch-bound; per-step launches)", "formation_hd_env", 9, 4096, 500, "step"),
+            ("configs[1] hd N=9 E=4096 (in-kernel 25-step rollouts)", "formation_hd_env", 9, 4096, 40, "rollout"),
+            ("configs[2] hd N=27 E=65536", "formation_hd_env", 27, 65536, 50, "step"),
+            ("configs[3] hd N=243 E=1024 (one GPU's share of 8192)", "formation_hd_env", 243, 1024, 30, "step"),
+            ("hd N=243 E=1024 state+reward only (no obs)", "formation_hd_env", 243, 1024, 30, "noobs"),
+            ("hd N=3 E=262144", "formation_hd_env", 3, 262144, 100, "step"),
+            ("basic N=3 L=3 E=262144", "basic_formation_env", 3, 262144, 100, "step")):
+        try:
+            env = formation_gym.make_batched_env(scen, E, N, 25, device=device, dtype=dtype, seed=1,
+                                                 write_obs=(mode != "noobs"))
+            env.reset()
+
+            def run(n):
+                for _ in range(n):
+                    if mode == "rollout":
+                        env.rollout_random(25)
+                    else:
+                        env.sample_actions(); env.step(env.actions)
+            run(5)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); run(steps); e1.record(); torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1)
+            env_steps = steps * (25 if mode == "rollout" else 1)
+            gbs = env.bytes_per_env_step() * E * env_steps / (ms * 1e-3) / 1e9
+            res.append({"config": name, "agent_steps_per_s": E * N * env_steps / (ms * 1e-3),
+                        "ms_per_env_step": ms / env_steps, "algorithmic_GBps": gbs, "hbm_frac": gbs / peak})
+            del env
+        except Exception as ex:  # keep the headline line alive
+            res.append({"config": name, "error": repr(ex)[:200]})
+    return res
+
+
+if __name__ == "__main__":
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)

@@ -1,0 +1,274 @@
+// fg_abi.cu -- extern "C" entry points declared in include/formation_gym_b200.h.
+// Validates arguments, converts fg_params (double) into the kernels' typed argument block and
+// launches asynchronously on the caller's stream.  No allocation, no global state, no sync.
+#include <cstdio>
+#include <cstring>
+#include <cmath>
+
+#include "../../include/formation_gym_b200.h"
+#include "fg_kernels.cuh"
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, const char* detail = "") {
+    snprintf(g_err, sizeof(g_err), fmt, detail);
+    return code;
+}
+
+uint32_t magic_for(int d) {          // floor(2^32 / d) + 1; 0 encodes d == 1 (fastdiv returns q)
+    if (d <= 1) return 0u;
+    return (uint32_t)((((uint64_t)1) << 32) / (uint64_t)d) + 1u;
+}
+
+template <typename T> double kcut_for();
+// Contact cut-off in units of contact_margin: beyond d_min + kcut*k the softplus penetration is
+// < k*exp(-kcut): 9e-17 (fp32 build, rounding of F ~ 6e-8) / 2e-25 (fp64 build, tolerance 1e-9).
+template <> double kcut_for<float>() { return 30.0; }
+template <> double kcut_for<double>() { return 50.0; }
+
+template <typename T>
+int fill_args(fg::KArgs<T>& a, const fg_params* p, const fg_buffers* b, int scenario, int E, int N, int L,
+              uint64_t seed, uint32_t tick, uint32_t env_offset) {
+    typedef typename fg::Ops<T>::R2 R2;
+    if (!p || !b) return fail(FG_ERR_ARG, "null params/buffers%s");
+    if (E < 1) return fail(FG_ERR_ARG, "E must be >= 1%s");
+    if (N < 1 || N > FG_MAX_AGENTS) return fail(FG_ERR_ARG, "N must be in [1, FG_MAX_AGENTS=256]%s");
+    if (scenario == FG_SCENARIO_HD) {
+        if (N < 3) return fail(FG_ERR_ARG, "formation_hd_env needs N >= 3 (formation_hd_env.py:58)%s");
+        L = N;
+    } else if (scenario == FG_SCENARIO_BASIC) {
+        if (L < 1 || L > FG_MAX_LANDMARKS) return fail(FG_ERR_ARG, "L must be in [1, FG_MAX_LANDMARKS]%s");
+    } else {
+        return fail(FG_ERR_ARG, "unknown scenario id%s");
+    }
+    if ((uint64_t)E * (uint64_t)N >= (1ull << 31)) return fail(FG_ERR_ARG, "E*N must be < 2^31%s");
+    if (p->n_walls < 0 || p->n_walls > FG_MAX_WALLS) return fail(FG_ERR_ARG, "n_walls out of range%s");
+    memset(&a, 0, sizeof(a));
+    a.pos = (R2*)b->pos; a.vel = (R2*)b->vel; a.act = (const R2*)b->act; a.comm = (R2*)b->comm;
+    a.shape = (R2*)b->ideal_shape; a.ivel = (R2*)b->ideal_vel; a.lm = (R2*)b->landmarks;
+    a.step = b->step; a.obs = (R2*)b->obs; a.reward = (T*)b->reward; a.indiv = (T*)b->indiv;
+    a.done = b->done; a.ep_return = (T*)b->ep_return; a.ep_coll = b->ep_collisions; a.stats = b->stats;
+    a.a_mass = (const T*)p->agent_mass; a.a_size = (const T*)p->agent_size_arr;
+    a.a_accel = (const T*)p->agent_accel; a.a_vmax = (const T*)p->agent_max_speed;
+    a.E = E; a.N = N; a.L = L;
+    a.EPC = fg::kBlock / N;
+    a.IPR = scenario == FG_SCENARIO_HD ? 3 * N : 2 + L + 2 * (N - 1);
+    a.magic_n = magic_for(N); a.magic_ipr = magic_for(a.IPR);
+    a.act_r2 = p->silent ? 1 : 2;
+    a.dt = (T)p->dt; a.keep = (T)(1.0 - p->damping); a.cforce = (T)p->contact_force;
+    a.margin = (T)p->contact_margin; a.size = (T)p->agent_size; a.mass = (T)p->mass;
+    a.vmax = (T)p->max_speed; a.u_noise = (T)p->u_noise; a.c_noise = (T)p->c_noise;
+    a.sens0 = (T)p->sensitivity; a.accel = (T)p->accel;
+    a.has_accel = p->has_accel; a.has_vmax = p->has_max_speed;
+    a.sens = p->action_prescaled ? (T)1 : (p->has_accel ? (T)p->accel : (T)p->sensitivity);
+    a.prescaled = p->action_prescaled;
+    a.gain = p->has_accel ? (T)((T)p->mass * (T)p->accel) : (T)p->mass;
+    a.kcut = (T)kcut_for<T>();
+    {
+        T dmin = a.size + a.size;
+        T c = dmin + a.kcut * a.margin;
+        a.cut2 = c * c;
+        // hd: (s1+s2)/2 (formation_hd_env.py:121); basic: s1+s2 (basic_formation_env.py:91)
+        a.rthr = scenario == FG_SCENARIO_HD ? dmin / (T)2 : dmin;
+        a.rthr2_hi = a.rthr * a.rthr * (T)1.0001;
+    }
+    a.collide = p->collide; a.silent = p->silent; a.world_length = p->world_length;
+    a.n_walls = p->n_walls;
+    for (int w = 0; w < p->n_walls; ++w) {
+        a.walls[w].orient = p->walls[w].orient; a.walls[w].hard = p->walls[w].hard;
+        a.walls[w].axis_pos = (T)p->walls[w].axis_pos; a.walls[w].end0 = (T)p->walls[w].end0;
+        a.walls[w].end1 = (T)p->walls[w].end1; a.walls[w].width = (T)p->walls[w].width;
+    }
+    a.n_steps = 1; a.random_actions = 0; a.auto_reset = 0;
+    a.seed = seed; a.tick = tick; a.env_offset = env_offset;
+    return FG_OK;
+}
+
+template <typename T>
+size_t smem_bytes(const fg::KArgs<T>& a, int scenario, bool het) {
+    typedef typename fg::Ops<T>::R2 R2;
+    typedef typename fg::Ops<T>::Bits Bits;
+    const size_t nA = (size_t)a.EPC * a.N;
+    const size_t nS = scenario == FG_SCENARIO_HD ? nA : (size_t)a.EPC * a.L;
+    size_t s = (4 * nA + nS + a.EPC) * sizeof(R2) + 2 * a.EPC * sizeof(Bits);
+    if (scenario == FG_SCENARIO_BASIC) s += (size_t)a.EPC * a.L * sizeof(T);
+    if (het) s += 5 * (size_t)a.N * sizeof(T);
+    s += 2 * a.EPC * sizeof(int);
+    return (s + 15) & ~(size_t)15;
+}
+
+template <typename T, int SCN, bool PHYS, bool OBSREW>
+int launch_het(const fg::KArgs<T>& a, bool het, size_t smem, cudaStream_t st) {
+    const int grid = (a.E + a.EPC - 1) / a.EPC;
+    if (het) fg::k_step<T, SCN, PHYS, OBSREW, true><<<grid, fg::kBlock, smem, st>>>(a);
+    else     fg::k_step<T, SCN, PHYS, OBSREW, false><<<grid, fg::kBlock, smem, st>>>(a);
+    cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess) return fail(FG_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(err));
+    return FG_OK;
+}
+
+template <typename T, bool PHYS, bool OBSREW>
+int launch(const fg::KArgs<T>& a, int scenario, const fg_params* p, void* stream) {
+    const bool het = p->agent_mass || p->agent_size_arr || p->agent_accel || p->agent_max_speed;
+    const size_t smem = smem_bytes<T>(a, scenario, het);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (scenario == FG_SCENARIO_HD) return launch_het<T, fg::kScnHD, PHYS, OBSREW>(a, het, smem, st);
+    return launch_het<T, fg::kScnBasic, PHYS, OBSREW>(a, het, smem, st);
+}
+
+template <typename T>
+int world_step_impl(const fg_params* p, const fg_buffers* b, int E, int N, uint64_t seed, uint32_t tick,
+                    uint32_t env_offset, void* stream) {
+    fg::KArgs<T> a;
+    // the physics does not depend on the scenario; hd's N>=3 rule must not apply here
+    int rc = fill_args<T>(a, p, b, FG_SCENARIO_BASIC, E, N, 1, seed, tick, env_offset);
+    if (rc) return rc;
+    if (!b->pos || !b->vel || !b->act) return fail(FG_ERR_ARG, "fg_world_step: pos/vel/act must be non-null%s");
+    return launch<T, true, false>(a, FG_SCENARIO_BASIC, p, stream);
+}
+
+template <typename T>
+int obs_reward_impl(const fg_params* p, const fg_buffers* b, int scenario, int E, int N, int L, void* stream) {
+    fg::KArgs<T> a;
+    int rc = fill_args<T>(a, p, b, scenario, E, N, L, 0, 0, 0);
+    if (rc) return rc;
+    if (!b->pos || !b->vel || !b->reward) return fail(FG_ERR_ARG, "fg_obs_reward: pos/vel/reward must be non-null%s");
+    if (scenario == FG_SCENARIO_HD && (!b->ideal_shape || !b->ideal_vel))
+        return fail(FG_ERR_ARG, "fg_obs_reward(hd): ideal_shape/ideal_vel must be non-null%s");
+    if (scenario == FG_SCENARIO_BASIC && !b->landmarks)
+        return fail(FG_ERR_ARG, "fg_obs_reward(basic): landmarks must be non-null%s");
+    a.step = nullptr; a.done = nullptr; a.ep_return = nullptr; a.ep_coll = nullptr; a.stats = nullptr;
+    return launch<T, false, true>(a, scenario, p, stream);
+}
+
+template <typename T>
+int step_fused_impl(const fg_params* p, const fg_buffers* b, int scenario, int E, int N, int L, int n_steps,
+                    int random_actions, int auto_reset, uint64_t seed, uint32_t tick, uint32_t env_offset,
+                    void* stream) {
+    fg::KArgs<T> a;
+    int rc = fill_args<T>(a, p, b, scenario, E, N, L, seed, tick, env_offset);
+    if (rc) return rc;
+    if (!b->pos || !b->vel || !b->reward || !b->done || !b->step)
+        return fail(FG_ERR_ARG, "fg_step_fused: pos/vel/reward/done/step must be non-null%s");
+    if (!random_actions && !b->act) return fail(FG_ERR_ARG, "fg_step_fused: act is null and random_actions == 0%s");
+    if (n_steps < 1) return fail(FG_ERR_ARG, "fg_step_fused: n_steps must be >= 1%s");
+    if (n_steps > 1 && !random_actions)
+        return fail(FG_ERR_ARG, "fg_step_fused: n_steps > 1 needs random_actions (one action set per call)%s");
+    if (random_actions && !p->silent)
+        return fail(FG_ERR_ARG, "fg_step_fused: random_actions supports silent agents only%s");
+    if (scenario == FG_SCENARIO_HD && (!b->ideal_shape || !b->ideal_vel))
+        return fail(FG_ERR_ARG, "fg_step_fused(hd): ideal_shape/ideal_vel must be non-null%s");
+    if (scenario == FG_SCENARIO_BASIC && !b->landmarks)
+        return fail(FG_ERR_ARG, "fg_step_fused(basic): landmarks must be non-null%s");
+    a.n_steps = n_steps; a.random_actions = random_actions; a.auto_reset = auto_reset;
+    return launch<T, true, true>(a, scenario, p, stream);
+}
+
+template <typename T>
+int reset_impl(const fg_params* p, const fg_buffers* b, int scenario, int E, int N, int L, const uint8_t* mask,
+               uint64_t seed, uint32_t tick, uint32_t env_offset, void* stream) {
+    fg::KArgs<T> a;
+    int rc = fill_args<T>(a, p, b, scenario, E, N, L, seed, tick, env_offset);
+    if (rc) return rc;
+    if (!b->pos || !b->vel) return fail(FG_ERR_ARG, "fg_reset: pos/vel must be non-null%s");
+    if (scenario == FG_SCENARIO_HD && (!b->ideal_shape || !b->ideal_vel))
+        return fail(FG_ERR_ARG, "fg_reset(hd): ideal_shape/ideal_vel must be non-null%s");
+    if (scenario == FG_SCENARIO_BASIC && !b->landmarks)
+        return fail(FG_ERR_ARG, "fg_reset(basic): landmarks must be non-null%s");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int grid = (E + 127) / 128;
+    if (scenario == FG_SCENARIO_HD) fg::k_reset<T, fg::kScnHD><<<grid, 128, 0, st>>>(a, mask);
+    else                            fg::k_reset<T, fg::kScnBasic><<<grid, 128, 0, st>>>(a, mask);
+    cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess) return fail(FG_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(err));
+    return FG_OK;
+}
+
+template <typename T>
+int random_actions_impl(void* act, int E, int N, uint64_t seed, uint32_t tick, uint32_t env_offset, void* stream) {
+    if (!act || E < 1 || N < 1) return fail(FG_ERR_ARG, "fg_random_actions: bad argument%s");
+    const size_t n = (size_t)E * N;
+    const int grid = (int)((n + 255) / 256);
+    fg::k_random_actions<T><<<grid, 256, 0, (cudaStream_t)stream>>>((typename fg::Ops<T>::R2*)act, E, N, seed, tick,
+                                                                   env_offset);
+    cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess) return fail(FG_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(err));
+    return FG_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int fg_abi_version(void) { return FG_ABI_VERSION; }
+
+const char* fg_last_error(void) { return g_err; }
+
+int fg_device_info(int* sm_count, int* cc_major, int* cc_minor) {
+    int dev = 0;
+    cudaError_t err = cudaGetDevice(&dev);
+    cudaDeviceProp prop;
+    if (err == cudaSuccess) err = cudaGetDeviceProperties(&prop, dev);
+    if (err != cudaSuccess) return fail(FG_ERR_CUDA, "fg_device_info: %s", cudaGetErrorString(err));
+    if (sm_count) *sm_count = prop.multiProcessorCount;
+    if (cc_major) *cc_major = prop.major;
+    if (cc_minor) *cc_minor = prop.minor;
+    return FG_OK;
+}
+
+int fg_launch_geometry(int N, int* envs_per_cta, int* threads_per_cta) {
+    if (N < 1 || N > FG_MAX_AGENTS) return fail(FG_ERR_ARG, "N must be in [1, FG_MAX_AGENTS=256]%s");
+    if (envs_per_cta) *envs_per_cta = fg::kBlock / N;
+    if (threads_per_cta) *threads_per_cta = fg::kBlock;
+    return FG_OK;
+}
+
+int fg_world_step(const fg_params* p, const fg_buffers* b, int E, int N, uint64_t seed, uint32_t tick,
+                  uint32_t env_offset, void* stream) {
+    return world_step_impl<float>(p, b, E, N, seed, tick, env_offset, stream);
+}
+int fg_world_step_f64(const fg_params* p, const fg_buffers* b, int E, int N, uint64_t seed, uint32_t tick,
+                      uint32_t env_offset, void* stream) {
+    return world_step_impl<double>(p, b, E, N, seed, tick, env_offset, stream);
+}
+
+int fg_obs_reward(const fg_params* p, const fg_buffers* b, int scenario, int E, int N, int L, void* stream) {
+    return obs_reward_impl<float>(p, b, scenario, E, N, L, stream);
+}
+int fg_obs_reward_f64(const fg_params* p, const fg_buffers* b, int scenario, int E, int N, int L, void* stream) {
+    return obs_reward_impl<double>(p, b, scenario, E, N, L, stream);
+}
+
+int fg_step_fused(const fg_params* p, const fg_buffers* b, int scenario, int E, int N, int L, int n_steps,
+                  int random_actions, int auto_reset, uint64_t seed, uint32_t tick, uint32_t env_offset,
+                  void* stream) {
+    return step_fused_impl<float>(p, b, scenario, E, N, L, n_steps, random_actions, auto_reset, seed, tick,
+                                  env_offset, stream);
+}
+int fg_step_fused_f64(const fg_params* p, const fg_buffers* b, int scenario, int E, int N, int L, int n_steps,
+                      int random_actions, int auto_reset, uint64_t seed, uint32_t tick, uint32_t env_offset,
+                      void* stream) {
+    return step_fused_impl<double>(p, b, scenario, E, N, L, n_steps, random_actions, auto_reset, seed, tick,
+                                   env_offset, stream);
+}
+
+int fg_reset(const fg_params* p, const fg_buffers* b, int scenario, int E, int N, int L, const uint8_t* mask,
+             uint64_t seed, uint32_t tick, uint32_t env_offset, void* stream) {
+    return reset_impl<float>(p, b, scenario, E, N, L, mask, seed, tick, env_offset, stream);
+}
+int fg_reset_f64(const fg_params* p, const fg_buffers* b, int scenario, int E, int N, int L, const uint8_t* mask,
+                 uint64_t seed, uint32_t tick, uint32_t env_offset, void* stream) {
+    return reset_impl<double>(p, b, scenario, E, N, L, mask, seed, tick, env_offset, stream);
+}
+
+int fg_random_actions(void* act, int E, int N, uint64_t seed, uint32_t tick, uint32_t env_offset, void* stream) {
+    return random_actions_impl<float>(act, E, N, seed, tick, env_offset, stream);
+}
+int fg_random_actions_f64(void* act, int E, int N, uint64_t seed, uint32_t tick, uint32_t env_offset,
+                          void* stream) {
+    return random_actions_impl<double>(act, E, N, seed, tick, env_offset, stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,561 @@
+// fg_kernels.cuh -- the fused MPE step kernel (sm_100a) and its small companions.
+//
+// One CTA owns a TILE of EPC = floor(256 / N) consecutive envs; thread t <-> (local env t / N,
+// agent t % N), so N = 3, 9, 27, 81, 243 fill 255, 252, 243, 243, 243 of the 256 lanes.  A tile's
+// state (pos, vel, ideal shape / landmarks, comm) is staged in shared memory with coalesced
+// 8-byte (fp32) / 16-byte (fp64) loads; the O(N^2) pair loops read the other agents of the same
+// env from shared memory (same address across the lanes of an env -> broadcast, no conflicts).
+// Phases of one env step (reference file:line for each in the code):
+//   load -> [sync] -> action force + pairwise contact force (OLD positions) + integrate
+//        -> [sync] -> centroid / collision count / Hausdorff partials (NEW positions)
+//        -> [sync] -> rewards, done, episode statistics -> [auto-reset, sync]
+//        -> observation rows emitted as ONE contiguous, fully coalesced span per tile.
+// The observation tensor is 24 N^2 of the 24 N^2 + 53 N + 16 algorithmic bytes per env-step, so
+// the kernel is an HBM-store-bound obs writer with the physics riding along.
+#pragma once
+#include "fg_math.cuh"
+
+namespace fg {
+
+constexpr int kBlock = 256;
+constexpr int kMaxWalls = 8;
+constexpr int kScnHD = 0;
+constexpr int kScnBasic = 1;
+
+template <typename T> struct WallT {
+    int orient, hard;
+    T axis_pos, end0, end1, width;
+};
+
+template <typename T> struct KArgs {
+    typedef typename Ops<T>::R2 R2;
+    // buffers (see include/formation_gym_b200.h fg_buffers)
+    R2* pos; R2* vel; const R2* act; R2* comm;
+    R2* shape; R2* ivel; R2* lm;
+    int32_t* step;
+    R2* obs; T* reward; T* indiv; uint8_t* done;
+    T* ep_return; int32_t* ep_coll; double* stats;
+    const T* a_mass; const T* a_size; const T* a_accel; const T* a_vmax;
+    // sizes
+    int E, N, L, EPC, IPR;           // IPR = R2 items per observation row (hd 3N; basic 2+L+2(N-1))
+    uint32_t magic_n, magic_ipr;     // fastdiv magics for N and IPR
+    int act_r2;                      // R2 elements per agent in act (1 silent, 2 with comm action)
+    // params in T
+    T dt, keep, cforce, margin, size, mass, vmax, u_noise, c_noise;
+    T sens0;                         // environment.py:218 sensitivity (5.0)
+    T accel;                         // scalar Entity.accel, used iff has_accel
+    T sens, gain;                    // effective scalars: sens = has_accel ? accel : sens0; gain = has_accel ? mass*accel : mass
+    T cut2;                          // (2*size + kcut*margin)^2 : contact early-out (uniform sizes)
+    T kcut;
+    T rthr, rthr2_hi;                // reward collision threshold and its guarded square
+    int has_accel, has_vmax, collide, silent, world_length, n_walls, prescaled;
+    int n_steps, random_actions, auto_reset;
+    uint64_t seed; uint32_t tick; uint32_t env_offset;
+    WallT<T> walls[kMaxWalls];
+};
+
+// ------------------------------------------------------------------------------------------------
+// get_entity_collision_force (core.py:289-322), both entities movable colliders (agents).
+// (dx,dy) = p_a - p_b with a < b in entity order.  Returns `force` (core.py:312).
+template <typename T>
+__device__ __forceinline__ void contact_force(T dx, T dy, T dmin, T k, T cf, T* fx, T* fy) {
+    typedef Ops<T> O;
+    T dist = O::norm2(dx, dy);                                   // core.py:305
+    T tt = O::div(-O::sub(dist, dmin), k);                       // -(dist - dist_min)/k
+    // np.logaddexp(0, tt): stable softplus (core.py:310)
+    T sp = (tt > (T)0) ? O::add(tt, O::log1p_(O::exp_(-tt))) : O::log1p_(O::exp_(tt));
+    T pen = O::mul(sp, k);
+    *fx = O::mul(O::div(O::mul(cf, dx), dist), pen);             // contact_force*delta/dist*pen
+    *fy = O::mul(O::div(O::mul(cf, dy), dist), pen);             // dist == 0 -> NaN, as reference
+}
+
+// get_wall_collision_force (core.py:325-362) on one entity
+template <typename T>
+__device__ __forceinline__ void wall_force(const WallT<T>& w, T px, T py, T size, T k, T cf, T* fx, T* fy) {
+    typedef Ops<T> O;
+    T prll = w.orient == 0 ? px : py;
+    T perp = w.orient == 0 ? py : px;
+    *fx = (T)0; *fy = (T)0;
+    if (prll < O::sub(w.end0, size) || prll > O::add(w.end1, size)) return;    // :335-337
+    T theta = (T)0, dmin;
+    if (prll < w.end0 || prll > w.end1) {                                       // :338-346
+        T past = prll < w.end0 ? O::sub(prll, w.end0) : O::sub(prll, w.end1);
+        theta = O::asin_(O::div(past, size));
+        T s, c; O::sincos_(theta, &s, &c);
+        dmin = O::add(O::mul(c, size), O::mul((T)0.5, w.width));
+    } else {
+        dmin = O::add(size, O::mul((T)0.5, w.width));                           // :350
+    }
+    T delta = O::sub(perp, w.axis_pos);                                         // :353
+    T dist = fabs(delta);
+    T tt = O::div(-O::sub(dist, dmin), k);
+    T sp = (tt > (T)0) ? O::add(tt, O::log1p_(O::exp_(-tt))) : O::log1p_(O::exp_(tt));
+    T pen = O::mul(sp, k);                                                      // :357
+    T fmag = O::mul(O::div(O::mul(cf, delta), dist), pen);                      // :358
+    T s, c; O::sincos_(theta, &s, &c);
+    T fperp = O::mul(c, fmag), fprll = O::mul(s, fabs(fmag));                   // :360-361
+    if (w.orient == 0) { *fx = fprll; *fy = fperp; } else { *fx = fperp; *fy = fprll; }
+}
+
+// ------------------------------------------------------------------------------------------------
+// The fused kernel.  PHYS: run World.step.  OBSREW: run observation/reward/done.  HET: per-agent
+// mass/size/accel/max_speed arrays (otherwise the scalar fast path).
+template <typename T, int SCN, bool PHYS, bool OBSREW, bool HET>
+__global__ void __launch_bounds__(kBlock) k_step(const __grid_constant__ KArgs<T> a) {
+    typedef Ops<T> O;
+    typedef typename O::R2 R2;
+    typedef typename O::Bits Bits;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+
+    const int N = a.N, EPC = a.EPC, L = a.L;
+    const int nA = EPC * N;
+    const int nS = (SCN == kScnHD) ? nA : EPC * L;
+    R2* s_old = reinterpret_cast<R2*>(smem_raw);      // positions the contact force reads
+    R2* s_new = s_old + nA;                           // positions after integration
+    R2* s_v = s_new + nA;                             // velocities after integration
+    R2* s_s = s_v + nA;                               // hd: centred ideal shape; basic: landmarks
+    R2* s_c = s_s + nS;                               // comm state
+    R2* s_iv = s_c + nA;                              // hd: ideal velocity per env
+    Bits* s_rowmax = reinterpret_cast<Bits*>(s_iv + EPC);
+    Bits* s_colmax = s_rowmax + EPC;
+    T* s_lmin = reinterpret_cast<T*>(s_colmax + EPC);         // basic: min_a |p_a - l_k| [EPC*L]
+    T* s_het = s_lmin + ((SCN == kScnBasic) ? EPC * L : 0);   // HET: mass,size,sens,gain,vmax [5N]
+    int* s_col = reinterpret_cast<int*>(s_het + (HET ? 5 * N : 0));
+    int* s_dn = s_col + EPC;                                  // episode-end flag per local env
+
+    const int t = threadIdx.x;
+    const int tile0 = blockIdx.x * EPC;                       // first env of this tile
+    const int le = (int)fastdiv((uint32_t)t, a.magic_n);
+    const int i = t - le * N;
+    const int e = tile0 + le;
+    const bool active = (t < nA) && (e < a.E);
+    const int nvalid = min(EPC, a.E - tile0);                 // envs of this tile that exist
+    const size_t g = (size_t)e * N + i;                       // global agent index
+    const uint32_t ge = a.env_offset + (uint32_t)e;           // global env id (RNG counter)
+
+    if (HET) {
+        for (int q = t; q < N; q += kBlock) {
+            T m = a.a_mass ? a.a_mass[q] : a.mass;
+            T acc = a.a_accel ? a.a_accel[q] : (T)-1;
+            s_het[q] = m;
+            s_het[N + q] = a.a_size ? a.a_size[q] : a.size;
+            // environment.py:218-221 (sensitivity := accel) and core.py:235-236 (gain mass*accel)
+            if (!a.a_accel && a.has_accel) acc = a.accel;
+            s_het[2 * N + q] = a.prescaled ? (T)1 : (acc >= (T)0 ? acc : a.sens0);
+            s_het[3 * N + q] = acc >= (T)0 ? O::mul(m, acc) : m;
+            s_het[4 * N + q] = a.a_vmax ? a.a_vmax[q] : (a.has_vmax ? a.vmax : (T)-1);
+        }
+    }
+
+    // ---- load the tile (coalesced: consecutive threads <-> consecutive agents of consecutive envs)
+    R2 p = O::make((T)0, (T)0), v = p, u = p, uc = p;
+    int stp = 0;
+    if (active) {
+        p = a.pos[g];
+        v = a.vel[g];
+        if (PHYS && !a.random_actions) {
+            u = a.act[g * a.act_r2];
+            if (a.act_r2 > 1) uc = a.act[g * a.act_r2 + 1];
+        }
+        if (PHYS) s_old[t] = p; else { s_new[t] = p; s_v[t] = v; }
+        if (OBSREW) {
+            if (SCN == kScnHD) s_s[t] = a.shape[g];
+            if (a.step) stp = a.step[e];
+            if (!PHYS) s_c[t] = a.comm ? a.comm[g] : O::make((T)0, (T)0);
+        }
+    }
+    if (OBSREW) {
+        if (SCN == kScnHD) {
+            if (active && i == 0) s_iv[le] = a.ivel[e];
+        } else {
+            for (int q = t; q < nvalid * L; q += kBlock) s_s[q] = a.lm[(size_t)tile0 * L + q];
+        }
+    }
+
+    for (int ts = 0; ts < a.n_steps; ++ts) {
+        if (OBSREW && t < EPC) { s_rowmax[t] = 0; s_colmax[t] = 0; s_col[t] = 0; }
+        __syncthreads();
+
+        // =============================== World.step (core.py:206-225) ===========================
+        if (PHYS) {
+            if (active) {
+                if (a.random_actions) {                                     // test.py:20
+                    U4 r = philox(a.seed, ge, (uint32_t)i, a.tick + (uint32_t)ts, kAction);
+                    u = O::make(uniform_pm1<T>(r.x), uniform_pm1<T>(r.y));
+                }
+                T m_i = HET ? s_het[i] : a.mass;
+                T size_i = HET ? s_het[N + i] : a.size;
+                T sens = HET ? s_het[2 * N + i] : a.sens;
+                T gain = HET ? s_het[3 * N + i] : a.gain;
+                // _set_action: u *= sensitivity (environment.py:216-221);
+                // apply_action_force: F = gain * u + noise (core.py:232-236)
+                T Fx = O::mul(gain, O::mul(u.x, sens));
+                T Fy = O::mul(gain, O::mul(u.y, sens));
+                if (a.u_noise > (T)0) {
+                    U4 r = philox(a.seed, ge, (uint32_t)i, a.tick + (uint32_t)ts, kUNoise);
+                    T n0, n1; normal_pair<T>(r.x, r.y, &n0, &n1);
+                    Fx = O::add(Fx, O::mul(n0, a.u_noise));
+                    Fy = O::add(Fy, O::mul(n1, a.u_noise));
+                }
+                // apply_environment_force (core.py:240-254): pairs a<b; contributions reach agent
+                // i in ascending order of the other index, exactly the reference's order.
+                if (a.collide) {
+                    const R2* envp = s_old + le * N;
+                    for (int j = 0; j < N; ++j) {
+                        if (j == i) continue;
+                        R2 q = envp[j];
+                        T dx = (j < i) ? O::sub(q.x, p.x) : O::sub(p.x, q.x);   // delta = p_a - p_b, a<b
+                        T dy = (j < i) ? O::sub(q.y, p.y) : O::sub(p.y, q.y);
+                        T d2 = dx * dx + dy * dy;
+                        T dmin, cut2;
+                        if (HET) {
+                            dmin = O::add((j < i) ? s_het[N + j] : size_i, (j < i) ? size_i : s_het[N + j]);
+                            T c = dmin + a.kcut * a.margin; cut2 = c * c;
+                        } else {
+                            dmin = O::add(a.size, a.size);                       // core.py:307
+                            cut2 = a.cut2;
+                        }
+                        // Far pairs: softplus(-(d-dmin)/k) < exp(-kcut) -- below the rounding of F
+                        // (DESIGN.md "contact cut-off").  !(>=) keeps NaN positions propagating.
+                        if (!(d2 >= cut2)) {
+                            T fx, fy;
+                            contact_force<T>(dx, dy, dmin, a.margin, a.cforce, &fx, &fy);
+                            if (HET) {
+                                T m_j = s_het[j];
+                                if (j < i) {       // i is entity b: force_b = -(1/ratio)*force, ratio = m_b/m_a
+                                    T c = -O::div((T)1, O::div(m_i, m_j));
+                                    Fx = O::add(O::mul(c, fx), Fx); Fy = O::add(O::mul(c, fy), Fy);
+                                } else {           // i is entity a: force_a = ratio*force
+                                    T r = O::div(m_j, m_i);
+                                    Fx = O::add(O::mul(r, fx), Fx); Fy = O::add(O::mul(r, fy), Fy);
+                                }
+                            } else {               // equal masses: ratio == 1 exactly
+                                if (j < i) { Fx = O::add(-fx, Fx); Fy = O::add(-fy, Fy); }
+                                else       { Fx = O::add(fx, Fx);  Fy = O::add(fy, Fy); }
+                            }
+                        }
+                    }
+                }
+                for (int w = 0; w < a.n_walls; ++w) {                          // core.py:255-261
+                    T fx, fy;
+                    wall_force<T>(a.walls[w], p.x, p.y, size_i, a.margin, a.cforce, &fx, &fy);
+                    Fx = O::add(Fx, fx); Fy = O::add(Fy, fy);
+                }
+                // integrate_state (core.py:264-277)
+                v.x = O::mul(v.x, a.keep); v.y = O::mul(v.y, a.keep);            // * (1 - damping)
+                v.x = O::add(v.x, O::mul(O::div(Fx, m_i), a.dt));
+                v.y = O::add(v.y, O::mul(O::div(Fy, m_i), a.dt));
+                T vmax = HET ? s_het[4 * N + i] : (a.has_vmax ? a.vmax : (T)-1);
+                if (vmax >= (T)0) {
+                    T sp = O::sqrt_(O::sq2(v.x, v.y));
+                    if (sp > vmax) {
+                        v.x = O::mul(O::div(v.x, sp), vmax);
+                        v.y = O::mul(O::div(v.y, sp), vmax);
+                    }
+                }
+                p.x = O::add(p.x, O::mul(v.x, a.dt));
+                p.y = O::add(p.y, O::mul(v.y, a.dt));
+                // update_agent_state (core.py:279-286)
+                R2 c = O::make((T)0, (T)0);
+                if (!a.silent) {
+                    c = uc;
+                    if (a.c_noise > (T)0) {
+                        U4 r = philox(a.seed, ge, (uint32_t)i, a.tick + (uint32_t)ts, kCNoise);
+                        T n0, n1; normal_pair<T>(r.x, r.y, &n0, &n1);
+                        c.x = O::add(c.x, O::mul(n0, a.c_noise));
+                        c.y = O::add(c.y, O::mul(n1, a.c_noise));
+                    }
+                }
+                s_new[t] = p; s_v[t] = v; s_c[t] = c;
+                if (!OBSREW || ts == a.n_steps - 1) {
+                    a.pos[g] = p; a.vel[g] = v;
+                    if (a.comm) a.comm[g] = c;
+                }
+            }
+            if (!OBSREW) return;
+            __syncthreads();
+        }
+
+        // ================= Scenario.reward partials on the NEW state (Q16) ======================
+        int col = 0;
+        T mpx = 0, mpy = 0, mvx = 0, mvy = 0;
+        if (active) {
+            const R2* envp = s_new + le * N;
+            const R2* envv = s_v + le * N;
+            T size_i = HET ? s_het[N + i] : a.size;
+            T spx = 0, spy = 0, svx = 0, svy = 0;
+            for (int j = 0; j < N; ++j) {
+                R2 q = envp[j];
+                if (SCN == kScnHD) {
+                    R2 w = envv[j];
+                    spx = O::add(spx, q.x); spy = O::add(spy, q.y);             // np.mean(.., 0): row order
+                    svx = O::add(svx, w.x); svy = O::add(svy, w.y);
+                }
+                // is_collision: hd excludes self, threshold (s1+s2)/2 (formation_hd_env.py:73,119-121);
+                // basic includes self, threshold s1+s2 (basic_formation_env.py:48-51,89-91)
+                if (a.collide && (SCN == kScnBasic || j != i)) {
+                    T dx = O::sub(q.x, p.x), dy = O::sub(q.y, p.y);
+                    T d2 = dx * dx + dy * dy;
+                    T thr, thr2;
+                    if (HET) {
+                        thr = O::add(s_het[N + j], size_i);
+                        if (SCN == kScnHD) thr = O::div(thr, (T)2);
+                        thr2 = thr * thr * (T)1.0001;
+                    } else { thr = a.rthr; thr2 = a.rthr2_hi; }
+                    if (d2 < thr2) { if (O::norm2(dx, dy) < thr) ++col; }
+                }
+            }
+            if (SCN == kScnHD) {
+                mpx = O::div(spx, (T)N); mpy = O::div(spy, (T)N);
+                mvx = O::div(svx, (T)N); mvy = O::div(svy, (T)N);
+                // reward part 1 (formation_hd_env.py:64-66): symmetric Hausdorff distance between the
+                // centred agent shape C and the ideal shape S.  Thread i owns row i (min_j |C_i-S_j|^2)
+                // and column i (min_j |C_j-S_i|^2); env-wide max via shared atomicMax on the bits.
+                const R2* envs = s_s + le * N;
+                R2 Si = envs[i];
+                T cix = O::sub(p.x, mpx), ciy = O::sub(p.y, mpy);
+                T rowmin = (T)INFINITY, colmin = (T)INFINITY;
+                bool nan_seen = false;
+                for (int j = 0; j < N; ++j) {
+                    R2 q = envp[j]; R2 Sj = envs[j];
+                    T cjx = O::sub(q.x, mpx), cjy = O::sub(q.y, mpy);
+                    T d_row = O::sq2(O::sub(cix, Sj.x), O::sub(ciy, Sj.y));
+                    T d_col = O::sq2(O::sub(cjx, Si.x), O::sub(cjy, Si.y));
+                    nan_seen |= (d_row != d_row) | (d_col != d_col);
+                    rowmin = fmin(rowmin, d_row);
+                    colmin = fmin(colmin, d_col);
+                }
+                if (nan_seen) { rowmin = O::from_bits(~(Bits)0 >> 1); colmin = rowmin; }  // +NaN
+                atomicMax(&s_rowmax[le], O::bits(rowmin));       // d2 >= 0: bit order == value order
+                atomicMax(&s_colmax[le], O::bits(colmin));
+            }
+            if (col) atomicAdd(&s_col[le], col);
+        }
+        if (SCN == kScnBasic) {
+            // reward part 1 (basic_formation_env.py:45-47): min over agents of |p_a - l_k| per landmark
+            for (int q = t; q < nvalid * L; q += kBlock) {
+                int qe = q / L;
+                R2 l = s_s[q];
+                const R2* envp = s_new + qe * N;
+                T m = (T)INFINITY;
+                bool nan_seen = false;
+                for (int j = 0; j < N; ++j) {
+                    R2 pj = envp[j];
+                    T d = O::norm2(O::sub(pj.x, l.x), O::sub(pj.y, l.y));
+                    nan_seen |= (d != d);
+                    m = fmin(m, d);
+                }
+                s_lmin[q] = nan_seen ? O::from_bits(~(Bits)0 >> 1) : m;
+            }
+        }
+        __syncthreads();
+
+        // ============ rewards, done, statistics (environment.py:126-138,172-177) ================
+        stp += 1;                                                             // environment.py:114
+        const bool dn = active && a.step && (stp >= a.world_length);
+        if (active && i == 0) s_dn[le] = dn ? 1 : 0;
+        if (active) {
+            T base;
+            if (SCN == kScnHD) {
+                Bits mx = max(s_rowmax[le], s_colmax[le]);
+                T form = -O::sqrt_(O::from_bits(mx));                           // -max(dH, dH')
+                T velr = O::norm2(O::sub(s_iv[le].x, mvx), O::sub(s_iv[le].y, mvy));   // :68-69
+                base = O::sub(form, velr);
+            } else {
+                base = (T)0;
+                for (int k = 0; k < L; ++k) base = O::sub(base, s_lmin[le * L + k]);
+            }
+            T r = base;
+            for (int c = 0; c < col; ++c) r = O::sub(r, (T)1);                 // rew -= 1 per collision
+            const int coltot = s_col[le];
+            // shared reward = sum_i r_i (environment.py:136): N*base - total collisions, in fp64
+            const double R = (double)N * (double)base - (double)coltot;
+            a.reward[g] = (T)R;
+            if (a.indiv) a.indiv[g] = r;
+            if (a.done) a.done[g] = (uint8_t)(a.step ? (stp >= a.world_length) : 0);
+            if (i == 0 && a.step) {
+                T ret = (T)R;
+                if (a.ep_return) { ret = a.ep_return[e] + (T)R; a.ep_return[e] = (dn && a.auto_reset) ? (T)0 : ret; }
+                int ec = coltot;
+                if (a.ep_coll) { ec += a.ep_coll[e]; a.ep_coll[e] = (dn && a.auto_reset) ? 0 : ec; }
+                if (dn && a.stats) {
+                    atomicAdd(&a.stats[0], 1.0);
+                    atomicAdd(&a.stats[1], (double)ret);
+                    atomicAdd(&a.stats[2], (double)ret * (double)ret);
+                    atomicAdd(&a.stats[3], (double)ec);
+                }
+            }
+        }
+
+        // ======== VecEnv auto-reset (env_wrappers.py:14-18; reset_world formation_hd_env.py:77-95)
+        if (PHYS && a.auto_reset) {
+            if (__syncthreads_or(dn ? 1 : 0)) {
+                const uint32_t tk = a.tick + (uint32_t)ts;
+                R2 lraw = O::make((T)0, (T)0);
+                if (dn) {
+                    U4 r = philox(a.seed, ge, (uint32_t)i, tk, kResetAgent);
+                    p = O::make(uniform_pm1<T>(r.x), uniform_pm1<T>(r.y));
+                    v = O::make((T)0, (T)0);
+                    s_new[t] = p; s_v[t] = v; s_c[t] = v;
+                    if (SCN == kScnHD) {
+                        U4 q = philox(a.seed, ge, (uint32_t)i, tk, kResetLandmark);
+                        lraw = O::make(uniform_pm1<T>(q.x), uniform_pm1<T>(q.y));
+                        s_old[t] = lraw;                      // scratch: s_old is dead after the physics
+                        if (a.lm) a.lm[g] = lraw;
+                        if (i == 0) {
+                            U4 w = philox(a.seed, ge, 0u, tk, kResetIdealVel);
+                            R2 iv = O::make(uniform_pm1<T>(w.x), uniform_pm1<T>(w.y));
+                            s_iv[le] = iv; a.ivel[e] = iv;
+                        }
+                    }
+                    stp = 0;
+                }
+                if (SCN == kScnBasic) {
+                    for (int q = t; q < nvalid * L; q += kBlock) {
+                        int qe = q / L, k = q - qe * L;
+                        if (s_dn[qe]) {
+                            U4 r = philox(a.seed, a.env_offset + (uint32_t)(tile0 + qe), (uint32_t)k, tk, kResetLandmark);
+                            R2 l = O::make(uniform_pm1<T>(r.x), uniform_pm1<T>(r.y));
+                            s_s[q] = l; a.lm[(size_t)tile0 * L + q] = l;
+                        }
+                    }
+                }
+                __syncthreads();
+                if (dn && SCN == kScnHD) {
+                    const R2* raw = s_old + le * N;
+                    T sx = 0, sy = 0;
+                    for (int j = 0; j < N; ++j) { sx = O::add(sx, raw[j].x); sy = O::add(sy, raw[j].y); }
+                    R2 S = O::make(O::sub(lraw.x, O::div(sx, (T)N)), O::sub(lraw.y, O::div(sy, (T)N)));  // :93
+                    s_s[t] = S; a.shape[g] = S;
+                }
+                if (dn && ts == a.n_steps - 1) { a.pos[g] = p; a.vel[g] = v; if (a.comm) a.comm[g] = v; }
+                __syncthreads();
+            }
+        }
+        if (active && i == 0 && a.step) a.step[e] = stp;
+
+        // hd observation side effect (formation_hd_env.py:40-44): every landmark moves by
+        // mean(agent pos) - mean(landmark pos).  Visualisation only; skipped when lm == NULL.
+        if (SCN == kScnHD && a.lm) {
+            R2 l = O::make((T)0, (T)0);
+            if (active) { l = a.lm[g]; s_old[t] = l; }       // s_old is scratch after the physics
+            __syncthreads();
+            if (active) {
+                const R2* envp = s_new + le * N;
+                const R2* envl = s_old + le * N;
+                T sx = 0, sy = 0, lx = 0, ly = 0;
+                for (int j = 0; j < N; ++j) {
+                    sx = O::add(sx, envp[j].x); sy = O::add(sy, envp[j].y);
+                    lx = O::add(lx, envl[j].x); ly = O::add(ly, envl[j].y);
+                }
+                T ddx = O::sub(O::div(sx, (T)N), O::div(lx, (T)N));
+                T ddy = O::sub(O::div(sy, (T)N), O::div(ly, (T)N));
+                a.lm[g] = O::make(O::add(l.x, ddx), O::add(l.y, ddy));
+            }
+            __syncthreads();
+        }
+
+        // ================= observation rows (formation_hd_env.py:52-59 / basic :29-41) ==========
+        // The tile's rows form ONE contiguous span of nvalid*N*IPR R2 items in HBM; consecutive
+        // threads write consecutive items (8 B fp32 / 16 B fp64 each): fully coalesced stores.
+        if (a.obs) {
+            const int IPR = a.IPR;
+            const uint32_t total = (uint32_t)(nvalid * N * IPR);
+            R2* out = a.obs + (size_t)tile0 * N * IPR;
+            for (uint32_t q = t; q < total; q += kBlock) {
+                const uint32_t row = fastdiv(q, a.magic_ipr);          // (local env, agent) row
+                const int k = (int)(q - row * IPR);                    // item within the row
+                const int rle = (int)fastdiv(row, a.magic_n);
+                const int ri = (int)row - rle * N;
+                R2 val;
+                if (SCN == kScnHD) {
+                    if (k == 0) val = s_v[row];                                        // p_vel
+                    else if (k < N) {                                                  // other_pos
+                        int j = k - 1; j += (j >= ri);
+                        R2 pj = s_new[rle * N + j], pi = s_new[row];
+                        val = O::make(O::sub(pj.x, pi.x), O::sub(pj.y, pi.y));
+                    } else if (k < 2 * N - 1) {                                        // comm
+                        int j = k - N; j += (j >= ri);
+                        val = s_c[rle * N + j];
+                    } else if (k < 3 * N - 1) val = s_s[rle * N + (k - (2 * N - 1))];  // ideal_shape
+                    else val = s_iv[rle];                                              // ideal_vel
+                } else {
+                    if (k == 0) val = s_v[row];                                        // p_vel
+                    else if (k == 1) val = s_new[row];                                 // p_pos
+                    else if (k < 2 + L) {                                              // landmarks - p
+                        R2 l = s_s[rle * L + (k - 2)], pi = s_new[row];
+                        val = O::make(O::sub(l.x, pi.x), O::sub(l.y, pi.y));
+                    } else if (k < 2 + L + (N - 1)) {                                  // other_pos
+                        int j = k - (2 + L); j += (j >= ri);
+                        R2 pj = s_new[rle * N + j], pi = s_new[row];
+                        val = O::make(O::sub(pj.x, pi.x), O::sub(pj.y, pi.y));
+                    } else {                                                           // comm
+                        int j = k - (2 + L + (N - 1)); j += (j >= ri);
+                        val = s_c[rle * N + j];
+                    }
+                }
+                out[q] = val;
+            }
+        }
+
+        if (!PHYS) break;
+        // next step of an in-kernel rollout: the new positions become the old ones
+        R2* tmp = s_old; s_old = s_new; s_new = tmp;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Scenario.reset_world + env.current_step = 0 for masked envs; one thread per env (reset of a whole
+// batch is off the hot loop; in-episode resets happen inside k_step).  Same Philox counters and the
+// same arithmetic as the in-kernel auto-reset, so both produce bit-identical states.
+template <typename T, int SCN>
+__global__ void k_reset(const __grid_constant__ KArgs<T> a, const uint8_t* __restrict__ mask) {
+    typedef Ops<T> O;
+    typedef typename O::R2 R2;
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= a.E) return;
+    if (mask && !mask[e]) return;
+    const int N = a.N, L = a.L;
+    const uint32_t ge = a.env_offset + (uint32_t)e;
+    const R2 zero = O::make((T)0, (T)0);
+    for (int i = 0; i < N; ++i) {
+        U4 r = philox(a.seed, ge, (uint32_t)i, a.tick, kResetAgent);
+        size_t g = (size_t)e * N + i;
+        a.pos[g] = O::make(uniform_pm1<T>(r.x), uniform_pm1<T>(r.y));
+        a.vel[g] = zero;
+        if (a.comm) a.comm[g] = zero;
+    }
+    T sx = 0, sy = 0;
+    for (int k = 0; k < L; ++k) {
+        U4 r = philox(a.seed, ge, (uint32_t)k, a.tick, kResetLandmark);
+        R2 l = O::make(uniform_pm1<T>(r.x), uniform_pm1<T>(r.y));
+        sx = O::add(sx, l.x); sy = O::add(sy, l.y);
+        if (a.lm) a.lm[(size_t)e * L + k] = l;
+    }
+    if (SCN == kScnHD) {
+        T mx = O::div(sx, (T)N), my = O::div(sy, (T)N);
+        for (int k = 0; k < N; ++k) {
+            U4 r = philox(a.seed, ge, (uint32_t)k, a.tick, kResetLandmark);
+            a.shape[(size_t)e * N + k] =
+                O::make(O::sub(uniform_pm1<T>(r.x), mx), O::sub(uniform_pm1<T>(r.y), my));
+        }
+        U4 w = philox(a.seed, ge, 0u, a.tick, kResetIdealVel);
+        a.ivel[e] = O::make(uniform_pm1<T>(w.x), uniform_pm1<T>(w.y));
+    }
+    if (a.step) a.step[e] = 0;
+    if (a.ep_return) a.ep_return[e] = (T)0;
+    if (a.ep_coll) a.ep_coll[e] = 0;
+}
+
+// Random policy act ~ U(-1,1) (test.py:20); same counters as the in-kernel rollout.
+template <typename T>
+__global__ void k_random_actions(typename Ops<T>::R2* __restrict__ act, int E, int N, uint64_t seed,
+                                 uint32_t tick, uint32_t env_offset) {
+    const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= (size_t)E * N) return;
+    const uint32_t e = (uint32_t)(g / N), i = (uint32_t)(g - (size_t)e * N);
+    U4 r = philox(seed, env_offset + e, i, tick, kAction);
+    act[g] = Ops<T>::make(uniform_pm1<T>(r.x), uniform_pm1<T>(r.y));
+}
+
+}  // namespace fg

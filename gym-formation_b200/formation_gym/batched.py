@@ -1,0 +1,287 @@
+"""BatchedFormationEnv -- thousands to millions of gym-formation envs as contiguous
+``[envs, agents, dim]`` device tensors, stepped by ONE fused sm_100a kernel per step.
+
+Shape contract = the reference's VecEnv wrappers (train/maddpg-v2/utils/env_wrappers.py:14-18,
+68-72; train/maddpg-v4/runner.py:204): ``obs[E,N,D]  rews[E,N,1]  dones[E,N]`` and auto-reset
+when the episode ends (terminal reward/done returned together with the RESET observation).
+
+Semantics of one ``step(actions)`` = ``MultiAgentEnv.step`` of the reference
+(formation_gym/environment.py:113-142) for every env: ``_set_action`` (u = a * 5), ``World.step``
+(formation_gym/core.py:206-225), scenario ``observation`` / ``reward`` for every agent
+(formation_gym/envs/formation_hd_env.py:38-75, basic_formation_env.py:29-52), ``done`` and the
+shared-reward sum.  All of it runs in the CUDA library behind include/formation_gym_b200.h;
+this class only owns tensors and calls the C ABI.  There is no CPU path.
+"""
+import ctypes as C
+
+import torch
+
+from . import _native as nat
+
+SCENARIOS = {"formation_hd_env": nat.FG_SCENARIO_HD, "basic_formation_env": nat.FG_SCENARIO_BASIC}
+# scenario defaults: agent size, episode length (formation_hd_env.py:13,26; basic_formation_env.py:18,
+# core.py:113)
+_DEFAULTS = {"formation_hd_env": dict(agent_size=0.03, world_length=100),
+             "basic_formation_env": dict(agent_size=0.1, world_length=50)}
+
+
+def obs_dim(scenario, num_agents, num_landmarks=3):
+    """Observation length per agent (hd: 6N, formation_hd_env.py:59; basic: 4+2L+4(N-1))."""
+    if scenario == "formation_hd_env":
+        return 6 * num_agents
+    return 4 + 2 * num_landmarks + 4 * (num_agents - 1)
+
+
+class BatchedFormationEnv:
+    """E independent envs of N agents on one GPU.
+
+    Parameters mirror ``make_env(scenario, benchmark, num_agents, episode_length)`` plus the batch
+    size.  ``env_offset`` is the global index of env 0 (multi-GPU sharding: Philox streams are
+    keyed by global env id, so results do not depend on the number of ranks).
+    """
+
+    def __init__(self, scenario="formation_hd_env", num_envs=4096, num_agents=9, episode_length=None,
+                 num_landmarks=3, device="cuda", dtype=torch.float32, seed=0, auto_reset=True,
+                 env_offset=0, write_obs=True, track_landmarks=False, u_noise=None, c_noise=None,
+                 silent=True, collide=True, accel=None, max_speed=None, mass=1.0, agent_size=None,
+                 agent_mass=None, agent_sizes=None, agent_accel=None, agent_max_speed=None,
+                 walls=(), dt=0.1, damping=0.25, contact_force=1e2, contact_margin=1e-3,
+                 sensitivity=5.0):
+        if scenario not in SCENARIOS:
+            raise ValueError("unknown scenario %r (supported: %s)" % (scenario, sorted(SCENARIOS)))
+        if dtype not in (torch.float32, torch.float64):
+            raise ValueError("dtype must be torch.float32 or torch.float64")
+        self._lib = nat.load()                      # raises when the CUDA extension is missing
+        if not torch.cuda.is_available():
+            raise nat.NativeError("no CUDA device: formation_gym has no CPU fallback")
+        self.scenario = scenario
+        self.scn = SCENARIOS[scenario]
+        self.E, self.N = int(num_envs), int(num_agents)
+        self.L = self.N if self.scn == nat.FG_SCENARIO_HD else int(num_landmarks)
+        if self.scn == nat.FG_SCENARIO_HD and self.N < 3:
+            raise ValueError("formation_hd_env needs num_agents >= 3 (formation_hd_env.py:58)")
+        if not (1 <= self.N <= nat.FG_MAX_AGENTS):
+            raise ValueError("num_agents must be in [1, %d]" % nat.FG_MAX_AGENTS)
+        self.D = obs_dim(scenario, self.N, self.L)
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise nat.NativeError("device must be a CUDA device: there is no CPU fallback")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        self.dtype = dtype
+        self._sfx = "" if dtype == torch.float32 else "_f64"
+        d = _DEFAULTS[scenario]
+        self.world_length = int(episode_length if episode_length is not None else d["world_length"])
+        self.silent = bool(silent)
+        self.act_dim = 2 if self.silent else 4
+        self.auto_reset = bool(auto_reset)
+        self.seed_value = int(seed) & 0xFFFFFFFFFFFFFFFF
+        self.env_offset = int(env_offset)
+        self._tick = 0
+        self.params = nat.make_params(
+            dt=dt, damping=damping, contact_force=contact_force, contact_margin=contact_margin,
+            sensitivity=sensitivity, agent_size=d["agent_size"] if agent_size is None else agent_size,
+            mass=mass, accel=accel, max_speed=max_speed, u_noise=u_noise, c_noise=c_noise,
+            collide=collide, silent=silent, world_length=self.world_length, walls=walls)
+        kw = dict(device=self.device, dtype=dtype)
+        E, N, L = self.E, self.N, self.L
+        # optional per-agent arrays (kept alive here; the params struct stores raw pointers)
+        self._per_agent = {}
+        for name, field, arr in (("agent_mass", "agent_mass", agent_mass),
+                                 ("agent_sizes", "agent_size_arr", agent_sizes),
+                                 ("agent_accel", "agent_accel", agent_accel),
+                                 ("agent_max_speed", "agent_max_speed", agent_max_speed)):
+            if arr is not None:
+                vals = [(-1.0 if x is None else float(x)) for x in arr]
+                if len(vals) != N:
+                    raise ValueError("%s must have num_agents entries" % name)
+                t = torch.tensor(vals, **kw)
+                self._per_agent[name] = t
+                setattr(self.params, field, t.data_ptr())
+        # state
+        self.pos = torch.zeros(E, N, 2, **kw)
+        self.vel = torch.zeros(E, N, 2, **kw)
+        self.comm = torch.zeros(E, N, 2, **kw)
+        self.landmarks = torch.zeros(E, L, 2, **kw) if (self.scn == nat.FG_SCENARIO_BASIC or track_landmarks) else None
+        self.ideal_shape = torch.zeros(E, N, 2, **kw) if self.scn == nat.FG_SCENARIO_HD else None
+        self.ideal_vel = torch.zeros(E, 2, **kw) if self.scn == nat.FG_SCENARIO_HD else None
+        self.step_count = torch.zeros(E, dtype=torch.int32, device=self.device)
+        # outputs
+        self.obs = torch.zeros(E, N, self.D, **kw) if write_obs else None
+        self.reward = torch.zeros(E, N, 1, **kw)
+        self.indiv = torch.zeros(E, N, **kw)
+        self._done_u8 = torch.zeros(E, N, dtype=torch.uint8, device=self.device)
+        self.done = self._done_u8.view(torch.bool)
+        self.actions = torch.zeros(E, N, self.act_dim, **kw)     # scratch for the random policy
+        # episode statistics (device side; all-reduced by formation_gym.distributed)
+        self.ep_return = torch.zeros(E, **kw)
+        self.ep_collisions = torch.zeros(E, dtype=torch.int32, device=self.device)
+        self.stats = torch.zeros(4, dtype=torch.float64, device=self.device)
+        self.launches = 0                                        # kernels launched by this object
+        self._bufs = self._make_buffers()
+
+    # ------------------------------------------------------------------ plumbing
+    def _make_buffers(self, act=None, obs="default"):
+        b = nat.fg_buffers()
+        b.pos, b.vel = nat.ptr(self.pos), nat.ptr(self.vel)
+        b.act = nat.ptr(act) if act is not None else nat.ptr(self.actions)
+        b.comm = nat.ptr(self.comm)
+        b.ideal_shape, b.ideal_vel = nat.ptr(self.ideal_shape), nat.ptr(self.ideal_vel)
+        b.landmarks = nat.ptr(self.landmarks)
+        b.step = nat.ptr(self.step_count)
+        b.obs = nat.ptr(self.obs) if obs == "default" else nat.ptr(obs)
+        b.reward, b.indiv, b.done = nat.ptr(self.reward), nat.ptr(self.indiv), nat.ptr(self._done_u8)
+        b.ep_return, b.ep_collisions = nat.ptr(self.ep_return), nat.ptr(self.ep_collisions)
+        b.stats = nat.ptr(self.stats)
+        return b
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _next_tick(self, n=1):
+        t = self._tick
+        self._tick = (self._tick + n) & 0xFFFFFFFF
+        return t
+
+    def _fn(self, name):
+        return getattr(self._lib, name + self._sfx)
+
+    def _check_actions(self, actions):
+        if not torch.is_tensor(actions):
+            actions = torch.as_tensor(actions)
+        if actions.device != self.device or actions.dtype != self.dtype:
+            actions = actions.to(device=self.device, dtype=self.dtype, non_blocking=True)
+        if tuple(actions.shape) != (self.E, self.N, self.act_dim):
+            raise ValueError("actions must have shape %s, got %s" %
+                             ((self.E, self.N, self.act_dim), tuple(actions.shape)))
+        return actions.contiguous()
+
+    # ------------------------------------------------------------------ API
+    def seed(self, seed=None):
+        """MultiAgentEnv.seed (environment.py:106-110): None -> 1."""
+        self.seed_value = (1 if seed is None else int(seed)) & 0xFFFFFFFFFFFFFFFF
+        self._tick = 0
+
+    def reset(self, mask=None):
+        """Scenario.reset_world + current_step = 0 for all (or masked) envs; returns obs [E,N,D]."""
+        m = None
+        if mask is not None:
+            m = torch.as_tensor(mask, device=self.device).to(torch.uint8).contiguous()
+            if tuple(m.shape) != (self.E,):
+                raise ValueError("mask must have shape (E,)")
+        with torch.cuda.device(self.device):
+            rc = self._fn("fg_reset")(C.byref(self.params), C.byref(self._bufs), self.scn, self.E, self.N,
+                                      self.L, nat.ptr(m), self.seed_value, self._next_tick(),
+                                      self.env_offset, self._stream())
+            nat.check(rc, "fg_reset")
+            self.launches += 1
+        if mask is None:
+            self.stats.zero_()
+        return self.observe()
+
+    def observe(self):
+        """Recompute obs / reward / individual rewards from the current state (no stepping)."""
+        with torch.cuda.device(self.device):
+            rc = self._fn("fg_obs_reward")(C.byref(self.params), C.byref(self._bufs), self.scn, self.E,
+                                           self.N, self.L, self._stream())
+            nat.check(rc, "fg_obs_reward")
+            self.launches += 1
+        return self.obs
+
+    def world_step(self, actions):
+        """``World.step`` only (physics; no observation / reward / done)."""
+        actions = self._check_actions(actions)
+        b = self._make_buffers(act=actions)
+        with torch.cuda.device(self.device):
+            rc = self._fn("fg_world_step")(C.byref(self.params), C.byref(b), self.E, self.N,
+                                           self.seed_value, self._next_tick(), self.env_offset,
+                                           self._stream())
+            nat.check(rc, "fg_world_step")
+            self.launches += 1
+
+    def step(self, actions):
+        """One fused env step.  Returns ``(obs[E,N,D], reward[E,N,1], done[E,N], info)`` with
+        ``info['individual_reward'] [E,N]`` (environment.py:130).  Outputs are views of buffers
+        owned by this object and are overwritten by the next step."""
+        actions = self._check_actions(actions)
+        b = self._bufs
+        if actions.data_ptr() != self.actions.data_ptr():
+            b = self._make_buffers(act=actions)
+        self._launch_fused(b, 1, 0)
+        return self.obs, self.reward, self.done, {"individual_reward": self.indiv}
+
+    def step_random(self):
+        """Random policy (test.py:20) drawn in-kernel from Philox, then the fused step."""
+        self._launch_fused(self._bufs, 1, 1)
+        return self.obs, self.reward, self.done, {"individual_reward": self.indiv}
+
+    def sample_actions(self, out=None):
+        """``[space.sample() for space in env.action_space]`` for every env: U(-1,1), on device.
+        Uses the tick of the NEXT step, i.e. exactly what step_random() would draw."""
+        if not self.silent:
+            raise nat.NativeError("sample_actions supports silent agents only")
+        out = self.actions if out is None else out
+        with torch.cuda.device(self.device):
+            rc = self._fn("fg_random_actions")(nat.ptr(out), self.E, self.N, self.seed_value,
+                                               self._tick, self.env_offset, self._stream())
+            nat.check(rc, "fg_random_actions")
+            self.launches += 1
+        return out
+
+    def rollout_random(self, n_steps):
+        """``n_steps`` random-policy steps in ONE launch with the state held on chip; obs / reward /
+        done buffers hold the last step's values afterwards."""
+        self._launch_fused(self._bufs, int(n_steps), 1)
+        return self.obs, self.reward, self.done, {"individual_reward": self.indiv}
+
+    def _launch_fused(self, bufs, n_steps, random_actions):
+        with torch.cuda.device(self.device):
+            rc = self._fn("fg_step_fused")(C.byref(self.params), C.byref(bufs), self.scn, self.E, self.N,
+                                           self.L, n_steps, random_actions, int(self.auto_reset),
+                                           self.seed_value, self._next_tick(n_steps), self.env_offset,
+                                           self._stream())
+            nat.check(rc, "fg_step_fused")
+            self.launches += 1
+
+    # ------------------------------------------------------------------ bookkeeping
+    @property
+    def share_obs(self):
+        """``obs.reshape(E, -1)`` (train/maddpg-v4/runner.py:204)."""
+        return self.obs.reshape(self.E, -1)
+
+    def episode_stats(self):
+        """Device-side episode statistics as python floats (synchronises)."""
+        n, s, s2, c = self.stats.tolist()
+        mean = s / n if n else float("nan")
+        return {"episodes": n, "return_sum": s, "return_sq_sum": s2, "collisions": c,
+                "return_mean": mean}
+
+    def bytes_per_env_step(self):
+        """Algorithmic HBM bytes per env-step: B_full(N) = 24N^2 + 53N + 16 for hd
+        fp32 with observations; without obs B_state(N) = 53N + 16.  Scaled by the element size."""
+        es = 4 if self.dtype == torch.float32 else 8
+        N, L = self.N, self.L
+        if self.scn == nat.FG_SCENARIO_HD:
+            rd = es * (2 * N * 3 + 2 * N + 2) + 4           # act, pos, vel, ideal_shape, ideal_vel, step
+        else:
+            rd = es * (2 * N * 3 + 2 * L) + 4               # act, pos, vel, landmarks, step
+        wr = es * (2 * N * 2 + N) + N + 4                   # pos, vel, reward, done, step
+        if self.obs is not None:
+            wr += es * N * self.D
+        return rd + wr
+
+    def state_dict(self):
+        sd = {k: getattr(self, k).clone() for k in
+              ("pos", "vel", "comm", "step_count", "ep_return", "ep_collisions", "stats")}
+        for k in ("landmarks", "ideal_shape", "ideal_vel"):
+            if getattr(self, k) is not None:
+                sd[k] = getattr(self, k).clone()
+        sd["rng"] = {"seed": self.seed_value, "tick": self._tick, "env_offset": self.env_offset}
+        return sd
+
+    def load_state_dict(self, sd):
+        for k, v in sd.items():
+            if k == "rng":
+                self.seed_value, self._tick, self.env_offset = v["seed"], v["tick"], v["env_offset"]
+            else:
+                getattr(self, k).copy_(v)

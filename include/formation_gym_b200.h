@@ -1,0 +1,178 @@
+/*
+ * formation_gym_b200.h -- C ABI of the B200-native MPE step path for jc-bao/gym-formation.
+ *
+ * The reference has no native layer: its hot path is per-object Python (formation_gym/
+ * environment.py:113-142 -> formation_gym/core.py:206-322 -> formation_gym/envs/
+ * formation_hd_env.py:38-75 / basic_formation_env.py:29-52).  This header declares the entry
+ * points a maintainer of the reference would bind (ctypes stub in INTEGRATION.md) to replace
+ * those functions with sm_100a kernels.  Each entry cites the reference code it replaces.
+ *
+ * Conventions
+ *  - Every buffer is CALLER-OWNED DEVICE memory (plain pointers; no torch types).  The library
+ *    allocates nothing persistent, keeps no global state and never frees caller memory.
+ *  - All work is enqueued asynchronously on `stream` (a cudaStream_t passed as void*; NULL is
+ *    the legacy default stream).  No internal synchronisation, no hidden streams.  Entry points
+ *    are re-entrant and may be called from several host threads on different streams/buffers.
+ *  - Layout is the reference's VecEnv contract (train/maddpg-v2/utils/env_wrappers.py:68-72),
+ *    env-major, contiguous:  pos/vel [E,N,2]  act [E,N,act_dim]  comm [E,N,2]  obs [E,N,D]
+ *    reward [E,N,1]  indiv [E,N]  done [E,N] (uint8)  step [E] (int32)  ideal_shape [E,N,2]
+ *    ideal_vel [E,2]  landmarks [E,L,2].   hd: L = N, D = 6N.  basic: D = 4 + 2L + 4(N-1).
+ *    act_dim = 2 for silent agents (both target scenarios), 2 + 2 when params.silent == 0.
+ *  - `float` entry points compute in fp32, the `_f64` twins in fp64 with FMA contraction
+ *    disabled (the 25-step 1e-9 parity build).  Same semantics otherwise.
+ *  - Return value: 0 on success; < 0 on error (FG_ERR_*), message via fg_last_error()
+ *    (thread-local).  No C++ exception crosses the ABI.  NaNs propagate exactly as in the
+ *    reference (coincident agents -> 0/0, core.py:312); no epsilon is added anywhere.
+ *  - The caller's `act` buffer is never written (the reference's in-place `u *= sensitivity`
+ *    on the caller's array, environment.py:216-221, is deliberately not reproduced).
+ *  - RNG: counter-based Philox4x32-10, key = seed, counter = (global env id, agent, tick,
+ *    purpose).  `env_offset` is the global index of env 0 of this buffer, so results do not
+ *    depend on launch geometry or on how envs are sharded over GPUs.  The caller supplies a
+ *    fresh `tick` per call (e.g. a global step counter).  Parity with the reference's global
+ *    MT19937 stream (np.random.*) is statistical only.
+ */
+#ifndef FORMATION_GYM_B200_H
+#define FORMATION_GYM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FG_ABI_VERSION 1
+#define FG_MAX_AGENTS 256      /* one CTA holds at least one whole env; 3^5 = 243 fits */
+#define FG_MAX_LANDMARKS 256
+#define FG_MAX_WALLS 8
+
+#define FG_OK 0
+#define FG_ERR_ARG (-1)        /* null pointer, bad size, unsupported combination */
+#define FG_ERR_CUDA (-2)       /* launch / runtime failure, see fg_last_error() */
+
+/* scenario ids */
+#define FG_SCENARIO_HD 0       /* formation_gym/envs/formation_hd_env.py */
+#define FG_SCENARIO_BASIC 1    /* formation_gym/envs/basic_formation_env.py */
+
+/* core.Wall (formation_gym/core.py:27-41) */
+typedef struct fg_wall {
+    int32_t orient;            /* 0 = 'H' (lies along x at y = axis_pos), 1 = 'V' */
+    int32_t hard;
+    double axis_pos, end0, end1, width;
+} fg_wall;
+
+/* World / Agent constants (formation_gym/core.py:45-110,112-139; environment.py:218-221). */
+typedef struct fg_params {
+    double dt;                 /* core.py:125  0.1 */
+    double damping;            /* core.py:127  0.25 */
+    double contact_force;      /* core.py:129  1e2 */
+    double contact_margin;     /* core.py:130  1e-3 */
+    double sensitivity;        /* environment.py:218  5.0 (replaced by accel when has_accel) */
+    double agent_size;         /* hd 0.03 (formation_hd_env.py:26), basic 0.1 */
+    double mass;               /* core.py:69  1.0 */
+    double accel;              /* core.py:65  used iff has_accel (scales the action twice) */
+    double max_speed;          /* core.py:64  used iff has_max_speed */
+    double u_noise;            /* core.py:97  0 = off (None) */
+    double c_noise;            /* core.py:99  0 = off (None) */
+    int32_t has_accel;
+    int32_t has_max_speed;
+    int32_t collide;           /* agents collide (formation_hd_env.py:24) */
+    int32_t silent;            /* 1: comm state = 0 (core.py:281-282); 0: c = action.c + noise */
+    int32_t world_length;      /* episode length; done = step >= world_length */
+    int32_t n_walls;
+    int32_t action_prescaled;  /* 1: `act` already is agent.action.u (after _set_action), i.e. World.step()
+                                  called on its own (core.py:206); the sensitivity multiply is skipped */
+    int32_t reserved_;
+    /* optional per-agent DEVICE arrays [N] in the entry point's real type; NULL = scalar above.
+       agent_accel / agent_max_speed entries < 0 mean "None" for that agent. */
+    const void* agent_mass;
+    const void* agent_size_arr;
+    const void* agent_accel;
+    const void* agent_max_speed;
+    fg_wall walls[FG_MAX_WALLS];
+} fg_params;
+
+/* Device buffers of one env batch (all caller-owned; element type = entry point's real type
+   unless stated).  Pointers marked (opt) may be NULL. */
+typedef struct fg_buffers {
+    void* pos;                 /* [E,N,2]  in/out  agent.state.p_pos */
+    void* vel;                 /* [E,N,2]  in/out  agent.state.p_vel */
+    const void* act;           /* [E,N,act_dim] in; unused when random actions are requested */
+    void* comm;                /* (opt) [E,N,2] out  agent.state.c */
+    void* ideal_shape;         /* hd: [E,N,2] Scenario.ideal_shape (centred; formation_hd_env.py:93) */
+    void* ideal_vel;           /* hd: [E,2]   Scenario.ideal_vel   (formation_hd_env.py:95) */
+    void* landmarks;           /* basic: [E,L,2] required.  hd: (opt) [E,N,2] in/out, re-centred on the
+                                  agents' centroid as the reference's observation side effect does
+                                  (formation_hd_env.py:40-44; visualisation only) */
+    int32_t* step;             /* [E] in/out  env.current_step */
+    void* obs;                 /* (opt) [E,N,D] out; NULL = state+reward only */
+    void* reward;              /* [E,N,1] out  shared reward sum_i r_i (environment.py:136-138) */
+    void* indiv;               /* (opt) [E,N] out  info['individual_reward'] (environment.py:130) */
+    uint8_t* done;             /* [E,N] out  (environment.py:172-177) */
+    void* ep_return;           /* (opt) [E] in/out running episode return (shared reward) */
+    int32_t* ep_collisions;    /* (opt) [E] in/out running count of reward-collisions */
+    double* stats;             /* (opt) [4] in/out: n_episodes, sum return, sum return^2,
+                                  sum collisions -- updated atomically at episode ends */
+} fg_buffers;
+
+int fg_abi_version(void);
+const char* fg_last_error(void);
+/* SM count and compute capability of the current device (host logic sizes grids with it). */
+int fg_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* World.step (formation_gym/core.py:206-225) preceded by MultiAgentEnv._set_action
+ * (environment.py:187-236): apply_action_force (core.py:228-237, Philox u-noise),
+ * apply_environment_force / get_entity_collision_force (core.py:240-262,289-322; walls
+ * 325-362), integrate_state (core.py:264-277), update_agent_state (core.py:279-286).
+ * Reads b->pos, vel, act; writes pos, vel, comm.  One fused kernel. */
+int fg_world_step(const fg_params* p, const fg_buffers* b, int E, int N,
+                  uint64_t seed, uint32_t tick, uint32_t env_offset, void* stream);
+int fg_world_step_f64(const fg_params* p, const fg_buffers* b, int E, int N,
+                      uint64_t seed, uint32_t tick, uint32_t env_offset, void* stream);
+
+/* Scenario.observation + Scenario.reward from the CURRENT state, for every agent of every env
+ * (formation_hd_env.py:38-75,119-121 / basic_formation_env.py:29-52,89-91) plus the shared
+ * reward sum (environment.py:136-138).  Writes obs, reward, indiv (and hd landmarks).
+ * Does not touch step/done. */
+int fg_obs_reward(const fg_params* p, const fg_buffers* b, int scenario, int E, int N, int L,
+                  void* stream);
+int fg_obs_reward_f64(const fg_params* p, const fg_buffers* b, int scenario, int E, int N, int L,
+                      void* stream);
+
+/* MultiAgentEnv.step (environment.py:113-142) fused into ONE launch: _set_action, World.step,
+ * observation, reward, done, shared-reward sum, episode statistics and (auto_reset != 0) the
+ * VecEnv auto-reset (train/maddpg-v2/utils/env_wrappers.py:14-18: when the episode ends the
+ * terminal reward/done are returned together with the RESET observation).
+ * n_steps > 1 runs a whole rollout inside the kernel with state held on chip; then actions are
+ * drawn in-kernel from the random policy U(-1,1) (test.py:20) and b->act is ignored.
+ * n_steps == 1 and random_actions == 0 is the plain step on caller-provided actions. */
+int fg_step_fused(const fg_params* p, const fg_buffers* b, int scenario, int E, int N, int L,
+                  int n_steps, int random_actions, int auto_reset,
+                  uint64_t seed, uint32_t tick, uint32_t env_offset, void* stream);
+int fg_step_fused_f64(const fg_params* p, const fg_buffers* b, int scenario, int E, int N, int L,
+                      int n_steps, int random_actions, int auto_reset,
+                      uint64_t seed, uint32_t tick, uint32_t env_offset, void* stream);
+
+/* Scenario.reset_world (formation_hd_env.py:77-95 / basic_formation_env.py:54-65) +
+ * MultiAgentEnv.reset's current_step = 0 (environment.py:145) for envs with mask[e] != 0
+ * (mask NULL = all).  Draw order per env follows the reference: agents, landmarks, ideal_vel.
+ * Writes pos, vel(=0), comm(=0), landmarks, ideal_shape, ideal_vel, step(=0), ep_return(=0). */
+int fg_reset(const fg_params* p, const fg_buffers* b, int scenario, int E, int N, int L,
+             const uint8_t* mask, uint64_t seed, uint32_t tick, uint32_t env_offset, void* stream);
+int fg_reset_f64(const fg_params* p, const fg_buffers* b, int scenario, int E, int N, int L,
+                 const uint8_t* mask, uint64_t seed, uint32_t tick, uint32_t env_offset,
+                 void* stream);
+
+/* Random policy: act[e,i,:] ~ U(-1,1) (test.py:20 -> Box.sample, environment.py:67-68), same
+ * Philox stream the in-kernel rollout uses, so step-by-step and in-kernel rollouts agree. */
+int fg_random_actions(void* act, int E, int N, uint64_t seed, uint32_t tick, uint32_t env_offset,
+                      void* stream);
+int fg_random_actions_f64(void* act, int E, int N, uint64_t seed, uint32_t tick,
+                          uint32_t env_offset, void* stream);
+
+/* Launch geometry chosen for (N): envs per CTA and threads per CTA (for reporting/tests). */
+int fg_launch_geometry(int N, int* envs_per_cta, int* threads_per_cta);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FORMATION_GYM_B200_H */

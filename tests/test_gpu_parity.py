@@ -1,0 +1,237 @@
+"""GPU parity tests: the CUDA path (through the C ABI, via BatchedFormationEnv) against
+ (a) the golden fixtures frozen from the unmodified reference (tests/golden/*.npz) and
+ (b) the numpy oracle on seeded random inputs.
+
+Tolerances (BASELINE.json north_star):
+  fp32 build : single step |err| <= 1e-5 on pos / vel / obs / individual reward;
+               shared reward atol 1e-5 + rtol 1e-6 (|R| reaches ~900 at N=243, where one fp32 ulp
+               is 6e-5 -- SURVEY.md section 7)
+  fp64 build : single step <= 1e-12; 25-step trajectories <= 1e-9
+"""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+import formation_gym  # noqa: E402
+from formation_gym.batched import BatchedFormationEnv  # noqa: E402
+from oracle import mpe_oracle as mo  # noqa: E402
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+F32_TOL = 1e-5
+
+
+def load(name):
+    return dict(np.load(os.path.join(GOLD, name)))
+
+
+def dev(x, dtype):
+    return torch.as_tensor(np.ascontiguousarray(x), dtype=dtype, device="cuda")
+
+
+def inject_hd(env, g, lm=True):
+    env.pos.copy_(dev(g["pos0"], env.dtype))
+    env.vel.copy_(dev(g["vel0"], env.dtype))
+    env.ideal_shape.copy_(dev(g["shape"], env.dtype))
+    env.ideal_vel.copy_(dev(g["ivel"], env.dtype))
+    if lm and env.landmarks is not None:
+        env.landmarks.copy_(dev(g["lm0"], env.dtype))
+    if "step0" in g:
+        env.step_count.copy_(torch.as_tensor(g["step0"], dtype=torch.int32, device="cuda"))
+
+
+def maxerr(a, b):
+    a = a.detach().double().cpu().numpy() if torch.is_tensor(a) else np.asarray(a, np.float64)
+    return float(np.max(np.abs(a - np.asarray(b, np.float64)))) if a.size else 0.0
+
+
+HD_SINGLE = sorted(os.path.basename(p) for p in glob.glob(os.path.join(GOLD, "hd_n*_spread.npz"))
+                   + glob.glob(os.path.join(GOLD, "hd_n*_clustered.npz")))
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64], ids=["f32", "f64"])
+@pytest.mark.parametrize("name", HD_SINGLE)
+def test_hd_single_step_golden(name, dtype):
+    g = load(name)
+    E, N = g["pos0"].shape[:2]
+    env = BatchedFormationEnv("formation_hd_env", E, N, episode_length=25, dtype=dtype,
+                              auto_reset=False, track_landmarks=True)
+    inject_hd(env, g)
+    obs, rew, done, info = env.step(dev(g["act"], dtype))
+    tol = F32_TOL if dtype == torch.float32 else 1e-12
+    assert maxerr(env.pos, g["pos"]) <= tol
+    assert maxerr(env.vel, g["vel"]) <= tol
+    o = obs if "obs_rows" not in g else obs[:, torch.as_tensor(g["obs_rows"], device="cuda")]
+    assert maxerr(o, g["obs"]) <= tol
+    assert maxerr(info["individual_reward"], g["indiv"]) <= (tol if dtype == torch.float32 else 1e-11)
+    R = g["reward"]
+    rtol = 1e-6 if dtype == torch.float32 else 1e-13
+    assert np.all(np.abs(rew[:, :, 0].double().cpu().numpy() - R) <= tol + rtol * np.abs(R))
+    assert np.array_equal(done.cpu().numpy(), g["done"])
+    assert np.array_equal(env.step_count.cpu().numpy(), g["step0"] + 1)
+    assert maxerr(env.landmarks, g["landmarks"]) <= (1e-5 if dtype == torch.float32 else 1e-12)
+
+
+@pytest.mark.parametrize("n", [3, 9, 27, 243])
+def test_hd_traj25_f64(n):
+    """25-step trajectories from the unmodified reference, fp64 build: <= 1e-9 (north star)."""
+    g = load("hd_n%d_traj25.npz" % n)
+    env = BatchedFormationEnv("formation_hd_env", 1, n, episode_length=100, dtype=torch.float64,
+                              auto_reset=False)
+    inject_hd(env, {k: v[None] for k, v in g.items() if k in ("pos0", "vel0", "shape", "ivel")}, lm=False)
+    worst = 0.0
+    for t in range(g["acts"].shape[0]):
+        obs, rew, done, info = env.step(dev(g["acts"][t][None], torch.float64))
+        worst = max(worst, maxerr(env.pos[0], g["pos"][t]), maxerr(env.vel[0], g["vel"][t]),
+                    maxerr(info["individual_reward"][0], g["indiv"][t]))
+        assert abs(float(rew[0, 0, 0]) - g["reward"][t][0]) <= 1e-9 * max(1.0, abs(g["reward"][t][0]))
+    o = obs[0] if "obs_rows" not in g else obs[0][torch.as_tensor(g["obs_rows"], device="cuda")]
+    worst = max(worst, maxerr(o, g["obs_last"]))
+    print("N=%d 25-step fp64 max abs err %.3e" % (n, worst))
+    assert worst <= 1e-9
+
+
+@pytest.mark.parametrize("n", [3, 9, 27])
+def test_hd_traj25_f32_reported(n):
+    """fp32 over 25 steps is not a contract number (contacts amplify rounding); it must stay sane."""
+    g = load("hd_n%d_traj25.npz" % n)
+    env = BatchedFormationEnv("formation_hd_env", 1, n, episode_length=100, auto_reset=False)
+    inject_hd(env, {k: v[None] for k, v in g.items() if k in ("pos0", "vel0", "shape", "ivel")}, lm=False)
+    for t in range(g["acts"].shape[0]):
+        env.step(dev(g["acts"][t][None], torch.float32))
+    err = maxerr(env.pos[0], g["pos"][-1])
+    print("N=%d 25-step fp32 max abs pos err %.3e" % (n, err))
+    assert err <= 5e-3
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64], ids=["f32", "f64"])
+def test_hd_hetero_golden(dtype):
+    """per-agent mass / accel / max_speed (core.py:235-236,271-276,314-318; accel-twice quirk)."""
+    g = load("hd_n9_hetero.npz")
+    t = g["tweak"]
+    E, N = g["pos0"].shape[:2]
+    env = BatchedFormationEnv("formation_hd_env", E, N, episode_length=25, dtype=dtype, auto_reset=False,
+                              agent_mass=t[:, 0], agent_accel=t[:, 1], agent_max_speed=t[:, 2])
+    inject_hd(env, g, lm=False)
+    obs, rew, done, info = env.step(dev(g["act"], dtype))
+    tol = F32_TOL if dtype == torch.float32 else 1e-12
+    assert maxerr(env.pos, g["pos"]) <= tol
+    assert maxerr(env.vel, g["vel"]) <= tol
+    assert maxerr(obs, g["obs"]) <= tol
+    assert maxerr(info["individual_reward"], g["indiv"]) <= tol * 10
+
+
+def test_hd_nan_quirk():
+    """Coincident agents -> NaN (core.py:312; train/README.md:194-197): same NaN pattern."""
+    g = load("hd_n3_nan.npz")
+    env = BatchedFormationEnv("formation_hd_env", 1, 3, episode_length=25, dtype=torch.float64,
+                              auto_reset=False)
+    inject_hd(env, {k: v[None] for k, v in g.items() if k in ("pos0", "vel0", "shape", "ivel")}, lm=False)
+    obs, rew, done, info = env.step(dev(g["act"][None], torch.float64))
+    assert np.array_equal(np.isnan(env.pos[0].cpu().numpy()), np.isnan(g["pos"]))
+    assert np.array_equal(np.isnan(env.vel[0].cpu().numpy()), np.isnan(g["vel"]))
+    assert np.array_equal(np.isnan(obs[0].cpu().numpy()), np.isnan(g["obs"]))
+    finite = np.isfinite(g["pos"])
+    assert maxerr(env.pos[0][torch.as_tensor(finite, device="cuda")], g["pos"][finite]) <= 1e-12
+
+
+BASIC = ["basic_n3_spread.npz", "basic_n3_clustered.npz", "basic_n5_clustered.npz",
+         "basic_n3_hetero.npz", "basic_n3_walls.npz"]
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64], ids=["f32", "f64"])
+@pytest.mark.parametrize("name", BASIC)
+def test_basic_single_step_golden(name, dtype):
+    g = load(name)
+    E, N = g["pos0"].shape[:2]
+    L = g["lm0"].shape[1]
+    kw = {}
+    if "tweak" in g:
+        t = g["tweak"]
+        kw = dict(agent_mass=t[:, 0], agent_accel=[None if x < 0 else x for x in t[:, 1]],
+                  agent_max_speed=[None if x < 0 else x for x in t[:, 2]])
+    if "walls" in g:
+        kw["walls"] = [('H' if w[0] == 0 else 'V', w[1], w[2], w[3], w[4]) for w in g["walls"]]
+    env = BatchedFormationEnv("basic_formation_env", E, N, episode_length=25, num_landmarks=L,
+                              dtype=dtype, auto_reset=False, **kw)
+    env.pos.copy_(dev(g["pos0"], dtype)); env.vel.copy_(dev(g["vel0"], dtype))
+    env.landmarks.copy_(dev(g["lm0"], dtype))
+    env.step_count.copy_(torch.as_tensor(g["step0"], dtype=torch.int32, device="cuda"))
+    obs, rew, done, info = env.step(dev(g["act"], dtype))
+    tol = F32_TOL if dtype == torch.float32 else 1e-11
+    assert maxerr(env.pos, g["pos"]) <= tol
+    assert maxerr(env.vel, g["vel"]) <= tol
+    assert maxerr(obs, g["obs"]) <= tol
+    assert maxerr(info["individual_reward"], g["indiv"]) <= tol
+    assert maxerr(rew[:, :, 0], g["reward"]) <= tol * 4
+    assert np.array_equal(done.cpu().numpy(), g["done"])
+
+
+def test_basic_traj25_f64():
+    g = load("basic_n3_traj25.npz")
+    env = BatchedFormationEnv("basic_formation_env", 1, 3, episode_length=50, dtype=torch.float64,
+                              auto_reset=False)
+    env.pos.copy_(dev(g["pos0"][None], torch.float64)); env.vel.copy_(dev(g["vel0"][None], torch.float64))
+    env.landmarks.copy_(dev(g["lm0"][None], torch.float64))
+    worst = 0.0
+    for t in range(g["acts"].shape[0]):
+        obs, rew, done, info = env.step(dev(g["acts"][t][None], torch.float64))
+        worst = max(worst, maxerr(env.pos[0], g["pos"][t]), maxerr(env.vel[0], g["vel"][t]),
+                    maxerr(info["individual_reward"][0], g["indiv"][t]))
+    worst = max(worst, maxerr(obs[0], g["obs_last"]))
+    print("basic 25-step fp64 max abs err %.3e" % worst)
+    assert worst <= 1e-9
+
+
+# ------------------------------------------------------------------ oracle on seeded random batches
+@pytest.mark.parametrize("E,N,spread", [(1000, 3, 0.08), (1000, 9, 0.2), (257, 9, 1.0), (64, 27, 0.35),
+                                        (37, 10, 0.2), (5, 81, 0.5), (3, 243, 0.8), (2, 256, 0.9)])
+def test_hd_vs_oracle_random(E, N, spread):
+    """Ragged sizes (E not a multiple of the tile, N not a power of 3, N = FG_MAX_AGENTS)."""
+    rng = np.random.default_rng(E * 1000 + N)
+    f32 = lambda x: x.astype(np.float32).astype(np.float64)  # noqa: E731
+    pos = f32(rng.uniform(-spread, spread, (E, N, 2)))
+    vel = f32(rng.uniform(-0.5, 0.5, (E, N, 2)))
+    act = f32(rng.uniform(-1, 1, (E, N, 2)))
+    lm = rng.uniform(-1, 1, (E, N, 2))
+    shape = f32(lm - lm.mean(1, keepdims=True))
+    ivel = f32(rng.uniform(-1, 1, (E, 2)))
+    step0 = rng.integers(0, 25, E)
+    ref = mo.hd_env_step(pos, vel, act, shape, ivel, step0, mo.WorldParams(world_length=25))
+    for dtype, tol in ((torch.float32, F32_TOL), (torch.float64, 1e-11)):
+        env = BatchedFormationEnv("formation_hd_env", E, N, episode_length=25, dtype=dtype, auto_reset=False)
+        inject_hd(env, dict(pos0=pos, vel0=vel, shape=shape, ivel=ivel, step0=step0), lm=False)
+        obs, rew, done, info = env.step(dev(act, dtype))
+        assert maxerr(env.pos, ref["pos"]) <= tol
+        assert maxerr(env.vel, ref["vel"]) <= tol
+        assert maxerr(obs, ref["obs"]) <= tol
+        assert maxerr(info["individual_reward"], ref["indiv"]) <= tol * (1 if dtype == torch.float32 else 10)
+        R = ref["reward"]
+        assert np.all(np.abs(rew[:, 0, 0].double().cpu().numpy() - R) <= tol + 1e-6 * np.abs(R))
+        assert np.array_equal(done[:, 0].cpu().numpy(), ref["done"])
+        assert bool((done == done[:, :1]).all())
+        assert bool((rew == rew[:, :1]).all())
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64], ids=["f32", "f64"])
+def test_separate_entry_points_match_fused(dtype):
+    """fg_world_step + fg_obs_reward == fg_step_fused: bit-exact in the fp64 build (no FMA
+    contraction anywhere); the fp32 instantiations may contract differently -> 1e-6."""
+    E, N = 300, 9
+    a = BatchedFormationEnv("formation_hd_env", E, N, episode_length=25, seed=3, auto_reset=False, dtype=dtype)
+    b = BatchedFormationEnv("formation_hd_env", E, N, episode_length=25, seed=3, auto_reset=False, dtype=dtype)
+    a.reset(); b.reset()
+    a.pos.mul_(0.15); b.pos.mul_(0.15)
+    act = a.sample_actions().clone()
+    a.step(act)
+    b.world_step(act); b.observe()
+    torch.cuda.synchronize()
+    for k in ("pos", "vel", "obs", "reward", "indiv"):
+        if dtype == torch.float64:
+            assert torch.equal(getattr(a, k), getattr(b, k)), k
+        else:
+            assert maxerr(getattr(a, k), getattr(b, k).double().cpu().numpy()) <= 1e-6, k
