@@ -49,6 +49,7 @@ template <typename T> struct KArgs {
     T kcut;
     T rthr, rthr2_hi;                // reward collision threshold and its guarded square
     int has_accel, has_vmax, collide, silent, world_length, n_walls, prescaled;
+    int mass_one;                    // mass == 1: F / m is exact without the division
     int n_steps, random_actions, auto_reset;
     uint64_t seed; uint32_t tick; uint32_t env_offset;
     WallT<T> walls[kMaxWalls];

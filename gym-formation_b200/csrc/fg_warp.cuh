@@ -1,0 +1,374 @@
+// fg_warp.cuh -- warp-autonomous fused step kernel for formation_hd_env with small N (sm_100a).
+//
+// Why it exists: at N = 9 the tile kernel in fg_kernels.cuh is ISSUE-bound, not HBM-bound
+// (profiles/r01_baseline_*: 115 M warp instructions per 131072-env launch, 73 % issue-active, 28 %
+// of the HBM roofline): it decodes (row, item) for every 8-byte observation item and crosses six
+// CTA barriers per step.  This kernel removes both costs:
+//
+//   * N is a template constant and EPW = floor(32 / N) whole envs live in ONE warp (lane <-> agent),
+//     so every exchange inside an env is warp-local: shared-memory slices private to the warp,
+//     __syncwarp() only, no __syncthreads() anywhere.  Warps drift freely, which spreads their
+//     load / compute / store phases over time.
+//   * every pair loop is unrolled with compile-time shared-memory offsets; far pairs cost
+//     6-7 instructions (a near-pair BITMASK is built branch-free and the softplus contact force /
+//     the exact collision test run afterwards only for set bits, in ascending-j order = the
+//     reference's accumulation order, core.py:242-254).
+//   * each lane writes ITS OWN observation row (3N float2 items, compile-time offsets, conflict-free
+//     because the row stride 3N is odd) into the warp's slice of shared memory, and the slice --
+//     one contiguous span of the [E,N,6N] tensor -- leaves the SM as ONE TMA bulk store
+//     (cp.async.bulk.global.shared::cta; SASS UBLKCP) issued by lane 0.  Row and env spans are only
+//     8-byte aligned for odd N (fp32), so a span that starts/ends on an odd 8-byte slot sends that
+//     one head/tail item with a plain 8-byte store.
+//
+// Semantics are those of fg::k_step<T, hd, PHYS, OBSREW> (fg_kernels.cuh) restricted to: uniform
+// agent constants, no walls, silent agents, landmarks not tracked.  Everything else takes the
+// tile kernel.  Reference citations are on the code below.
+#pragma once
+#include "fg_kernels.cuh"
+
+namespace fg {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+
+// Per-warp shared-memory slice layout (bytes), shared by host (sizing) and device (carving).
+template <typename T, int N, bool WOBS> struct WarpLayout {
+    typedef typename Ops<T>::R2 R2;
+    typedef typename Ops<T>::Bits Bits;
+    static constexpr int EPW = 32 / N;             // envs per warp
+    static constexpr int NA = EPW * N;             // active lanes
+    static constexpr int IPR = 3 * N;              // R2 items per observation row (6N scalars)
+    static constexpr int OBS_ITEMS = WOBS ? NA * IPR : 0;
+    static constexpr size_t off_obs = 0;                                     // +16 B slack for the 8-byte phase
+    static constexpr size_t off_pold = off_obs + (WOBS ? (size_t)OBS_ITEMS * sizeof(R2) + 16 : 0);
+    static constexpr size_t off_pnew = off_pold + (size_t)NA * sizeof(R2);   // [EPW][2N]: p_0..p_{N-1} twice
+    static constexpr size_t off_cen = off_pnew + (size_t)2 * NA * sizeof(R2);
+    static constexpr size_t off_shp = off_cen + (size_t)NA * sizeof(R2);
+    static constexpr size_t off_vel = off_shp + (size_t)NA * sizeof(R2);
+    static constexpr size_t off_mean = off_vel + (size_t)NA * sizeof(R2);    // [EPW][2]: mean pos, mean vel
+    static constexpr size_t off_max = off_mean + (size_t)2 * EPW * sizeof(R2);
+    static constexpr size_t off_col = off_max + (size_t)EPW * sizeof(Bits);
+    static constexpr size_t raw = off_col + (size_t)EPW * sizeof(int);
+    static constexpr size_t stride = (raw + 15) & ~(size_t)15;
+};
+
+// One observation row of formation_hd_env (formation_hd_env.py:52-59) from the warp's shared state:
+// [p_vel | p_j - p_i (j != i ascending) | comm zeros | ideal_shape.flatten() | ideal_vel].
+// Generic (rolled) version, used by the auto-reset path only; the hot path fuses these stores into
+// the reward loop.
+template <typename T, int N>
+__device__ __forceinline__ void fill_row_hd(typename Ops<T>::R2* row, const typename Ops<T>::R2* eP,
+                                            const typename Ops<T>::R2* eS, typename Ops<T>::R2 p,
+                                            typename Ops<T>::R2 v, typename Ops<T>::R2 iv, int i) {
+    typedef Ops<T> O;
+    row[0] = v;
+    for (int k = 1; k < N; ++k) {
+        typename O::R2 q = eP[k];                               // agent (i + k) mod N
+        const int slot = (i + k < N) ? (i + k) : (i + k - N + 1);
+        row[slot] = O::make(O::sub(q.x, p.x), O::sub(q.y, p.y));
+    }
+    for (int k = 0; k < N - 1; ++k) row[N + k] = O::make((T)0, (T)0);
+    for (int k = 0; k < N; ++k) row[2 * N - 1 + k] = eS[k];
+    row[3 * N - 1] = iv;
+}
+
+template <typename T, int N, bool WOBS>
+__global__ void __launch_bounds__(256) k_hd_warp(const __grid_constant__ KArgs<T> a) {
+    typedef Ops<T> O;
+    typedef typename O::R2 R2;
+    typedef typename O::Bits Bits;
+    typedef WarpLayout<T, N, WOBS> LY;
+    constexpr int EPW = LY::EPW, NA = LY::NA, IPR = LY::IPR;
+    constexpr unsigned FULL = 0xffffffffu;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+
+    const int lane = threadIdx.x & 31;
+    const int wib = threadIdx.x >> 5;
+    const int gw = blockIdx.x * (blockDim.x >> 5) + wib;                    // global warp index
+    const int env0 = gw * EPW;
+    if (env0 >= a.E) return;                                                // warp-uniform; no CTA barriers below
+    const int nval = min(EPW, a.E - env0);
+    const bool active = lane < nval * N;
+    const int le = active ? lane / N : 0;
+    const int i = active ? lane - le * N : 0;
+    const int e = env0 + le;
+    const size_t g = (size_t)env0 * N + lane;                               // global agent index
+    const uint32_t ge = a.env_offset + (uint32_t)e;                         // global env id (Philox counter)
+    const unsigned envmask = ((1u << N) - 1u) << (le * N);                  // lanes of this env
+
+    unsigned char* wr = smem_raw + (size_t)wib * LY::stride;
+    R2* s_pold = reinterpret_cast<R2*>(wr + LY::off_pold);
+    R2* s_pnew = reinterpret_cast<R2*>(wr + LY::off_pnew);
+    R2* s_cen = reinterpret_cast<R2*>(wr + LY::off_cen);
+    R2* s_shp = reinterpret_cast<R2*>(wr + LY::off_shp);
+    R2* s_vel = reinterpret_cast<R2*>(wr + LY::off_vel);
+    R2* s_mean = reinterpret_cast<R2*>(wr + LY::off_mean);
+    Bits* s_max = reinterpret_cast<Bits*>(wr + LY::off_max);
+    int* s_col = reinterpret_cast<int*>(wr + LY::off_col);
+
+    // The warp's observation span in HBM and its shared-memory image.  The image starts at the same
+    // offset modulo 16 as the span so that the 16-byte-aligned middle can go out as one bulk copy.
+    R2* g_obs = nullptr;
+    R2* s_obs = nullptr;
+    uint32_t obs_bytes = 0, obs_head = 0;
+    if (WOBS) {
+        g_obs = a.obs + (size_t)env0 * N * IPR;
+        obs_head = (uint32_t)((16u - ((uint32_t)(uintptr_t)g_obs & 15u)) & 15u);   // 0 or 8 (fp32), 0 (fp64)
+        s_obs = reinterpret_cast<R2*>(wr + LY::off_obs + ((16u - obs_head) & 15u));
+        obs_bytes = (uint32_t)(nval * N * IPR) * (uint32_t)sizeof(R2);
+    }
+
+    const R2 zero = O::make((T)0, (T)0);
+    R2 p = zero, v = zero, u = zero, S = zero, iv = zero;
+    int stp = 0;
+    if (active) {                                                           // coalesced: lane <-> consecutive agent
+        p = a.pos[g];
+        v = a.vel[g];
+        S = a.shape[g];
+        if (!a.random_actions) u = a.act[g];
+        iv = a.ivel[e];
+        if (a.step) stp = a.step[e];
+    }
+    if (lane < NA) s_shp[lane] = S;
+    bool bulk_pending = false;
+
+    for (int ts = 0; ts < a.n_steps; ++ts) {
+        if (lane < EPW) { s_max[lane] = 0; s_col[lane] = 0; }
+        if (lane < NA) s_pold[lane] = p;
+        __syncwarp();
+
+        // =============================== World.step (core.py:206-225) ===========================
+        if (active) {
+            if (a.random_actions) {                                         // test.py:20
+                U4 r = philox(a.seed, ge, (uint32_t)i, a.tick + (uint32_t)ts, kAction);
+                u = O::make(uniform_pm1<T>(r.x), uniform_pm1<T>(r.y));
+            }
+            // _set_action: u *= sensitivity (environment.py:216-221); apply_action_force:
+            // F = gain * u + noise (core.py:232-236)
+            T Fx = O::mul(a.gain, O::mul(u.x, a.sens));
+            T Fy = O::mul(a.gain, O::mul(u.y, a.sens));
+            if (a.u_noise > (T)0) {
+                U4 r = philox(a.seed, ge, (uint32_t)i, a.tick + (uint32_t)ts, kUNoise);
+                T n0, n1; normal_pair<T>(r.x, r.y, &n0, &n1);
+                Fx = O::add(Fx, O::mul(n0, a.u_noise));
+                Fy = O::add(Fy, O::mul(n1, a.u_noise));
+            }
+            // apply_environment_force (core.py:240-254).  Pass 1 (branch-free, unrolled): bit j of
+            // `near` <=> pair (i, j) is inside the contact cut-off (or its distance is NaN).
+            if (a.collide) {
+                const R2* ep = s_pold + le * N;
+                unsigned near = 0;
+#pragma unroll
+                for (int j = 0; j < N; ++j) {
+                    R2 q = ep[j];
+                    T dx = O::sub(p.x, q.x), dy = O::sub(p.y, q.y);
+                    T d2 = dx * dx + dy * dy;
+                    near |= (!(d2 >= a.cut2)) ? (1u << j) : 0u;             // !(>=) keeps NaN pairs
+                }
+                near &= ~(1u << i);
+                // Pass 2: the near pairs in ascending j -- the order in which the reference's a<b
+                // double loop adds contributions to agent i.
+                const T dmin = O::add(a.size, a.size);                      // core.py:307
+                while (near) {
+                    const int j = __ffs(near) - 1;
+                    near &= near - 1;
+                    R2 q = ep[j];
+                    T dx = (j < i) ? O::sub(q.x, p.x) : O::sub(p.x, q.x);   // delta = p_a - p_b, a < b
+                    T dy = (j < i) ? O::sub(q.y, p.y) : O::sub(p.y, q.y);
+                    T fx, fy;
+                    contact_force<T>(dx, dy, dmin, a.margin, a.cforce, &fx, &fy);
+                    if (j < i) { Fx = O::add(-fx, Fx); Fy = O::add(-fy, Fy); }   // equal masses: ratio 1
+                    else       { Fx = O::add(fx, Fx);  Fy = O::add(fy, Fy); }
+                }
+            }
+            // integrate_state (core.py:264-277); F / m with m == 1 is exact, skip the division
+            v.x = O::mul(v.x, a.keep); v.y = O::mul(v.y, a.keep);
+            T ax = a.mass_one ? Fx : O::div(Fx, a.mass);
+            T ay = a.mass_one ? Fy : O::div(Fy, a.mass);
+            v.x = O::add(v.x, O::mul(ax, a.dt));
+            v.y = O::add(v.y, O::mul(ay, a.dt));
+            if (a.has_vmax) {
+                T sp = O::sqrt_(O::sq2(v.x, v.y));
+                if (sp > a.vmax) {
+                    v.x = O::mul(O::div(v.x, sp), a.vmax);
+                    v.y = O::mul(O::div(v.y, sp), a.vmax);
+                }
+            }
+            p.x = O::add(p.x, O::mul(v.x, a.dt));
+            p.y = O::add(p.y, O::mul(v.y, a.dt));
+            // update_agent_state (core.py:279-286): silent agents -> c = 0
+            s_pnew[le * 2 * N + i] = p;
+            s_pnew[le * 2 * N + N + i] = p;
+            s_vel[lane] = v;
+            if (ts == a.n_steps - 1) {
+                a.pos[g] = p; a.vel[g] = v;
+                if (a.comm) a.comm[g] = zero;
+            }
+        }
+        // any non-finite position in an env makes its centroid, hence the whole shape term, NaN
+        const bool bad = !(fabs(p.x) < (T)INFINITY) || !(fabs(p.y) < (T)INFINITY);
+        const bool env_bad = (__ballot_sync(FULL, active && bad) & envmask) != 0u;
+        __syncwarp();
+
+        // ================= Scenario.reward on the NEW state (formation_hd_env.py:61-75; Q16) =====
+        // centroid and mean velocity: one lane per (env, {pos, vel}), summed in agent order like
+        // np.mean(axis=0)
+        if (lane < 2 * nval) {
+            const int qe = lane >> 1, which = lane & 1;
+            const R2* src = which ? (s_vel + qe * N) : (s_pnew + qe * 2 * N);
+            T sx = 0, sy = 0;
+#pragma unroll
+            for (int j = 0; j < N; ++j) { R2 q = src[j]; sx = O::add(sx, q.x); sy = O::add(sy, q.y); }
+            s_mean[lane] = O::make(O::div(sx, (T)N), O::div(sy, (T)N));
+        }
+        __syncwarp();
+        const R2 mp = s_mean[2 * le], mv = s_mean[2 * le + 1];
+        const R2 C = O::make(O::sub(p.x, mp.x), O::sub(p.y, mp.y));         // centred agent shape
+        if (lane < NA) s_cen[lane] = C;
+        if (WOBS && bulk_pending) {                                         // previous step's image is still being read
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            bulk_pending = false;
+        }
+        __syncwarp();
+
+        int col = 0;
+        if (active) {
+            const R2* eS = s_shp + le * N;
+            const R2* eC = s_cen + le * N;
+            const R2* eP = s_pnew + le * 2 * N + i;                         // eP[k] = agent (i + k) mod N
+            R2* row = WOBS ? (s_obs + lane * IPR) : nullptr;
+            T rowmin = (T)INFINITY, colmin = (T)INFINITY;
+            unsigned hit = 0;
+            if (WOBS) row[0] = v;                                           // p_vel
+#pragma unroll
+            for (int k = 0; k < N; ++k) {
+                // symmetric Hausdorff partials (formation_hd_env.py:64-66): row i = min_k |C_i - S_k|^2,
+                // column i = min_k |C_k - S_i|^2
+                R2 Sk = eS[k], Ck = eC[k];
+                rowmin = fmin(rowmin, O::sq2(O::sub(C.x, Sk.x), O::sub(C.y, Sk.y)));
+                colmin = fmin(colmin, O::sq2(O::sub(Ck.x, S.x), O::sub(Ck.y, S.y)));
+                if (WOBS) row[2 * N - 1 + k] = Sk;                          // ideal_shape.flatten()
+                if (k >= 1) {
+                    R2 q = eP[k];
+                    T dx = O::sub(q.x, p.x), dy = O::sub(q.y, p.y);         // other_pos (formation_hd_env.py:55)
+                    if (WOBS) {
+                        const int slot = (i + k < N) ? (i + k) : (i + k - N + 1);
+                        row[slot] = O::make(dx, dy);
+                    }
+                    T d2 = dx * dx + dy * dy;
+                    hit |= (d2 < a.rthr2_hi) ? (1u << k) : 0u;
+                }
+            }
+            if (WOBS) {
+#pragma unroll
+                for (int k = 0; k < N - 1; ++k) row[N + k] = zero;          // comm of the others (silent)
+                row[3 * N - 1] = iv;                                        // ideal_vel
+            }
+            // is_collision (formation_hd_env.py:71-74,119-121): exact test only for candidates
+            while (a.collide && hit) {
+                const int k = __ffs(hit) - 1;
+                hit &= hit - 1;
+                R2 q = eP[k];
+                if (O::norm2(O::sub(q.x, p.x), O::sub(q.y, p.y)) < a.rthr) ++col;
+            }
+            atomicMax(&s_max[le], O::bits(fmax(rowmin, colmin)));           // d2 >= 0: bit order == value order
+            if (col) atomicAdd(&s_col[le], col);
+        }
+        __syncwarp();
+
+        // ============ rewards, done, statistics (environment.py:126-138,172-177) ================
+        stp += 1;                                                           // environment.py:114
+        const bool dn = active && a.step && (stp >= a.world_length);
+        if (active) {
+            T form = -O::sqrt_(O::from_bits(s_max[le]));                    // -max(dH(C,S), dH(S,C))
+            if (env_bad) form = O::from_bits(~(Bits)0 >> 1);                // NaN, as the reference
+            T velr = O::norm2(O::sub(iv.x, mv.x), O::sub(iv.y, mv.y));      // formation_hd_env.py:68-69
+            T base = O::sub(form, velr);
+            T r = base;
+            for (int c = 0; c < col; ++c) r = O::sub(r, (T)1);              // rew -= 1 per collision
+            const int coltot = s_col[le];
+            // shared reward = sum_i r_i (environment.py:136): N*base - total collisions, in fp64
+            const double R = (double)N * (double)base - (double)coltot;
+            a.reward[g] = (T)R;
+            if (a.indiv) a.indiv[g] = r;
+            if (a.done) a.done[g] = (uint8_t)(a.step ? (stp >= a.world_length) : 0);
+            if (i == 0 && a.step) {
+                T ret = (T)R;
+                if (a.ep_return) { ret = a.ep_return[e] + (T)R; a.ep_return[e] = (dn && a.auto_reset) ? (T)0 : ret; }
+                int ec = coltot;
+                if (a.ep_coll) { ec += a.ep_coll[e]; a.ep_coll[e] = (dn && a.auto_reset) ? 0 : ec; }
+                if (dn && a.stats) {
+                    atomicAdd(&a.stats[0], 1.0);
+                    atomicAdd(&a.stats[1], (double)ret);
+                    atomicAdd(&a.stats[2], (double)ret * (double)ret);
+                    atomicAdd(&a.stats[3], (double)ec);
+                }
+            }
+        }
+
+        // ======== VecEnv auto-reset (env_wrappers.py:14-18; reset_world formation_hd_env.py:77-95)
+        if (a.auto_reset && __any_sync(FULL, dn)) {
+            const uint32_t tk = a.tick + (uint32_t)ts;
+            R2 lraw = zero;
+            if (dn) {
+                U4 r = philox(a.seed, ge, (uint32_t)i, tk, kResetAgent);
+                p = O::make(uniform_pm1<T>(r.x), uniform_pm1<T>(r.y));
+                v = zero;
+                U4 q = philox(a.seed, ge, (uint32_t)i, tk, kResetLandmark);
+                lraw = O::make(uniform_pm1<T>(q.x), uniform_pm1<T>(q.y));
+                U4 w = philox(a.seed, ge, 0u, tk, kResetIdealVel);
+                iv = O::make(uniform_pm1<T>(w.x), uniform_pm1<T>(w.y));
+                s_pold[lane] = lraw;                                        // scratch: pold is dead until the next step
+                s_pnew[le * 2 * N + i] = p;
+                s_pnew[le * 2 * N + N + i] = p;
+                if (i == 0) a.ivel[e] = iv;
+                stp = 0;
+            }
+            __syncwarp();
+            if (dn) {
+                const R2* raw = s_pold + le * N;
+                T sx = 0, sy = 0;
+                for (int j = 0; j < N; ++j) { sx = O::add(sx, raw[j].x); sy = O::add(sy, raw[j].y); }
+                S = O::make(O::sub(lraw.x, O::div(sx, (T)N)), O::sub(lraw.y, O::div(sy, (T)N)));   // :93
+                s_shp[lane] = S;
+                a.shape[g] = S;
+                if (ts == a.n_steps - 1) { a.pos[g] = p; a.vel[g] = v; }
+            }
+            __syncwarp();
+            if (WOBS && dn)                                                 // the RESET observation (env_wrappers.py:16-17)
+                fill_row_hd<T, N>(s_obs + lane * IPR, s_pnew + le * 2 * N + i, s_shp + le * N, p, v, iv, i);
+        }
+        if (active && i == 0 && a.step) a.step[e] = stp;
+
+        // ================= observation rows leave the SM as one bulk copy =======================
+        if (WOBS) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // generic-proxy writes -> async proxy
+            __syncwarp();
+            const uint32_t head = obs_head < obs_bytes ? obs_head : obs_bytes;
+            const uint32_t mid = (obs_bytes - head) & ~15u;
+            const uint32_t tail = obs_bytes - head - mid;                   // 0 or 8 (fp32)
+            if (lane == 0) {
+                if (mid) {
+                    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                                 :: "l"(reinterpret_cast<unsigned char*>(g_obs) + head),
+                                    "r"(smem_u32(reinterpret_cast<unsigned char*>(s_obs) + head)), "r"(mid)
+                                 : "memory");
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+            } else if (lane == 1) {
+                if (head) g_obs[0] = s_obs[0];
+            } else if (lane == 2) {
+                if (tail) {
+                    const uint32_t it = (head + mid) / (uint32_t)sizeof(R2);
+                    g_obs[it] = s_obs[it];
+                }
+            }
+            bulk_pending = true;
+        }
+    }
+    // the shared-memory image must outlive the bulk copy's reads
+    if (WOBS && bulk_pending && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+
+}  // namespace fg
