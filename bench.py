@@ -48,6 +48,8 @@ def parse():
     ap.add_argument("--dtype", default="f32", choices=["f32", "f64"])
     ap.add_argument("--no-obs", action="store_true", help="state+reward only (B_state accounting)")
     ap.add_argument("--e2e-steps", type=int, default=10)
+    ap.add_argument("--graph-steps", type=int, default=50,
+                    help="env steps per CUDA graph in the timed region (0 = plain per-step launches)")
     ap.add_argument("--cpu-seconds", type=float, default=3.0)
     ap.add_argument("--no-also", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -172,6 +174,7 @@ def workload_config(a, envs_per_unit, where):
                            a.episode_length),
             "scenario": a.scenario, "agents": a.agents, "envs_per_gpu": envs_per_unit if where == "gpu" else None,
             "episode_length": a.episode_length, "obs": not a.no_obs,
+            "launch": ("cuda graph of per-step launches" if a.graph_steps > 0 else "per-step launches") if where == "gpu" else None,
             "l2": "inputs larger than L2 (step traffic > 126 MB), no flush" if where == "gpu" else None}
 
 
@@ -211,9 +214,17 @@ def run_b200(a):
         one_step()
     torch.cuda.synchronize()
 
+    # ---- timed region 1 (-> value): EXACTLY K steps, replayed from a CUDA graph of per-step launches
+    # (random-policy kernel + fused step kernel per step; the Philox tick lives on the device so every
+    # replayed step draws fresh numbers).  Host cost per step ~0, so the number is the GPU's.
+    chunk = max(1, min(K, a.graph_steps))
+    while K % chunk:
+        chunk -= 1
+    graph = env.capture_steps(chunk) if a.graph_steps > 0 else None
+    if graph is not None:
+        graph.replay()
+    torch.cuda.synchronize()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ka = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
-    kb = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
         sampler.start()
@@ -221,16 +232,35 @@ def run_b200(a):
     launches0 = env.launches
     barrier(); torch.cuda.synchronize()
     ev0.record()
+    if graph is not None:
+        for _ in range(K // chunk):
+            graph.replay()
+    else:
+        for _ in range(K):
+            one_step()
+    ev1.record()
+    torch.cuda.synchronize(); barrier()
+    launches = 2 * K                                              # fg::k_random_actions + step kernel per step
+    ms = ev0.elapsed_time(ev1)
+
+    # ---- timed region 2 (-> roofline): the same K steps as per-step launches with CUDA events around
+    # every fused-step launch, on the launching stream.  A device-side sleep is queued first so that
+    # the host runs ahead and the kernels execute back to back (otherwise event-to-event time would
+    # include the host's submission gap, not the kernel).
+    ka = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    kb = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    er0, er1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda._sleep(int(2.0e9 * min(0.4, 250e-6 * K + 0.01)))
+    er0.record()
     for k in range(K):
         env.sample_actions()
         ka[k].record()
         env.step(env.actions)
         kb[k].record()
-    ev1.record()
+    er1.record()
     torch.cuda.synchronize(); barrier()
-    launches = env.launches - launches0
-    ms = ev0.elapsed_time(ev1)
-    # keep the sampler alive a little if the region was short, so it has samples under load
+    region2_ms = er0.elapsed_time(er1)
+    # keep the sampler alive a little if the regions were short, so it has samples under load
     clocks = None
     if sampler:
         t_extra = time.time()
@@ -303,11 +333,16 @@ def run_b200(a):
         traffic = tj.get(key, {}).get("dram_bytes_per_launch")
     except Exception:
         pass
-    roofline = {"bound": "hbm", "kernel": "fg::k_step<%s,hd,phys,obsrew> (fg_step_fused)" % a.dtype,
+    kname = ("fg::k_hd_warp<%s,%d,obs=%s> (fg_step_fused, warp-autonomous persistent kernel)"
+             % (a.dtype, N, "yes" if not a.no_obs else "no")) if (a.scenario == "formation_hd_env" and N in (3, 9, 27)) \
+        else "fg::k_step<%s> (fg_step_fused, tile kernel)" % a.dtype
+    roofline = {"bound": "hbm", "kernel": kname,
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "peak_source": peak_src, "kernel_ms": kernel_ms,
                 "algorithmic_bytes_per_env_step": env.bytes_per_env_step(),
-                "share_of_step": kernel_ms * K / ms}
+                "share_of_step": kernel_ms * K / region2_ms,
+                "timing": "CUDA events around each fused-step launch over a second K-step region of per-step "
+                          "launches (region 1, which gives `value`, replays the same launches from a CUDA graph)"}
 
     cpu_baseline = None
     if world == 1 and not a.no_cpu_baseline:
@@ -340,6 +375,7 @@ def also_configs(formation_gym, torch, device, dtype, peak):
     res = []
     for name, scen, N, E, steps, mode in (
             ("configs[1] hd N=9 E=4096 (launch-bound; per-step launches)", "formation_hd_env", 9, 4096, 500, "step"),
+            ("configs[1] hd N=9 E=4096 (CUDA graph of 25 per-step launches)", "formation_hd_env", 9, 4096, 40, "graph"),
             ("configs[1] hd N=9 E=4096 (in-kernel 25-step rollouts)", "formation_hd_env", 9, 4096, 40, "rollout"),
             ("configs[2] hd N=27 E=65536", "formation_hd_env", 27, 65536, 50, "step"),
             ("configs[3] hd N=243 E=1024 (one GPU's share of 8192)", "formation_hd_env", 243, 1024, 30, "step"),
@@ -351,10 +387,14 @@ def also_configs(formation_gym, torch, device, dtype, peak):
                                                  write_obs=(mode != "noobs"))
             env.reset()
 
+            graph = env.capture_steps(25) if mode == "graph" else None
+
             def run(n):
                 for _ in range(n):
                     if mode == "rollout":
                         env.rollout_random(25)
+                    elif mode == "graph":
+                        graph.replay()
                     else:
                         env.sample_actions(); env.step(env.actions)
             run(5)
@@ -362,7 +402,7 @@ def also_configs(formation_gym, torch, device, dtype, peak):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(); run(steps); e1.record(); torch.cuda.synchronize()
             ms = e0.elapsed_time(e1)
-            env_steps = steps * (25 if mode == "rollout" else 1)
+            env_steps = steps * (25 if mode in ("rollout", "graph") else 1)
             gbs = env.bytes_per_env_step() * E * env_steps / (ms * 1e-3) / 1e9
             res.append({"config": name, "agent_steps_per_s": E * N * env_steps / (ms * 1e-3),
                         "ms_per_env_step": ms / env_steps, "algorithmic_GBps": gbs, "hbm_frac": gbs / peak})

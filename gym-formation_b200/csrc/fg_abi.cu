@@ -55,6 +55,7 @@ int fill_args(fg::KArgs<T>& a, const fg_params* p, const fg_buffers* b, int scen
     a.shape = (R2*)b->ideal_shape; a.ivel = (R2*)b->ideal_vel; a.lm = (R2*)b->landmarks;
     a.step = b->step; a.obs = (R2*)b->obs; a.reward = (T*)b->reward; a.indiv = (T*)b->indiv;
     a.done = b->done; a.ep_return = (T*)b->ep_return; a.ep_coll = b->ep_collisions; a.stats = b->stats;
+    a.tick_dev = b->tick_dev;
     a.a_mass = (const T*)p->agent_mass; a.a_size = (const T*)p->agent_size_arr;
     a.a_accel = (const T*)p->agent_accel; a.a_vmax = (const T*)p->agent_max_speed;
     a.E = E; a.N = N; a.L = L;
@@ -126,39 +127,57 @@ int launch(const fg::KArgs<T>& a, int scenario, const fg_params* p, void* stream
 
 
 // ---- warp-autonomous fast path (fg_warp.cuh) ----------------------------------------------------
-// Warps per CTA: the choice that keeps the most warps resident per SM (occupancy API; shared
-// memory is the limiter: one observation-span image per warp), computed once per instantiation.
+// Resident CTAs per SM for w warps per CTA (occupancy API; shared memory is the limiter: one
+// observation-span image per warp).  Computed once per instantiation; all GPUs of a box are alike.
+struct WarpGeom { int ctas[4]; int best; int sms; };      // index: log2(w), w = 1, 2, 4, 8
+
 template <typename T, int N, bool WOBS>
-int warps_per_cta() {
-    static const int best = [] {
+const WarpGeom& warp_geom() {
+    static const WarpGeom geom = [] {
         typedef fg::WarpLayout<T, N, WOBS> LY;
-        int best_w = 1, best_res = -1;
-        for (int w = 8; w >= 1; w >>= 1) {
+        WarpGeom g_; g_.best = 0; g_.sms = 148;
+        int dev = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess)
+            cudaDeviceGetAttribute(&g_.sms, cudaDevAttrMultiProcessorCount, dev);
+        int best_res = -1;
+        for (int l = 3; l >= 0; --l) {
+            const int w = 1 << l;
             const size_t smem = (size_t)w * LY::stride;
+            g_.ctas[l] = 0;
             if (smem > 227 * 1024) continue;
             if (cudaFuncSetAttribute(fg::k_hd_warp<T, N, WOBS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)smem) != cudaSuccess) { cudaGetLastError(); continue; }
             int ctas = 0;
             if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, fg::k_hd_warp<T, N, WOBS>, 32 * w, smem)
                 != cudaSuccess) { cudaGetLastError(); continue; }
-            if (ctas * w > best_res) { best_res = ctas * w; best_w = w; }
+            g_.ctas[l] = ctas;
+            if (ctas * w > best_res) { best_res = ctas * w; g_.best = l; }
         }
-        return best_w;
+        return g_;
     }();
-    return best;
+    return geom;
 }
 
 template <typename T, int N, bool WOBS>
 int launch_warp_n(const fg::KArgs<T>& a, cudaStream_t st) {
     typedef fg::WarpLayout<T, N, WOBS> LY;
-    int w = warps_per_cta<T, N, WOBS>();
-    const int warps = (a.E + LY::EPW - 1) / LY::EPW;
-    while (w > 1 && (warps + w - 1) / w < 2 * 148) w >>= 1;        // small batches: spread over the SMs
+    const WarpGeom& gm = warp_geom<T, N, WOBS>();
+    const int spans = (a.E + LY::EPW - 1) / LY::EPW;
+    int l = gm.best;
+    while (l > 0 && (spans >> l) < 2 * gm.sms) --l;                // small batches: spread over the SMs
+    if (gm.ctas[l] < 1) return fail(FG_ERR_CUDA, "k_hd_warp does not fit on this device%s");
+    const int w = 1 << l;
     const size_t smem = (size_t)w * LY::stride;
     cudaError_t err = cudaFuncSetAttribute(fg::k_hd_warp<T, N, WOBS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            (int)smem);
     if (err != cudaSuccess) return fail(FG_ERR_CUDA, "cudaFuncSetAttribute failed: %s", cudaGetErrorString(err));
-    fg::k_hd_warp<T, N, WOBS><<<(warps + w - 1) / w, 32 * w, smem, st>>>(a);
+    // persistent warps: at most one resident wave; each warp walks spans gw, gw + nwarps, ...
+    int grid = (spans + w - 1) / w;
+    int wave = gm.sms * gm.ctas[l];
+    { const char* e_ = getenv("FG_WAVES"); if (e_) wave *= atoi(e_); }
+    if (grid > wave) grid = wave;
+    if ((grid * w) & 1) ++grid;                                    // even warp count (16-byte phase, fg_warp.cuh)
+    fg::k_hd_warp<T, N, WOBS><<<grid, 32 * w, smem, st>>>(a);
     err = cudaGetLastError();
     if (err != cudaSuccess) return fail(FG_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(err));
     return FG_OK;
@@ -259,12 +278,13 @@ int reset_impl(const fg_params* p, const fg_buffers* b, int scenario, int E, int
 }
 
 template <typename T>
-int random_actions_impl(void* act, int E, int N, uint64_t seed, uint32_t tick, uint32_t env_offset, void* stream) {
+int random_actions_impl(void* act, int E, int N, uint64_t seed, uint32_t tick, uint32_t env_offset,
+                        const uint32_t* tick_dev, void* stream) {
     if (!act || E < 1 || N < 1) return fail(FG_ERR_ARG, "fg_random_actions: bad argument%s");
     const size_t n = (size_t)E * N;
     const int grid = (int)((n + 255) / 256);
     fg::k_random_actions<T><<<grid, 256, 0, (cudaStream_t)stream>>>((typename fg::Ops<T>::R2*)act, E, N, seed, tick,
-                                                                   env_offset);
+                                                                   env_offset, tick_dev);
     cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess) return fail(FG_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(err));
     return FG_OK;
@@ -335,12 +355,13 @@ int fg_reset_f64(const fg_params* p, const fg_buffers* b, int scenario, int E, i
     return reset_impl<double>(p, b, scenario, E, N, L, mask, seed, tick, env_offset, stream);
 }
 
-int fg_random_actions(void* act, int E, int N, uint64_t seed, uint32_t tick, uint32_t env_offset, void* stream) {
-    return random_actions_impl<float>(act, E, N, seed, tick, env_offset, stream);
+int fg_random_actions(void* act, int E, int N, uint64_t seed, uint32_t tick, uint32_t env_offset,
+                      const uint32_t* tick_dev, void* stream) {
+    return random_actions_impl<float>(act, E, N, seed, tick, env_offset, tick_dev, stream);
 }
 int fg_random_actions_f64(void* act, int E, int N, uint64_t seed, uint32_t tick, uint32_t env_offset,
-                          void* stream) {
-    return random_actions_impl<double>(act, E, N, seed, tick, env_offset, stream);
+                          const uint32_t* tick_dev, void* stream) {
+    return random_actions_impl<double>(act, E, N, seed, tick, env_offset, tick_dev, stream);
 }
 
 }  // extern "C"

@@ -52,8 +52,22 @@ template <typename T> struct KArgs {
     int mass_one;                    // mass == 1: F / m is exact without the division
     int n_steps, random_actions, auto_reset;
     uint64_t seed; uint32_t tick; uint32_t env_offset;
+    uint32_t* tick_dev;              // (opt) [2]: device tick added to `tick`, arrival counter (CUDA graphs)
     WallT<T> walls[kMaxWalls];
 };
+
+// Device-side tick for CUDA-graph replays: every launch reads tick_dev[0] at its start; the LAST
+// arriving participant (CTA or warp) of a stepping kernel advances it by the number of env steps
+// the launch performed and re-arms the arrival counter tick_dev[1].
+__device__ __forceinline__ void tick_arrive(uint32_t* tick_dev, unsigned participants, int n_steps, bool leader) {
+    if (tick_dev && leader) {
+        __threadfence();
+        if (atomicAdd(&tick_dev[1], 1u) == participants - 1u) {
+            tick_dev[1] = 0u;
+            tick_dev[0] += (uint32_t)n_steps;
+        }
+    }
+}
 
 // ------------------------------------------------------------------------------------------------
 // get_entity_collision_force (core.py:289-322), both entities movable colliders (agents).
@@ -123,8 +137,11 @@ __global__ void __launch_bounds__(kBlock) k_step(const __grid_constant__ KArgs<T
     T* s_het = s_lmin + ((SCN == kScnBasic) ? EPC * L : 0);   // HET: mass,size,sens,gain,vmax [5N]
     int* s_col = reinterpret_cast<int*>(s_het + (HET ? 5 * N : 0));
     int* s_dn = s_col + EPC;                                  // episode-end flag per local env
+    __shared__ double s_stat[4];                              // episode statistics of this CTA's envs
+    if (threadIdx.x < 4) s_stat[threadIdx.x] = 0.0;
 
     const int t = threadIdx.x;
+    const uint32_t tick0 = a.tick + (a.tick_dev ? a.tick_dev[0] : 0u);   // read before the first barrier
     const int tile0 = blockIdx.x * EPC;                       // first env of this tile
     const int le = (int)fastdiv((uint32_t)t, a.magic_n);
     const int i = t - le * N;
@@ -181,7 +198,7 @@ __global__ void __launch_bounds__(kBlock) k_step(const __grid_constant__ KArgs<T
         if (PHYS) {
             if (active) {
                 if (a.random_actions) {                                     // test.py:20
-                    U4 r = philox(a.seed, ge, (uint32_t)i, a.tick + (uint32_t)ts, kAction);
+                    U4 r = philox(a.seed, ge, (uint32_t)i, tick0 + (uint32_t)ts, kAction);
                     u = O::make(uniform_pm1<T>(r.x), uniform_pm1<T>(r.y));
                 }
                 T m_i = HET ? s_het[i] : a.mass;
@@ -193,7 +210,7 @@ __global__ void __launch_bounds__(kBlock) k_step(const __grid_constant__ KArgs<T
                 T Fx = O::mul(gain, O::mul(u.x, sens));
                 T Fy = O::mul(gain, O::mul(u.y, sens));
                 if (a.u_noise > (T)0) {
-                    U4 r = philox(a.seed, ge, (uint32_t)i, a.tick + (uint32_t)ts, kUNoise);
+                    U4 r = philox(a.seed, ge, (uint32_t)i, tick0 + (uint32_t)ts, kUNoise);
                     T n0, n1; normal_pair<T>(r.x, r.y, &n0, &n1);
                     Fx = O::add(Fx, O::mul(n0, a.u_noise));
                     Fy = O::add(Fy, O::mul(n1, a.u_noise));
@@ -261,7 +278,7 @@ __global__ void __launch_bounds__(kBlock) k_step(const __grid_constant__ KArgs<T
                 if (!a.silent) {
                     c = uc;
                     if (a.c_noise > (T)0) {
-                        U4 r = philox(a.seed, ge, (uint32_t)i, a.tick + (uint32_t)ts, kCNoise);
+                        U4 r = philox(a.seed, ge, (uint32_t)i, tick0 + (uint32_t)ts, kCNoise);
                         T n0, n1; normal_pair<T>(r.x, r.y, &n0, &n1);
                         c.x = O::add(c.x, O::mul(n0, a.c_noise));
                         c.y = O::add(c.y, O::mul(n1, a.c_noise));
@@ -273,7 +290,7 @@ __global__ void __launch_bounds__(kBlock) k_step(const __grid_constant__ KArgs<T
                     if (a.comm) a.comm[g] = c;
                 }
             }
-            if (!OBSREW) return;
+            if (!OBSREW) { tick_arrive(a.tick_dev, gridDim.x, a.n_steps, t == 0); return; }
             __syncthreads();
         }
 
@@ -379,11 +396,11 @@ __global__ void __launch_bounds__(kBlock) k_step(const __grid_constant__ KArgs<T
                 if (a.ep_return) { ret = a.ep_return[e] + (T)R; a.ep_return[e] = (dn && a.auto_reset) ? (T)0 : ret; }
                 int ec = coltot;
                 if (a.ep_coll) { ec += a.ep_coll[e]; a.ep_coll[e] = (dn && a.auto_reset) ? 0 : ec; }
-                if (dn && a.stats) {
-                    atomicAdd(&a.stats[0], 1.0);
-                    atomicAdd(&a.stats[1], (double)ret);
-                    atomicAdd(&a.stats[2], (double)ret * (double)ret);
-                    atomicAdd(&a.stats[3], (double)ec);
+                if (dn && a.stats) {             // per-CTA accumulators; one set of global atomics per CTA below
+                    atomicAdd(&s_stat[0], 1.0);
+                    atomicAdd(&s_stat[1], (double)ret);
+                    atomicAdd(&s_stat[2], (double)ret * (double)ret);
+                    atomicAdd(&s_stat[3], (double)ec);
                 }
             }
         }
@@ -391,7 +408,7 @@ __global__ void __launch_bounds__(kBlock) k_step(const __grid_constant__ KArgs<T
         // ======== VecEnv auto-reset (env_wrappers.py:14-18; reset_world formation_hd_env.py:77-95)
         if (PHYS && a.auto_reset) {
             if (__syncthreads_or(dn ? 1 : 0)) {
-                const uint32_t tk = a.tick + (uint32_t)ts;
+                const uint32_t tk = tick0 + (uint32_t)ts;
                 R2 lraw = O::make((T)0, (T)0);
                 if (dn) {
                     U4 r = philox(a.seed, ge, (uint32_t)i, tk, kResetAgent);
@@ -503,6 +520,11 @@ __global__ void __launch_bounds__(kBlock) k_step(const __grid_constant__ KArgs<T
         // next step of an in-kernel rollout: the new positions become the old ones
         R2* tmp = s_old; s_old = s_new; s_new = tmp;
     }
+    if (OBSREW && a.stats) {
+        __syncthreads();
+        if (t < 4 && s_stat[0] != 0.0) atomicAdd(&a.stats[t], s_stat[t]);
+    }
+    if (PHYS) tick_arrive(a.tick_dev, gridDim.x, a.n_steps, t == 0);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -518,9 +540,10 @@ __global__ void k_reset(const __grid_constant__ KArgs<T> a, const uint8_t* __res
     if (mask && !mask[e]) return;
     const int N = a.N, L = a.L;
     const uint32_t ge = a.env_offset + (uint32_t)e;
+    const uint32_t tick0 = a.tick + (a.tick_dev ? a.tick_dev[0] : 0u);
     const R2 zero = O::make((T)0, (T)0);
     for (int i = 0; i < N; ++i) {
-        U4 r = philox(a.seed, ge, (uint32_t)i, a.tick, kResetAgent);
+        U4 r = philox(a.seed, ge, (uint32_t)i, tick0, kResetAgent);
         size_t g = (size_t)e * N + i;
         a.pos[g] = O::make(uniform_pm1<T>(r.x), uniform_pm1<T>(r.y));
         a.vel[g] = zero;
@@ -528,7 +551,7 @@ __global__ void k_reset(const __grid_constant__ KArgs<T> a, const uint8_t* __res
     }
     T sx = 0, sy = 0;
     for (int k = 0; k < L; ++k) {
-        U4 r = philox(a.seed, ge, (uint32_t)k, a.tick, kResetLandmark);
+        U4 r = philox(a.seed, ge, (uint32_t)k, tick0, kResetLandmark);
         R2 l = O::make(uniform_pm1<T>(r.x), uniform_pm1<T>(r.y));
         sx = O::add(sx, l.x); sy = O::add(sy, l.y);
         if (a.lm) a.lm[(size_t)e * L + k] = l;
@@ -536,11 +559,11 @@ __global__ void k_reset(const __grid_constant__ KArgs<T> a, const uint8_t* __res
     if (SCN == kScnHD) {
         T mx = O::div(sx, (T)N), my = O::div(sy, (T)N);
         for (int k = 0; k < N; ++k) {
-            U4 r = philox(a.seed, ge, (uint32_t)k, a.tick, kResetLandmark);
+            U4 r = philox(a.seed, ge, (uint32_t)k, tick0, kResetLandmark);
             a.shape[(size_t)e * N + k] =
                 O::make(O::sub(uniform_pm1<T>(r.x), mx), O::sub(uniform_pm1<T>(r.y), my));
         }
-        U4 w = philox(a.seed, ge, 0u, a.tick, kResetIdealVel);
+        U4 w = philox(a.seed, ge, 0u, tick0, kResetIdealVel);
         a.ivel[e] = O::make(uniform_pm1<T>(w.x), uniform_pm1<T>(w.y));
     }
     if (a.step) a.step[e] = 0;
@@ -551,9 +574,10 @@ __global__ void k_reset(const __grid_constant__ KArgs<T> a, const uint8_t* __res
 // Random policy act ~ U(-1,1) (test.py:20); same counters as the in-kernel rollout.
 template <typename T>
 __global__ void k_random_actions(typename Ops<T>::R2* __restrict__ act, int E, int N, uint64_t seed,
-                                 uint32_t tick, uint32_t env_offset) {
+                                 uint32_t tick, uint32_t env_offset, const uint32_t* __restrict__ tick_dev) {
     const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= (size_t)E * N) return;
+    if (tick_dev) tick += tick_dev[0];
     const uint32_t e = (uint32_t)(g / N), i = (uint32_t)(g - (size_t)e * N);
     U4 r = philox(seed, env_offset + e, i, tick, kAction);
     act[g] = Ops<T>::make(uniform_pm1<T>(r.x), uniform_pm1<T>(r.y));

@@ -8,7 +8,7 @@ import os
 
 from . import _build
 
-FG_ABI_VERSION = 1
+FG_ABI_VERSION = 2
 FG_MAX_AGENTS = 256
 FG_MAX_LANDMARKS = 256
 FG_MAX_WALLS = 8
@@ -53,7 +53,7 @@ class fg_buffers(C.Structure):
         ("ideal_shape", C.c_void_p), ("ideal_vel", C.c_void_p), ("landmarks", C.c_void_p),
         ("step", C.c_void_p), ("obs", C.c_void_p), ("reward", C.c_void_p), ("indiv", C.c_void_p),
         ("done", C.c_void_p), ("ep_return", C.c_void_p), ("ep_collisions", C.c_void_p),
-        ("stats", C.c_void_p),
+        ("stats", C.c_void_p), ("tick_dev", C.c_void_p),
     ]
 
 
@@ -89,7 +89,7 @@ def load():
             [P(fg_params), P(fg_buffers), I, I, I, I, I, I, I, U64, U32, U32, VP]
         getattr(lib, "fg_reset" + sfx).argtypes = \
             [P(fg_params), P(fg_buffers), I, I, I, I, VP, U64, U32, U32, VP]
-        getattr(lib, "fg_random_actions" + sfx).argtypes = [VP, I, I, U64, U32, U32, VP]
+        getattr(lib, "fg_random_actions" + sfx).argtypes = [VP, I, I, U64, U32, U32, VP, VP]
     for name in EXPORTS:
         if name != "fg_last_error":
             getattr(lib, name).restype = I

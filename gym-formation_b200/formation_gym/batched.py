@@ -16,7 +16,11 @@ import ctypes as C
 
 import torch
 
+import contextlib
+
 from . import _native as nat
+
+_NULL_CTX = contextlib.nullcontext()
 
 SCENARIOS = {"formation_hd_env": nat.FG_SCENARIO_HD, "basic_formation_env": nat.FG_SCENARIO_BASIC}
 # scenario defaults: agent size, episode length (formation_hd_env.py:13,26; basic_formation_env.py:18,
@@ -118,6 +122,11 @@ class BatchedFormationEnv:
         self.ep_collisions = torch.zeros(E, dtype=torch.int32, device=self.device)
         self.stats = torch.zeros(4, dtype=torch.float64, device=self.device)
         self.launches = 0                                        # kernels launched by this object
+        # device-side tick (CUDA graphs): [0] is added to the host tick, [1] is the kernels' arrival
+        # counter.  Stays zero -- and the host counter advances -- until use_device_tick(True).
+        self._tick_dev = torch.zeros(2, dtype=torch.int32, device=self.device)
+        self._device_tick = False
+        self._ext_bufs = None
         self._bufs = self._make_buffers()
 
     # ------------------------------------------------------------------ plumbing
@@ -133,15 +142,37 @@ class BatchedFormationEnv:
         b.reward, b.indiv, b.done = nat.ptr(self.reward), nat.ptr(self.indiv), nat.ptr(self._done_u8)
         b.ep_return, b.ep_collisions = nat.ptr(self.ep_return), nat.ptr(self.ep_collisions)
         b.stats = nat.ptr(self.stats)
+        b.tick_dev = nat.ptr(self._tick_dev) if self._device_tick else None
         return b
 
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
-    def _next_tick(self, n=1):
+    def _on_device(self):
+        """Context that makes ``self.device`` current; free when it already is (the common case --
+        one process per GPU), so a step costs one ctypes call on the host."""
+        if torch.cuda.current_device() == self.device.index:
+            return _NULL_CTX
+        return torch.cuda.device(self.device)
+
+    def _next_tick(self, n=1, stepping=False):
+        """Host part of the Philox tick.  While the device tick is on, the stepping kernels advance
+        ``_tick_dev[0]`` themselves and the host part stays frozen (total = host + device)."""
         t = self._tick
-        self._tick = (self._tick + n) & 0xFFFFFFFF
+        if not (stepping and self._device_tick):
+            self._tick = (self._tick + n) & 0xFFFFFFFF
         return t
+
+    def use_device_tick(self, on=True):
+        """Keep the step counter that seeds Philox on the DEVICE, so that a CUDA graph holding step
+        launches (whose kernel arguments are frozen at capture) draws fresh numbers on every replay.
+        Switching it off folds the device count back into the host counter (synchronises)."""
+        if not on and self._device_tick:
+            self._tick = (self._tick + int(self._tick_dev[0].item())) & 0xFFFFFFFF
+            self._tick_dev.zero_()
+        self._device_tick = bool(on)
+        self._bufs = self._make_buffers()           # the buffer block carries (or drops) the tick pointer
+        self._ext_bufs = None
 
     def _fn(self, name):
         return getattr(self._lib, name + self._sfx)
@@ -161,6 +192,7 @@ class BatchedFormationEnv:
         """MultiAgentEnv.seed (environment.py:106-110): None -> 1."""
         self.seed_value = (1 if seed is None else int(seed)) & 0xFFFFFFFFFFFFFFFF
         self._tick = 0
+        self._tick_dev.zero_()
 
     def reset(self, mask=None):
         """Scenario.reset_world + current_step = 0 for all (or masked) envs; returns obs [E,N,D]."""
@@ -169,7 +201,7 @@ class BatchedFormationEnv:
             m = torch.as_tensor(mask, device=self.device).to(torch.uint8).contiguous()
             if tuple(m.shape) != (self.E,):
                 raise ValueError("mask must have shape (E,)")
-        with torch.cuda.device(self.device):
+        with self._on_device():
             rc = self._fn("fg_reset")(C.byref(self.params), C.byref(self._bufs), self.scn, self.E, self.N,
                                       self.L, nat.ptr(m), self.seed_value, self._next_tick(),
                                       self.env_offset, self._stream())
@@ -181,7 +213,7 @@ class BatchedFormationEnv:
 
     def observe(self):
         """Recompute obs / reward / individual rewards from the current state (no stepping)."""
-        with torch.cuda.device(self.device):
+        with self._on_device():
             rc = self._fn("fg_obs_reward")(C.byref(self.params), C.byref(self._bufs), self.scn, self.E,
                                            self.N, self.L, self._stream())
             nat.check(rc, "fg_obs_reward")
@@ -192,9 +224,9 @@ class BatchedFormationEnv:
         """``World.step`` only (physics; no observation / reward / done)."""
         actions = self._check_actions(actions)
         b = self._make_buffers(act=actions)
-        with torch.cuda.device(self.device):
+        with self._on_device():
             rc = self._fn("fg_world_step")(C.byref(self.params), C.byref(b), self.E, self.N,
-                                           self.seed_value, self._next_tick(), self.env_offset,
+                                           self.seed_value, self._next_tick(1, True), self.env_offset,
                                            self._stream())
             nat.check(rc, "fg_world_step")
             self.launches += 1
@@ -203,10 +235,13 @@ class BatchedFormationEnv:
         """One fused env step.  Returns ``(obs[E,N,D], reward[E,N,1], done[E,N], info)`` with
         ``info['individual_reward'] [E,N]`` (environment.py:130).  Outputs are views of buffers
         owned by this object and are overwritten by the next step."""
-        actions = self._check_actions(actions)
+        if actions is not self.actions:
+            actions = self._check_actions(actions)
         b = self._bufs
         if actions.data_ptr() != self.actions.data_ptr():
-            b = self._make_buffers(act=actions)
+            if self._ext_bufs is None or self._ext_bufs[0] != actions.data_ptr():
+                self._ext_bufs = (actions.data_ptr(), self._make_buffers(act=actions))
+            b = self._ext_bufs[1]
         self._launch_fused(b, 1, 0)
         return self.obs, self.reward, self.done, {"individual_reward": self.indiv}
 
@@ -221,9 +256,11 @@ class BatchedFormationEnv:
         if not self.silent:
             raise nat.NativeError("sample_actions supports silent agents only")
         out = self.actions if out is None else out
-        with torch.cuda.device(self.device):
+        with self._on_device():
             rc = self._fn("fg_random_actions")(nat.ptr(out), self.E, self.N, self.seed_value,
-                                               self._tick, self.env_offset, self._stream())
+                                               self._tick, self.env_offset,
+                                               nat.ptr(self._tick_dev) if self._device_tick else None,
+                                               self._stream())
             nat.check(rc, "fg_random_actions")
             self.launches += 1
         return out
@@ -235,13 +272,43 @@ class BatchedFormationEnv:
         return self.obs, self.reward, self.done, {"individual_reward": self.indiv}
 
     def _launch_fused(self, bufs, n_steps, random_actions):
-        with torch.cuda.device(self.device):
+        with self._on_device():
             rc = self._fn("fg_step_fused")(C.byref(self.params), C.byref(bufs), self.scn, self.E, self.N,
                                            self.L, n_steps, random_actions, int(self.auto_reset),
-                                           self.seed_value, self._next_tick(n_steps), self.env_offset,
+                                           self.seed_value, self._next_tick(n_steps, True), self.env_offset,
                                            self._stream())
             nat.check(rc, "fg_step_fused")
             self.launches += 1
+
+    def capture_steps(self, n_steps=1, policy=None):
+        """Capture ``n_steps`` x (policy, fused env step) into ONE CUDA graph and return it; call
+        ``graph.replay()`` to run them.  ``policy=None`` is the random policy (test.py:20) written
+        into ``self.actions``; otherwise ``policy(env)`` is called during capture and must enqueue,
+        on the current stream, whatever fills ``self.actions`` from ``self.obs``.  Replays cost no
+        host work per step, which is what small batches (launch-bound per step) need.  Turns the
+        device tick on."""
+        self.use_device_tick(True)
+        torch.cuda.synchronize(self.device)
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+
+        def body():
+            for _ in range(int(n_steps)):
+                if policy is None:
+                    self.sample_actions()
+                else:
+                    policy(self)
+                self._launch_fused(self._bufs, 1, 0)
+
+        with torch.cuda.stream(side):          # warm-up outside capture (lazy module loading, statics)
+            self.sample_actions() if policy is None else policy(self)
+            self._launch_fused(self._bufs, 1, 0)
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        torch.cuda.synchronize(self.device)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            body()
+        return graph
 
     # ------------------------------------------------------------------ bookkeeping
     @property
@@ -276,12 +343,14 @@ class BatchedFormationEnv:
         for k in ("landmarks", "ideal_shape", "ideal_vel"):
             if getattr(self, k) is not None:
                 sd[k] = getattr(self, k).clone()
-        sd["rng"] = {"seed": self.seed_value, "tick": self._tick, "env_offset": self.env_offset}
+        sd["rng"] = {"seed": self.seed_value, "env_offset": self.env_offset,
+                     "tick": (self._tick + int(self._tick_dev[0].item())) & 0xFFFFFFFF}
         return sd
 
     def load_state_dict(self, sd):
         for k, v in sd.items():
             if k == "rng":
                 self.seed_value, self._tick, self.env_offset = v["seed"], v["tick"], v["env_offset"]
+                self._tick_dev.zero_()
             else:
                 getattr(self, k).copy_(v)

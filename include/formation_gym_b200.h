@@ -26,7 +26,7 @@
  *  - The caller's `act` buffer is never written (the reference's in-place `u *= sensitivity`
  *    on the caller's array, environment.py:216-221, is deliberately not reproduced).
  *  - RNG: counter-based Philox4x32-10, key = seed, counter = (global env id, agent, tick,
- *    purpose).  `env_offset` is the global index of env 0 of this buffer, so results do not
+ *    purpose); tick = the `tick` argument + fg_buffers.tick_dev[0] when that pointer is given.  `env_offset` is the global index of env 0 of this buffer, so results do not
  *    depend on launch geometry or on how envs are sharded over GPUs.  The caller supplies a
  *    fresh `tick` per call (e.g. a global step counter).  Parity with the reference's global
  *    MT19937 stream (np.random.*) is statistical only.
@@ -40,7 +40,7 @@
 extern "C" {
 #endif
 
-#define FG_ABI_VERSION 1
+#define FG_ABI_VERSION 2
 #define FG_MAX_AGENTS 256      /* one CTA holds at least one whole env; 3^5 = 243 fits */
 #define FG_MAX_LANDMARKS 256
 #define FG_MAX_WALLS 8
@@ -112,6 +112,11 @@ typedef struct fg_buffers {
     int32_t* ep_collisions;    /* (opt) [E] in/out running count of reward-collisions */
     double* stats;             /* (opt) [4] in/out: n_episodes, sum return, sum return^2,
                                   sum collisions -- updated atomically at episode ends */
+    uint32_t* tick_dev;        /* (opt) [2] in/out, zero-initialised by the caller: [0] is ADDED to the
+                                  `tick` argument of every entry point; fg_world_step / fg_step_fused
+                                  advance it by the number of env steps they ran ([1] is their arrival
+                                  counter).  Lets a CUDA graph of step launches be replayed with fresh
+                                  random numbers although its kernel arguments are frozen. */
 } fg_buffers;
 
 int fg_abi_version(void);
@@ -165,9 +170,9 @@ int fg_reset_f64(const fg_params* p, const fg_buffers* b, int scenario, int E, i
 /* Random policy: act[e,i,:] ~ U(-1,1) (test.py:20 -> Box.sample, environment.py:67-68), same
  * Philox stream the in-kernel rollout uses, so step-by-step and in-kernel rollouts agree. */
 int fg_random_actions(void* act, int E, int N, uint64_t seed, uint32_t tick, uint32_t env_offset,
-                      void* stream);
+                      const uint32_t* tick_dev, void* stream);
 int fg_random_actions_f64(void* act, int E, int N, uint64_t seed, uint32_t tick,
-                          uint32_t env_offset, void* stream);
+                          uint32_t env_offset, const uint32_t* tick_dev, void* stream);
 
 /* Launch geometry chosen for (N): envs per CTA and threads per CTA (for reporting/tests). */
 int fg_launch_geometry(int N, int* envs_per_cta, int* threads_per_cta);
