@@ -1,0 +1,243 @@
+"""CPU-only tests (no GPU, no compute calls into the CUDA library):
+  * the C-ABI shared library loads and exports every symbol include/formation_gym_b200.h declares,
+    and the ctypes mirror of its structs has the C compiler's layout;
+  * host logic of the drop-in facade: make_env signature, spaces, types (API contract frozen from
+    the unmodified reference in tests/golden/api_contract.json), loud failure without a device;
+  * the per-object loop port used as the timed CPU baseline agrees with the golden fixtures;
+  * multi-GPU plumbing on the gloo backend at world_size 2 (env-range sharding + stats all-reduce).
+"""
+import ctypes as C
+import json
+import os
+import re
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+HEADER = os.path.join(ROOT, "include", "formation_gym_b200.h")
+
+
+# ------------------------------------------------------------------ C ABI
+def _declared_symbols():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(fg_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    from formation_gym import _build, _native
+    _build.build()                                  # nvcc cross-compiles without a GPU
+    lib = C.CDLL(_native.lib_path())
+    syms = _declared_symbols()
+    assert len(syms) >= 14 and "fg_step_fused" in syms and "fg_step_fused_f64" in syms
+    for s in syms:
+        assert hasattr(lib, s), "missing export %s" % s
+    assert sorted(_native.EXPORTS) == syms          # the binding covers exactly the header
+    assert _native.load().fg_abi_version() == _native.FG_ABI_VERSION == 2
+
+
+def test_ctypes_structs_match_c_layout():
+    """Compile a 10-line C program against the header and compare sizeof/offsetof with ctypes."""
+    from formation_gym import _native
+    prog = r'''
+#include <stdio.h>
+#include <stddef.h>
+#include "formation_gym_b200.h"
+int main(void) {
+  printf("%zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(fg_params), sizeof(fg_buffers), sizeof(fg_wall),
+         offsetof(fg_params, has_accel), offsetof(fg_params, agent_mass), offsetof(fg_params, walls),
+         offsetof(fg_buffers, step), offsetof(fg_buffers, tick_dev));
+  return 0; }
+'''
+    with tempfile.TemporaryDirectory() as d:
+        src, exe = os.path.join(d, "l.c"), os.path.join(d, "l")
+        open(src, "w").write(prog)
+        subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), src, "-o", exe])
+        got = [int(x) for x in subprocess.check_output([exe]).split()]
+    P, B = _native.fg_params, _native.fg_buffers
+    want = [C.sizeof(P), C.sizeof(B), C.sizeof(_native.fg_wall), P.has_accel.offset, P.agent_mass.offset,
+            P.walls.offset, B.step.offset, B.tick_dev.offset]
+    assert got == want
+
+
+def test_bad_arguments_are_rejected_without_a_device():
+    """Argument validation happens before any CUDA call: status < 0 and a message, no exception."""
+    from formation_gym import _native as nat
+    lib = nat.load()
+    p, b = nat.make_params(), nat.fg_buffers()
+    rc = lib.fg_step_fused(C.byref(p), C.byref(b), nat.FG_SCENARIO_HD, 4, 2, 2, 1, 0, 0, 0, 0, 0, None)
+    assert rc == -1 and b"N >= 3" in lib.fg_last_error()
+    rc = lib.fg_step_fused(C.byref(p), C.byref(b), nat.FG_SCENARIO_HD, 4, 300, 300, 1, 0, 0, 0, 0, 0, None)
+    assert rc == -1 and b"FG_MAX_AGENTS" in lib.fg_last_error()
+    rc = lib.fg_step_fused(C.byref(p), C.byref(b), nat.FG_SCENARIO_HD, 4, 9, 9, 1, 0, 0, 0, 0, 0, None)
+    assert rc == -1 and b"non-null" in lib.fg_last_error()
+    rc = lib.fg_reset(None, None, 0, 1, 3, 3, None, 0, 0, 0, None)
+    assert rc == -1
+    epc, thr = nat.launch_geometry(243)
+    assert (epc, thr) == (1, 256)
+    with pytest.raises(nat.NativeError):
+        nat.ptr(__import__("torch").zeros(3))       # CPU tensors are refused: no CPU path
+
+
+# ------------------------------------------------------------------ facade host logic
+@pytest.mark.parametrize("scenario,n", [("formation_hd_env", 9), ("basic_formation_env", 3)])
+def test_api_contract_static(scenario, n):
+    import formation_gym
+    from formation_gym import _native as nat
+    want = json.load(open(os.path.join(GOLD, "api_contract.json")))["api"][scenario]
+    np.random.seed(0)
+    env = formation_gym.make_env(scenario, False, n)
+    assert env.num_agents == want["num_agents"] == len(env.agents)
+    assert len(env.world.landmarks) == want["n_landmarks"]
+    assert env.world_length == want["world_length"]
+    assert env.shared_reward == want["shared_reward"]
+    assert env.world.dim_c == want["dim_c"]
+    assert abs(env.world.agents[0].size - want["agent_size"]) < 1e-12
+    assert list(env.observation_space[0].shape) == want["obs_space_shape"]
+    assert list(env.share_observation_space[0].shape) == want["share_obs_space_shape"]
+    assert list(env.action_space[0].shape) == want["action_shape"]
+    assert float(env.action_space[0].low[0]) == want["action_low"]
+    assert float(env.action_space[0].high[0]) == want["action_high"]
+    a = env.action_space[0].sample()
+    assert a.shape == (2,) and a.dtype == np.float32 and np.all(np.abs(a) <= 1)
+    # README's 4-argument form (README.md:61)
+    env4 = formation_gym.make_env(scenario, False, n, 25)
+    assert env4.world_length == 25
+    # reset_world ran on the host RNG like the reference: agents in [-1, 1]^2, zero velocity
+    for ag in env.world.agents:
+        assert np.all(np.abs(ag.state.p_pos) <= 1) and np.all(ag.state.p_vel == 0)
+    # the step path has no CPU fallback: without a CUDA device it must fail loudly
+    import torch
+    if not torch.cuda.is_available():
+        with pytest.raises((nat.NativeError, RuntimeError)):
+            env.step([np.zeros(2) for _ in range(n)])
+
+
+def test_make_env_rejects_unknown_scenarios_and_small_hd():
+    import formation_gym
+    with pytest.raises(ValueError):
+        formation_gym.make_env("formation_hd_obs_env", False, 9)
+    with pytest.raises(Exception):
+        formation_gym.make_env("formation_hd_env", False, 2)      # formation_hd_env.py:58 needs N >= 3
+
+
+def test_product_package_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "gym-formation_b200")
+    for dp, _, fs in os.walk(pkg):
+        for f in fs:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dp, f)).read()
+                assert "import oracle" not in txt and "from oracle" not in txt, os.path.join(dp, f)
+
+
+# ------------------------------------------------------------------ CPU-baseline port vs golden
+def _port_from_state(scenario, pos, vel, extra, world_length):
+    from oracle import ref_loop_port as rp
+    n = pos.shape[0]
+    np.random.seed(0)
+    env = rp.RefLoopEnv(scenario, n, world_length, num_landmarks=(extra["lm"].shape[0] if "lm" in extra else 3))
+    for a, p, v in zip(env.agents, pos, vel):
+        a.pos, a.vel = p.copy(), v.copy()
+    if scenario == "formation_hd_env":
+        env.ideal_shape, env.ideal_vel = extra["shape"].copy(), extra["ivel"].copy()
+        for l, p in zip(env.landmarks, extra["lm"]):
+            l.pos = p.copy()
+    else:
+        for l, p in zip(env.landmarks, extra["lm"]):
+            l.pos = p.copy()
+    return env
+
+
+@pytest.mark.parametrize("name", ["hd_n9_clustered.npz", "hd_n3_spread.npz", "hd_n27_clustered.npz"])
+def test_loop_port_matches_golden_hd(name):
+    g = dict(np.load(os.path.join(GOLD, name)))
+    for e in range(min(4, g["pos0"].shape[0])):
+        env = _port_from_state("formation_hd_env", g["pos0"][e], g["vel0"][e],
+                               dict(shape=g["shape"][e], ivel=g["ivel"][e], lm=g["lm0"][e]), 25)
+        env.current_step = int(g["step0"][e])
+        obs_n, rew_n, done_n, info_n = env.step(list(g["act"][e]))
+        P = np.stack([a.pos for a in env.agents]); V = np.stack([a.vel for a in env.agents])
+        assert np.abs(P - g["pos"][e]).max() <= 1e-12 and np.abs(V - g["vel"][e]).max() <= 1e-12
+        rows = g["obs_rows"] if "obs_rows" in g else np.arange(P.shape[0])
+        assert np.abs(np.stack(obs_n)[rows] - g["obs"][e]).max() <= 1e-12
+        ind = np.array([i["individual_reward"] for i in info_n])
+        assert np.abs(ind - g["indiv"][e]).max() <= 1e-10
+        assert abs(rew_n[0][0] - g["reward"][e][0]) <= 1e-9
+        assert rew_n[0] is rew_n[-1]                    # [[R]] * N aliases one list (environment.py:138)
+        assert list(done_n) == list(g["done"][e])
+
+
+def test_loop_port_matches_golden_basic():
+    g = dict(np.load(os.path.join(GOLD, "basic_n3_clustered.npz")))
+    for e in range(min(4, g["pos0"].shape[0])):
+        env = _port_from_state("basic_formation_env", g["pos0"][e], g["vel0"][e], dict(lm=g["lm0"][e]), 25)
+        env.current_step = int(g["step0"][e])
+        obs_n, rew_n, done_n, info_n = env.step(list(g["act"][e]))
+        P = np.stack([a.pos for a in env.agents])
+        assert np.abs(P - g["pos"][e]).max() <= 1e-12
+        assert np.abs(np.stack(obs_n) - g["obs"][e]).max() <= 1e-12
+        ind = np.array([i["individual_reward"] for i in info_n])
+        assert np.abs(ind - g["indiv"][e]).max() <= 1e-10
+
+
+# ------------------------------------------------------------------ multi-process plumbing (gloo)
+def test_shard_range_partitions_exactly():
+    from formation_gym.distributed import shard_range
+    for total in (0, 1, 7, 8, 1000003, 1 << 20):
+        for world in (1, 2, 3, 8):
+            spans = [shard_range(total, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == total
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [hi - lo for lo, hi in spans]
+            assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        shard_range(10, 2, 2)
+
+
+_GLOO_WORKER = r'''
+import os, sys, json
+sys.path.insert(0, os.path.join(%(root)r, "gym-formation_b200"))
+import torch, torch.distributed as dist
+from formation_gym import distributed as fgd
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo", rank=rank, world_size=world)
+lo, hi = fgd.shard_range(1001, rank, world)
+# per-rank statistics as the step kernels would leave them: [episodes, sum R, sum R^2, sum collisions]
+R = torch.arange(lo, hi, dtype=torch.float64) * 0.5 - 100.0
+stats = torch.stack([torch.tensor(float(hi - lo), dtype=torch.float64), R.sum(), (R * R).sum(),
+                     torch.tensor(float(3 * (hi - lo)), dtype=torch.float64)])
+out = fgd.all_reduce_stats(stats.clone())
+if rank == 0:
+    print(json.dumps({"lo_hi": [lo, hi], "stats": out.tolist(), "summary": fgd.summarize(out)}))
+dist.destroy_process_group()
+'''
+
+
+def test_gloo_world_size_2_stats_allreduce():
+    """One process per rank over gloo: contiguous env ranges, all-reduced statistics equal the
+    single-process sums (the only collective of the design; NCCL does the same on GPUs)."""
+    import socket
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    with tempfile.TemporaryDirectory() as d:
+        script = os.path.join(d, "w.py")
+        open(script, "w").write(_GLOO_WORKER % {"root": ROOT})
+        procs = []
+        for r in range(2):
+            env = dict(os.environ, RANK=str(r), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+            procs.append(subprocess.Popen([sys.executable, script], env=env, stdout=subprocess.PIPE,
+                                          stderr=subprocess.PIPE, text=True))
+        outs = [p.communicate(timeout=180) for p in procs]
+        for p, (o, e) in zip(procs, outs):
+            assert p.returncode == 0, e[-2000:]
+    res = json.loads(outs[0][0].strip().splitlines()[-1])
+    R = np.arange(1001, dtype=np.float64) * 0.5 - 100.0
+    assert res["lo_hi"] == [0, 501]
+    assert res["stats"][0] == 1001 and res["stats"][3] == 3003
+    assert abs(res["stats"][1] - R.sum()) < 1e-6 and abs(res["stats"][2] - (R * R).sum()) < 1e-3
+    assert abs(res["summary"]["return_mean"] - R.mean()) < 1e-9
+    assert abs(res["summary"]["return_std"] - R.std()) < 1e-6

@@ -1,0 +1,140 @@
+"""Drop-in API tests on the GPU: ``formation_gym.make_env(...).reset()/step()`` (the reference's
+public API, formation_gym/__init__.py:6-17 + environment.py:113-156) driven like test.py drives it,
+checked against trajectories frozen from the UNMODIFIED reference (tests/golden/*_traj25.npz) and
+against the API contract (types, lengths, aliasing) in tests/golden/api_contract.json.
+
+The facade computes in fp64 (like the reference), so the 25-step bar is 1e-9.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+import formation_gym  # noqa: E402
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def load(name):
+    return dict(np.load(os.path.join(GOLD, name)))
+
+
+def inject(env, g, scenario):
+    for a, p, v in zip(env.world.agents, g["pos0"], g["vel0"]):
+        a.state.p_pos, a.state.p_vel = p.copy(), v.copy()
+        a.state.c = np.zeros(env.world.dim_c)
+    sc = env.observation_callback.__self__
+    if scenario == "formation_hd_env":
+        sc.ideal_shape, sc.ideal_vel = g["shape"].copy(), g["ivel"].copy()
+    else:
+        for l, p in zip(env.world.landmarks, g["lm0"]):
+            l.state.p_pos = p.copy()
+    env.current_step = 0
+
+
+@pytest.mark.parametrize("scenario,name,n", [("formation_hd_env", "hd_n9_traj25.npz", 9),
+                                             ("formation_hd_env", "hd_n27_traj25.npz", 27),
+                                             ("basic_formation_env", "basic_n3_traj25.npz", 3)])
+def test_make_env_step_matches_reference_trajectory(scenario, name, n):
+    g = load(name)
+    want = json.load(open(os.path.join(GOLD, "api_contract.json")))["api"][scenario]
+    np.random.seed(3)
+    env = formation_gym.make_env(scenario, False, n, 100)
+    obs_n = env.reset()
+    assert isinstance(obs_n, list) and len(obs_n) == n and obs_n[0].shape == tuple(env.observation_space[0].shape)
+    inject(env, g, scenario)
+    worst = 0.0
+    for t in range(g["acts"].shape[0]):
+        acts = [g["acts"][t][i].copy() for i in range(n)]
+        keep = [a.copy() for a in acts]
+        obs_n, reward_n, done_n, info_n = env.step(acts)
+        # types and structure (environment.py:126-142)
+        assert isinstance(obs_n, list) and len(obs_n) == n
+        assert obs_n[0].dtype == np.dtype(want["obs_dtype"]) == np.float64
+        assert obs_n[0].shape == tuple(env.observation_space[0].shape)
+        assert isinstance(reward_n, list) and isinstance(reward_n[0], list) and len(reward_n[0]) == 1
+        assert reward_n[0] is reward_n[-1]                       # [[R]] * N aliases one inner list
+        assert all(type(d) is bool for d in done_n) and not any(done_n)
+        assert sorted(info_n[0].keys()) == want["info_keys"]
+        assert all(np.array_equal(a, k) for a, k in zip(acts, keep))   # caller's actions untouched (Q4)
+        P = np.stack([a.state.p_pos for a in env.world.agents])
+        V = np.stack([a.state.p_vel for a in env.world.agents])
+        ind = np.array([i["individual_reward"] for i in info_n])
+        worst = max(worst, np.abs(P - g["pos"][t]).max(), np.abs(V - g["vel"][t]).max(),
+                    np.abs(ind - g["indiv"][t]).max())
+        assert abs(reward_n[0][0] - g["reward"][t][0]) <= 1e-9 * max(1.0, abs(g["reward"][t][0]))
+    O = np.stack(obs_n)
+    rows = g["obs_rows"] if "obs_rows" in g else np.arange(n)
+    worst = max(worst, np.abs(O[rows] - g["obs_last"]).max())
+    assert env.current_step == g["acts"].shape[0]
+    print("%s N=%d facade 25-step max abs err %.3e" % (scenario, n, worst))
+    assert worst <= 1e-9
+
+
+def test_done_and_reset_like_test_py():
+    """test.py:14-28 loop: random policy, reset when all done; done flips at world_length."""
+    np.random.seed(5)
+    env = formation_gym.make_env("formation_hd_env", False, 9, 4)
+    env.seed(5)
+    env.reset()
+    for t in range(1, 10):
+        act_n = [space.sample() for space in env.action_space]
+        obs_n, reward_n, done_n, info_n = env.step(act_n)
+        assert all(d == (env.current_step >= 4) for d in done_n)
+        if np.all(done_n):
+            obs_n = env.reset()
+            assert env.current_step == 0
+            assert all(np.all(a.state.p_vel == 0) for a in env.world.agents)
+
+
+def test_scenario_hooks_serve_kernel_results():
+    """The per-agent hooks (Scenario.observation / reward) evaluate on the GPU and equal what the
+    fused env.step reports for the same state; the hd landmark shift side effect is reproduced
+    (formation_hd_env.py:40-44)."""
+    np.random.seed(9)
+    env = formation_gym.make_env("formation_hd_env", False, 9, 25)
+    env.reset()
+    sc = env.observation_callback.__self__
+    obs_n, reward_n, done_n, info_n = env.step([s.sample() for s in env.action_space])
+    for i, ag in enumerate(env.world.agents):
+        assert np.allclose(sc.observation(ag, env.world), obs_n[i], atol=1e-12)
+        assert abs(sc.reward(ag, env.world) - info_n[i]["individual_reward"]) <= 1e-12
+    P = np.stack([a.state.p_pos for a in env.world.agents])
+    L = np.stack([l.state.p_pos for l in env.world.landmarks])
+    assert np.abs(P.mean(0) - L.mean(0)).max() <= 1e-12
+    assert np.abs((L - L.mean(0)) - sc.ideal_shape).max() <= 1e-9
+
+
+def test_custom_callbacks_use_gpu_world_step():
+    """User-supplied reward/observation hooks (the plugin API): physics still runs in the kernel
+    (World.step), the hooks are called like the reference does (environment.py:126-134)."""
+    from formation_gym.environment import MultiAgentEnv
+    from formation_gym.envs.formation_hd_env import Scenario
+    np.random.seed(1)
+    sc = Scenario()
+    world = sc.make_world(5, 10)
+    calls = {"r": 0}
+
+    def reward(agent, w):
+        calls["r"] += 1
+        return -float(np.sum(np.square(agent.state.p_pos)))
+
+    def observation(agent, w):
+        return np.concatenate([agent.state.p_vel, agent.state.p_pos])
+
+    env = MultiAgentEnv(world, sc.reset_world, reward, observation)
+    env.reset()
+    p0 = np.stack([a.state.p_pos for a in world.agents]); v0 = np.stack([a.state.p_vel for a in world.agents])
+    acts = [np.array([0.3, -0.2]) for _ in range(5)]
+    obs_n, reward_n, done_n, info_n = env.step(acts)
+    assert calls["r"] == 5 and obs_n[0].shape == (4,)
+    # free flight (agents far apart with overwhelming probability): v' = v*0.75 + 5*a*0.1; p' = p + v'*0.1
+    v1 = v0 * 0.75 + np.array([1.5, -1.0]) * 0.1
+    far = np.min(np.linalg.norm(p0[:, None] - p0[None] + np.eye(5)[..., None] * 9, axis=-1)) > 0.2
+    if far:
+        assert np.abs(np.stack([a.state.p_vel for a in world.agents]) - v1).max() <= 1e-12
+        assert np.abs(np.stack([a.state.p_pos for a in world.agents]) - (p0 + v1 * 0.1)).max() <= 1e-12
+    assert abs(reward_n[0][0] - sum(i["individual_reward"] for i in info_n)) <= 1e-12
