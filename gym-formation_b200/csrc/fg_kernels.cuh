@@ -50,11 +50,41 @@ template <typename T> struct KArgs {
     T rthr, rthr2_hi;                // reward collision threshold and its guarded square
     int has_accel, has_vmax, collide, silent, world_length, n_walls, prescaled;
     int mass_one;                    // mass == 1: F / m is exact without the division
+    int row_tma;                     // tile kernel: long hd rows leave through TMA bulk stores (see k_step)
     int n_steps, random_actions, auto_reset;
     uint64_t seed; uint32_t tick; uint32_t env_offset;
     uint32_t* tick_dev;              // (opt) [2]: device tick added to `tick`, arrival counter (CUDA graphs)
     WallT<T> walls[kMaxWalls];
 };
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+
+// One contiguous piece of an observation row, smem image -> HBM: the 16-byte-aligned middle as a TMA
+// bulk store (cp.async.bulk, L2 evict_first; the caller commits the group), an odd 8-byte head / tail
+// item as plain stores.  `img` holds the piece at the same offset modulo 16 as `dst`.
+// Called by a whole warp: lane 0 issues the bulk copy, lanes 1 and 2 the head / tail items.
+template <typename R2>
+__device__ __forceinline__ void row_piece_store(R2* dst, const R2* img, uint32_t bytes, int lane) {
+    const uint32_t head = min((uint32_t)((16u - ((uint32_t)(uintptr_t)dst & 15u)) & 15u), bytes);
+    const uint32_t mid = (bytes - head) & ~15u;
+    const uint32_t tail = bytes - head - mid;
+    if (lane == 0) {
+        if (mid) {
+            uint64_t pol;
+            asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;"
+                         :: "l"(reinterpret_cast<unsigned char*>(dst) + head),
+                            "r"(smem_u32(reinterpret_cast<const unsigned char*>(img) + head)), "r"(mid), "l"(pol)
+                         : "memory");
+        }
+    } else if (lane == 1) {
+        if (head) dst[0] = img[0];
+    } else if (lane == 2) {
+        if (tail) { const uint32_t it = (head + mid) / (uint32_t)sizeof(R2); dst[it] = img[it]; }
+    }
+}
 
 // Device-side tick for CUDA-graph replays: every launch reads tick_dev[0] at its start; the LAST
 // arriving participant (CTA or warp) of a stepping kernel advances it by the number of env steps
@@ -115,8 +145,11 @@ __device__ __forceinline__ void wall_force(const WallT<T>& w, T px, T py, T size
 // ------------------------------------------------------------------------------------------------
 // The fused kernel.  PHYS: run World.step.  OBSREW: run observation/reward/done.  HET: per-agent
 // mass/size/accel/max_speed arrays (otherwise the scalar fast path).
-template <typename T, int SCN, bool PHYS, bool OBSREW, bool HET>
-__global__ void __launch_bounds__(kBlock) k_step(const __grid_constant__ KArgs<T> a) {
+// OM selects the observation writer (one per instantiation keeps registers low): 0 = flat item loop
+// (short rows), 1 = one warp per row with plain streaming stores, 2 = one warp per row, static row part
+// bulk-stored from a shared image (hd, silent agents, long rows).
+template <typename T, int SCN, bool PHYS, bool OBSREW, bool HET, int OM>
+__global__ void __launch_bounds__(kBlock, (OM == 2) ? 4 : 3) k_step(const __grid_constant__ KArgs<T> a) {
     typedef Ops<T> O;
     typedef typename O::R2 R2;
     typedef typename O::Bits Bits;
@@ -125,18 +158,27 @@ __global__ void __launch_bounds__(kBlock) k_step(const __grid_constant__ KArgs<T
     const int N = a.N, EPC = a.EPC, L = a.L;
     const int nA = EPC * N;
     const int nS = (SCN == kScnHD) ? nA : EPC * L;
-    R2* s_old = reinterpret_cast<R2*>(smem_raw);      // positions the contact force reads
+    // row-TMA region (OM == 2): per local env two images of the row's static part
+    // [comm zeros (N-1) | ideal_shape (N) | ideal_vel], one per 16-byte phase, then one staging
+    // buffer per warp for a row's dynamic part [p_vel | other_pos (N-1)].
+    const int rt_img = 2 * N + 1;                     // items per static image incl. one pad item
+    const int rt_dyn = (N + 3) & ~1;                  // items per staging buffer (16-byte multiple)
+    R2* s_rt_img = reinterpret_cast<R2*>(smem_raw);
+    R2* s_rt_dyn = s_rt_img + (OM == 2 ? 2 * rt_img * EPC : 0);
+    R2* s_old = s_rt_dyn + (OM == 2 ? 2 * rt_dyn * (kBlock / 32) : 0);   // positions the contact force reads
     R2* s_new = s_old + nA;                           // positions after integration
     R2* s_v = s_new + nA;                             // velocities after integration
     R2* s_s = s_v + nA;                               // hd: centred ideal shape; basic: landmarks
     R2* s_c = s_s + nS;                               // comm state
     R2* s_iv = s_c + nA;                              // hd: ideal velocity per env
-    Bits* s_rowmax = reinterpret_cast<Bits*>(s_iv + EPC);
-    Bits* s_colmax = s_rowmax + EPC;
-    T* s_lmin = reinterpret_cast<T*>(s_colmax + EPC);         // basic: min_a |p_a - l_k| [EPC*L]
+    R2* s_mean = s_iv + EPC;                          // hd: [EPC][2] centroid, mean velocity
+    R2* s_cen = s_mean + 2 * EPC;                     // hd: centred new positions [nA]
+    Bits* s_rowmax = reinterpret_cast<Bits*>(s_cen + ((SCN == kScnHD) ? nA : 0));   // max of the Hausdorff minima
+    T* s_lmin = reinterpret_cast<T*>(s_rowmax + EPC);         // basic: min_a |p_a - l_k| [EPC*L]
     T* s_het = s_lmin + ((SCN == kScnBasic) ? EPC * L : 0);   // HET: mass,size,sens,gain,vmax [5N]
     int* s_col = reinterpret_cast<int*>(s_het + (HET ? 5 * N : 0));
     int* s_dn = s_col + EPC;                                  // episode-end flag per local env
+    int* s_bad = s_dn + EPC;                                  // env has a non-finite position (NaN quirk, Q9)
     __shared__ double s_stat[4];                              // episode statistics of this CTA's envs
     if (threadIdx.x < 4) s_stat[threadIdx.x] = 0.0;
 
@@ -191,7 +233,7 @@ __global__ void __launch_bounds__(kBlock) k_step(const __grid_constant__ KArgs<T
     }
 
     for (int ts = 0; ts < a.n_steps; ++ts) {
-        if (OBSREW && t < EPC) { s_rowmax[t] = 0; s_colmax[t] = 0; s_col[t] = 0; }
+        if (OBSREW && t < EPC) { s_rowmax[t] = 0; s_col[t] = 0; s_bad[t] = 0; }
         __syncthreads();
 
         // =============================== World.step (core.py:206-225) ===========================
@@ -219,37 +261,69 @@ __global__ void __launch_bounds__(kBlock) k_step(const __grid_constant__ KArgs<T
                 // i in ascending order of the other index, exactly the reference's order.
                 if (a.collide) {
                     const R2* envp = s_old + le * N;
-                    for (int j = 0; j < N; ++j) {
-                        if (j == i) continue;
-                        R2 q = envp[j];
-                        T dx = (j < i) ? O::sub(q.x, p.x) : O::sub(p.x, q.x);   // delta = p_a - p_b, a<b
-                        T dy = (j < i) ? O::sub(q.y, p.y) : O::sub(p.y, q.y);
-                        T d2 = dx * dx + dy * dy;
-                        T dmin, cut2;
-                        if (HET) {
-                            dmin = O::add((j < i) ? s_het[N + j] : size_i, (j < i) ? size_i : s_het[N + j]);
-                            T c = dmin + a.kcut * a.margin; cut2 = c * c;
-                        } else {
-                            dmin = O::add(a.size, a.size);                       // core.py:307
-                            cut2 = a.cut2;
-                        }
-                        // Far pairs: softplus(-(d-dmin)/k) < exp(-kcut) -- below the rounding of F
-                        // (DESIGN.md "contact cut-off").  !(>=) keeps NaN positions propagating.
-                        if (!(d2 >= cut2)) {
-                            T fx, fy;
-                            contact_force<T>(dx, dy, dmin, a.margin, a.cforce, &fx, &fy);
-                            if (HET) {
-                                T m_j = s_het[j];
-                                if (j < i) {       // i is entity b: force_b = -(1/ratio)*force, ratio = m_b/m_a
-                                    T c = -O::div((T)1, O::div(m_i, m_j));
-                                    Fx = O::add(O::mul(c, fx), Fx); Fy = O::add(O::mul(c, fy), Fy);
-                                } else {           // i is entity a: force_a = ratio*force
-                                    T r = O::div(m_j, m_i);
-                                    Fx = O::add(O::mul(r, fx), Fx); Fy = O::add(O::mul(r, fy), Fy);
-                                }
-                            } else {               // equal masses: ratio == 1 exactly
-                                if (j < i) { Fx = O::add(-fx, Fx); Fy = O::add(-fy, Fy); }
+                    if (!HET) {
+                        // uniform agents: per chunk of 32 partners, pass 1 builds a near-pair bitmask
+                        // branch-free (7 instructions per pair), pass 2 evaluates the softplus force only
+                        // for set bits, in ascending j (the reference's accumulation order).
+                        const T dmin = O::add(a.size, a.size);                  // core.py:307
+                        for (int j0 = 0; j0 < N; j0 += 32) {
+                            const int jn = min(32, N - j0);
+                            unsigned near = 0;
+#pragma unroll 8
+                            for (int jj = 0; jj < jn; ++jj) {
+                                R2 q = envp[j0 + jj];
+                                T dx = O::sub(p.x, q.x), dy = O::sub(p.y, q.y);
+                                T d2 = dx * dx + dy * dy;
+                                // Far pairs: softplus(-(d-dmin)/k) < exp(-kcut) -- below the rounding of
+                                // F (DESIGN.md "contact cut-off").  !(>=) keeps NaN positions propagating.
+                                near |= (!(d2 >= a.cut2)) ? (1u << jj) : 0u;
+                            }
+                            if ((unsigned)(i - j0) < 32u) near &= ~(1u << (i - j0));
+                            while (near) {
+                                const int j = j0 + __ffs(near) - 1;
+                                near &= near - 1;
+                                R2 q = envp[j];
+                                T dx = (j < i) ? O::sub(q.x, p.x) : O::sub(p.x, q.x);   // delta = p_a - p_b, a<b
+                                T dy = (j < i) ? O::sub(q.y, p.y) : O::sub(p.y, q.y);
+                                T fx, fy;
+                                contact_force<T>(dx, dy, dmin, a.margin, a.cforce, &fx, &fy);
+                                if (j < i) { Fx = O::add(-fx, Fx); Fy = O::add(-fy, Fy); }   // equal masses: ratio 1
                                 else       { Fx = O::add(fx, Fx);  Fy = O::add(fy, Fy); }
+                            }
+                        }
+                    } else {
+                        for (int j = 0; j < N; ++j) {
+                            if (j == i) continue;
+                            R2 q = envp[j];
+                            T dx = (j < i) ? O::sub(q.x, p.x) : O::sub(p.x, q.x);   // delta = p_a - p_b, a<b
+                            T dy = (j < i) ? O::sub(q.y, p.y) : O::sub(p.y, q.y);
+                            T d2 = dx * dx + dy * dy;
+                            T dmin, cut2;
+                            if (HET) {
+                                dmin = O::add((j < i) ? s_het[N + j] : size_i, (j < i) ? size_i : s_het[N + j]);
+                                T c = dmin + a.kcut * a.margin; cut2 = c * c;
+                            } else {
+                                dmin = O::add(a.size, a.size);                       // core.py:307
+                                cut2 = a.cut2;
+                            }
+                            // Far pairs: softplus(-(d-dmin)/k) < exp(-kcut) -- below the rounding of F
+                            // (DESIGN.md "contact cut-off").  !(>=) keeps NaN positions propagating.
+                            if (!(d2 >= cut2)) {
+                                T fx, fy;
+                                contact_force<T>(dx, dy, dmin, a.margin, a.cforce, &fx, &fy);
+                                if (HET) {
+                                    T m_j = s_het[j];
+                                    if (j < i) {       // i is entity b: force_b = -(1/ratio)*force, ratio = m_b/m_a
+                                        T c = -O::div((T)1, O::div(m_i, m_j));
+                                        Fx = O::add(O::mul(c, fx), Fx); Fy = O::add(O::mul(c, fy), Fy);
+                                    } else {           // i is entity a: force_a = ratio*force
+                                        T r = O::div(m_j, m_i);
+                                        Fx = O::add(O::mul(r, fx), Fx); Fy = O::add(O::mul(r, fy), Fy);
+                                    }
+                                } else {               // equal masses: ratio == 1 exactly
+                                    if (j < i) { Fx = O::add(-fx, Fx); Fy = O::add(-fy, Fy); }
+                                    else       { Fx = O::add(fx, Fx);  Fy = O::add(fy, Fy); }
+                                }
                             }
                         }
                     }
@@ -296,56 +370,81 @@ __global__ void __launch_bounds__(kBlock) k_step(const __grid_constant__ KArgs<T
 
         // ================= Scenario.reward partials on the NEW state (Q16) ======================
         int col = 0;
-        T mpx = 0, mpy = 0, mvx = 0, mvy = 0;
+        T mvx = 0, mvy = 0;
+        if (SCN == kScnHD) {
+            // a non-finite position makes the centroid, hence the whole shape term, NaN (Q9)
+            if (active && (!(fabs(p.x) < (T)INFINITY) || !(fabs(p.y) < (T)INFINITY))) s_bad[le] = 1;
+            // centroid and mean velocity: one thread per (env, {pos, vel}), summed in agent order
+            // like np.mean(axis=0) (formation_hd_env.py:65,68)
+            if (t < 2 * nvalid) {
+                const int qe = t >> 1;
+                const R2* src = (t & 1) ? (s_v + qe * N) : (s_new + qe * N);
+                T sx = 0, sy = 0;
+#pragma unroll 4
+                for (int j = 0; j < N; ++j) { R2 q = src[j]; sx = O::add(sx, q.x); sy = O::add(sy, q.y); }
+                s_mean[t] = O::make(O::div(sx, (T)N), O::div(sy, (T)N));
+            }
+            __syncthreads();
+            if (active) {
+                const R2 mp = s_mean[2 * le], mv = s_mean[2 * le + 1];
+                mvx = mv.x; mvy = mv.y;
+                s_cen[t] = O::make(O::sub(p.x, mp.x), O::sub(p.y, mp.y));      // centred agent shape
+            }
+            __syncthreads();
+        }
         if (active) {
             const R2* envp = s_new + le * N;
-            const R2* envv = s_v + le * N;
-            T size_i = HET ? s_het[N + i] : a.size;
-            T spx = 0, spy = 0, svx = 0, svy = 0;
-            for (int j = 0; j < N; ++j) {
-                R2 q = envp[j];
-                if (SCN == kScnHD) {
-                    R2 w = envv[j];
-                    spx = O::add(spx, q.x); spy = O::add(spy, q.y);             // np.mean(.., 0): row order
-                    svx = O::add(svx, w.x); svy = O::add(svy, w.y);
-                }
-                // is_collision: hd excludes self, threshold (s1+s2)/2 (formation_hd_env.py:73,119-121);
-                // basic includes self, threshold s1+s2 (basic_formation_env.py:48-51,89-91)
-                if (a.collide && (SCN == kScnBasic || j != i)) {
-                    T dx = O::sub(q.x, p.x), dy = O::sub(q.y, p.y);
-                    T d2 = dx * dx + dy * dy;
-                    T thr, thr2;
-                    if (HET) {
-                        thr = O::add(s_het[N + j], size_i);
+            // is_collision: hd excludes self, threshold (s1+s2)/2 (formation_hd_env.py:73,119-121);
+            // basic includes self, threshold s1+s2 (basic_formation_env.py:48-51,89-91)
+            if (a.collide) {
+                if (!HET) {
+                    // candidates by squared distance (bitmask per 32 partners), exact sqrt test after (Q18)
+                    for (int j0 = 0; j0 < N; j0 += 32) {
+                        const int jn = min(32, N - j0);
+                        unsigned hit = 0;
+#pragma unroll 8
+                        for (int jj = 0; jj < jn; ++jj) {
+                            R2 q = envp[j0 + jj];
+                            T dx = O::sub(q.x, p.x), dy = O::sub(q.y, p.y);
+                            T d2 = dx * dx + dy * dy;
+                            hit |= (d2 < a.rthr2_hi) ? (1u << jj) : 0u;
+                        }
+                        if (SCN == kScnHD && (unsigned)(i - j0) < 32u) hit &= ~(1u << (i - j0));
+                        while (hit) {
+                            const int j = j0 + __ffs(hit) - 1;
+                            hit &= hit - 1;
+                            R2 q = envp[j];
+                            if (O::norm2(O::sub(q.x, p.x), O::sub(q.y, p.y)) < a.rthr) ++col;
+                        }
+                    }
+                } else {
+                    const T size_i = s_het[N + i];
+                    for (int j = 0; j < N; ++j) {
+                        if (SCN == kScnHD && j == i) continue;
+                        R2 q = envp[j];
+                        T dx = O::sub(q.x, p.x), dy = O::sub(q.y, p.y);
+                        T d2 = dx * dx + dy * dy;
+                        T thr = O::add(s_het[N + j], size_i);
                         if (SCN == kScnHD) thr = O::div(thr, (T)2);
-                        thr2 = thr * thr * (T)1.0001;
-                    } else { thr = a.rthr; thr2 = a.rthr2_hi; }
-                    if (d2 < thr2) { if (O::norm2(dx, dy) < thr) ++col; }
+                        if (d2 < thr * thr * (T)1.0001) { if (O::norm2(dx, dy) < thr) ++col; }
+                    }
                 }
             }
             if (SCN == kScnHD) {
-                mpx = O::div(spx, (T)N); mpy = O::div(spy, (T)N);
-                mvx = O::div(svx, (T)N); mvy = O::div(svy, (T)N);
                 // reward part 1 (formation_hd_env.py:64-66): symmetric Hausdorff distance between the
                 // centred agent shape C and the ideal shape S.  Thread i owns row i (min_j |C_i-S_j|^2)
                 // and column i (min_j |C_j-S_i|^2); env-wide max via shared atomicMax on the bits.
                 const R2* envs = s_s + le * N;
-                R2 Si = envs[i];
-                T cix = O::sub(p.x, mpx), ciy = O::sub(p.y, mpy);
+                const R2* envc = s_cen + le * N;
+                const R2 Si = envs[i], Ci = envc[i];
                 T rowmin = (T)INFINITY, colmin = (T)INFINITY;
-                bool nan_seen = false;
+#pragma unroll 4
                 for (int j = 0; j < N; ++j) {
-                    R2 q = envp[j]; R2 Sj = envs[j];
-                    T cjx = O::sub(q.x, mpx), cjy = O::sub(q.y, mpy);
-                    T d_row = O::sq2(O::sub(cix, Sj.x), O::sub(ciy, Sj.y));
-                    T d_col = O::sq2(O::sub(cjx, Si.x), O::sub(cjy, Si.y));
-                    nan_seen |= (d_row != d_row) | (d_col != d_col);
-                    rowmin = fmin(rowmin, d_row);
-                    colmin = fmin(colmin, d_col);
+                    R2 Cj = envc[j]; R2 Sj = envs[j];
+                    rowmin = fmin(rowmin, O::sq2(O::sub(Ci.x, Sj.x), O::sub(Ci.y, Sj.y)));
+                    colmin = fmin(colmin, O::sq2(O::sub(Cj.x, Si.x), O::sub(Cj.y, Si.y)));
                 }
-                if (nan_seen) { rowmin = O::from_bits(~(Bits)0 >> 1); colmin = rowmin; }  // +NaN
-                atomicMax(&s_rowmax[le], O::bits(rowmin));       // d2 >= 0: bit order == value order
-                atomicMax(&s_colmax[le], O::bits(colmin));
+                atomicMax(&s_rowmax[le], O::bits(fmax(rowmin, colmin)));   // d2 >= 0: bit order == value order
             }
             if (col) atomicAdd(&s_col[le], col);
         }
@@ -375,8 +474,8 @@ __global__ void __launch_bounds__(kBlock) k_step(const __grid_constant__ KArgs<T
         if (active) {
             T base;
             if (SCN == kScnHD) {
-                Bits mx = max(s_rowmax[le], s_colmax[le]);
-                T form = -O::sqrt_(O::from_bits(mx));                           // -max(dH, dH')
+                T form = -O::sqrt_(O::from_bits(s_rowmax[le]));                 // -max(dH, dH')
+                if (s_bad[le]) form = O::from_bits(~(Bits)0 >> 1);              // NaN, as the reference
                 T velr = O::norm2(O::sub(s_iv[le].x, mvx), O::sub(s_iv[le].y, mvy));   // :68-69
                 base = O::sub(form, velr);
             } else {
@@ -478,41 +577,130 @@ __global__ void __launch_bounds__(kBlock) k_step(const __grid_constant__ KArgs<T
         // threads write consecutive items (8 B fp32 / 16 B fp64 each): fully coalesced stores.
         if (a.obs) {
             const int IPR = a.IPR;
-            const uint32_t total = (uint32_t)(nvalid * N * IPR);
-            R2* out = a.obs + (size_t)tile0 * N * IPR;
-            for (uint32_t q = t; q < total; q += kBlock) {
-                const uint32_t row = fastdiv(q, a.magic_ipr);          // (local env, agent) row
-                const int k = (int)(q - row * IPR);                    // item within the row
-                const int rle = (int)fastdiv(row, a.magic_n);
-                const int ri = (int)row - rle * N;
-                R2 val;
-                if (SCN == kScnHD) {
-                    if (k == 0) val = s_v[row];                                        // p_vel
-                    else if (k < N) {                                                  // other_pos
-                        int j = k - 1; j += (j >= ri);
-                        R2 pj = s_new[rle * N + j], pi = s_new[row];
-                        val = O::make(O::sub(pj.x, pi.x), O::sub(pj.y, pi.y));
-                    } else if (k < 2 * N - 1) {                                        // comm
-                        int j = k - N; j += (j >= ri);
-                        val = s_c[rle * N + j];
-                    } else if (k < 3 * N - 1) val = s_s[rle * N + (k - (2 * N - 1))];  // ideal_shape
-                    else val = s_iv[rle];                                              // ideal_vel
-                } else {
-                    if (k == 0) val = s_v[row];                                        // p_vel
-                    else if (k == 1) val = s_new[row];                                 // p_pos
-                    else if (k < 2 + L) {                                              // landmarks - p
-                        R2 l = s_s[rle * L + (k - 2)], pi = s_new[row];
-                        val = O::make(O::sub(l.x, pi.x), O::sub(l.y, pi.y));
-                    } else if (k < 2 + L + (N - 1)) {                                  // other_pos
-                        int j = k - (2 + L); j += (j >= ri);
-                        R2 pj = s_new[rle * N + j], pi = s_new[row];
-                        val = O::make(O::sub(pj.x, pi.x), O::sub(pj.y, pi.y));
-                    } else {                                                           // comm
-                        int j = k - (2 + L + (N - 1)); j += (j >= ri);
-                        val = s_c[rle * N + j];
+            if (OM == 2) {
+                // Long hd rows, silent agents: 2/3 of every row ([comm zeros | ideal_shape | ideal_vel]) is the
+                // same for all rows of an env, so it is built ONCE per env in shared memory (in both
+                // 16-byte phases) and bulk-stored N times from there; only the N dynamic items of a row
+                // are staged per row.  Per row: ~6 instructions per dynamic item + 2 bulk stores.
+                const int lane = t & 31, wp = t >> 5;
+                for (int qe = 0; qe < nvalid; ++qe) {
+                    R2* im0 = s_rt_img + (size_t)qe * 2 * rt_img;
+                    R2* im1 = im0 + rt_img;
+                    for (int k = t; k < 2 * N; k += kBlock) {
+                        R2 val = (k < N - 1) ? O::make((T)0, (T)0) : (k < 2 * N - 1 ? s_s[qe * N + (k - (N - 1))] : s_iv[qe]);
+                        im0[k] = val; im1[k] = val;
                     }
                 }
-                out[q] = val;
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncthreads();
+                R2* dyn2 = s_rt_dyn + wp * 2 * rt_dyn;                           // two staging buffers per warp
+                const int nrows = nvalid * N;
+                int pending = 0;
+                for (int row = wp; row < nrows; row += kBlock / 32) {
+                    R2* dyn = dyn2 + (pending & 1) * rt_dyn;
+                    const int rle = (int)fastdiv((uint32_t)row, a.magic_n);
+                    const int ri = row - rle * N;
+                    R2* out = a.obs + ((size_t)tile0 * N + row) * IPR;
+                    const uint32_t ph = ((uint32_t)(uintptr_t)out & 15u) ? 1u : 0u;     // odd 8-byte slot (fp32 only)
+                    R2* img = dyn + ph;                                                 // same phase as `out`
+                    // the buffer being refilled was sent two rows ago: at most one younger group may be in flight
+                    if (pending >= 2 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                    __syncwarp();
+                    const R2* P = s_new + rle * N;
+                    const R2 pi = P[ri];
+                    if (lane == 0) img[0] = s_v[row];                                   // p_vel
+                    for (int k = lane; k < N - 1; k += 32) {                            // other_pos
+                        R2 pj = P[k + (k >= ri)];
+                        img[1 + k] = O::make(O::sub(pj.x, pi.x), O::sub(pj.y, pi.y));
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    __syncwarp();
+                    row_piece_store<R2>(out, img, (uint32_t)(N * sizeof(R2)), lane);
+                    // static part: starts N items later -> opposite phase when sizeof(R2) == 8 and N is odd
+                    R2* outs = out + N;
+                    const uint32_t phs = ((uint32_t)(uintptr_t)outs & 15u) ? 1u : 0u;
+                    const R2* ims = s_rt_img + (size_t)rle * 2 * rt_img + (phs ? rt_img : 0);
+                    // image phase: im0 is 16-byte aligned, im1 = im0 + (2N+1) items is 8 mod 16 (fp32)
+                    row_piece_store<R2>(outs, ims, (uint32_t)(2 * N * sizeof(R2)), lane);
+                    if (lane == 0) asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    ++pending;
+                }
+                // the images must outlive the bulk copies' reads (kernel exit or the next rollout step)
+                if (pending && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                __syncthreads();
+            } else if (OM == 1) {
+                // Long rows (N >= 16): one warp per row, one simple loop per row segment -- no per-item
+                // (row, item) decode; consecutive lanes store consecutive 8-byte items (256 B per
+                // instruction, rows are contiguous in HBM).  st.global.cs: write-once streaming data.
+                const int lane = t & 31;
+                const int nrows = nvalid * N;
+                for (int row = t >> 5; row < nrows; row += kBlock / 32) {
+                    const int rle = (int)fastdiv((uint32_t)row, a.magic_n);
+                    const int ri = row - rle * N;
+                    R2* out = a.obs + ((size_t)tile0 * N + row) * IPR;
+                    const R2* P = s_new + rle * N;
+                    const R2 pi = P[ri];
+                    if (lane == 0) O::stcs(out, s_v[row]);                              // p_vel
+                    int base = 1;
+                    if (SCN == kScnBasic) {
+                        if (lane == 1) O::stcs(out + 1, pi);                            // p_pos
+                        const R2* Lm = s_s + rle * L;
+                        for (int k = lane; k < L; k += 32) {                            // landmarks - p
+                            R2 l = Lm[k];
+                            O::stcs(out + 2 + k, O::make(O::sub(l.x, pi.x), O::sub(l.y, pi.y)));
+                        }
+                        base = 2 + L;
+                    }
+                    for (int k = lane; k < N - 1; k += 32) {                            // other_pos
+                        R2 pj = P[k + (k >= ri)];
+                        O::stcs(out + base + k, O::make(O::sub(pj.x, pi.x), O::sub(pj.y, pi.y)));
+                    }
+                    const R2* Cm = s_c + rle * N;
+                    for (int k = lane; k < N - 1; k += 32)                              // comm
+                        O::stcs(out + base + (N - 1) + k, Cm[k + (k >= ri)]);
+                    if (SCN == kScnHD) {
+                        const R2* Sh = s_s + rle * N;
+                        for (int k = lane; k < N; k += 32) O::stcs(out + 2 * N - 1 + k, Sh[k]);   // ideal_shape
+                        if (lane == 0) O::stcs(out + 3 * N - 1, s_iv[rle]);             // ideal_vel
+                    }
+                }
+            } else {
+                const uint32_t total = (uint32_t)(nvalid * N * IPR);
+                R2* out = a.obs + (size_t)tile0 * N * IPR;
+                for (uint32_t q = t; q < total; q += kBlock) {
+                    const uint32_t row = fastdiv(q, a.magic_ipr);          // (local env, agent) row
+                    const int k = (int)(q - row * IPR);                    // item within the row
+                    const int rle = (int)fastdiv(row, a.magic_n);
+                    const int ri = (int)row - rle * N;
+                    R2 val;
+                    if (SCN == kScnHD) {
+                        if (k == 0) val = s_v[row];                                        // p_vel
+                        else if (k < N) {                                                  // other_pos
+                            int j = k - 1; j += (j >= ri);
+                            R2 pj = s_new[rle * N + j], pi = s_new[row];
+                            val = O::make(O::sub(pj.x, pi.x), O::sub(pj.y, pi.y));
+                        } else if (k < 2 * N - 1) {                                        // comm
+                            int j = k - N; j += (j >= ri);
+                            val = s_c[rle * N + j];
+                        } else if (k < 3 * N - 1) val = s_s[rle * N + (k - (2 * N - 1))];  // ideal_shape
+                        else val = s_iv[rle];                                              // ideal_vel
+                    } else {
+                        if (k == 0) val = s_v[row];                                        // p_vel
+                        else if (k == 1) val = s_new[row];                                 // p_pos
+                        else if (k < 2 + L) {                                              // landmarks - p
+                            R2 l = s_s[rle * L + (k - 2)], pi = s_new[row];
+                            val = O::make(O::sub(l.x, pi.x), O::sub(l.y, pi.y));
+                        } else if (k < 2 + L + (N - 1)) {                                  // other_pos
+                            int j = k - (2 + L); j += (j >= ri);
+                            R2 pj = s_new[rle * N + j], pi = s_new[row];
+                            val = O::make(O::sub(pj.x, pi.x), O::sub(pj.y, pi.y));
+                        } else {                                                           // comm
+                            int j = k - (2 + L + (N - 1)); j += (j >= ri);
+                            val = s_c[rle * N + j];
+                        }
+                    }
+                    out[q] = val;
+                }
             }
         }
 

@@ -33,6 +33,7 @@ template <> struct Ops<float> {
     static __device__ __forceinline__ Bits bits(float a) { return __float_as_uint(a); }
     static __device__ __forceinline__ float from_bits(Bits b) { return __uint_as_float(b); }
     static __device__ __forceinline__ R2 make(float x, float y) { return make_float2(x, y); }
+    static __device__ __forceinline__ void stcs(R2* p, R2 v) { __stcs(p, v); }   // st.global.cs (streaming)
 };
 
 template <> struct Ops<double> {
@@ -59,6 +60,7 @@ template <> struct Ops<double> {
     static __device__ __forceinline__ Bits bits(double a) { return (Bits)__double_as_longlong(a); }
     static __device__ __forceinline__ double from_bits(Bits b) { return __longlong_as_double((long long)b); }
     static __device__ __forceinline__ R2 make(double x, double y) { return make_double2(x, y); }
+    static __device__ __forceinline__ void stcs(R2* p, R2 v) { __stcs(p, v); }
 };
 
 // ---- Philox4x32-10 (Salmon et al., SC'11).  counter = (env, agent, tick, purpose), key = seed ----

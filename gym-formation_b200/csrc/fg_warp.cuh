@@ -28,10 +28,6 @@
 
 namespace fg {
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) {
-    return (uint32_t)__cvta_generic_to_shared(p);
-}
-
 // Per-warp shared-memory slice layout (bytes), shared by host (sizing) and device (carving).
 template <typename T, int N, bool WOBS> struct WarpLayout {
     typedef typename Ops<T>::R2 R2;

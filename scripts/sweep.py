@@ -52,11 +52,12 @@ def run(N, E, obs=True, steps=50, reps=4, env=None, only_step=False, warm=0.0):
 
 
 if __name__ == "__main__":
-    for N, E in ((9, 131072), (9, 4096), (27, 65536), (3, 262144), (243, 1024)):
-        for obs, only in ((True, False), (True, True), (False, True)):
-            us, gbs = run(N, E, obs, only_step=only, reps=8)
-            print(N, E, "obs", obs, "only_step", only, "%.1f us  %.0f GB/s" % (us, gbs), LAST, flush=True)
-    for envv in ({"FG_OBS_POLICY": 1}, {"FG_WAVES": 2}):
-        for N, E in ((9, 131072), (27, 65536)):
-            us, gbs = run(N, E, True, env=envv, only_step=True, reps=8)
-            print(N, E, envv, "%.1f us  %.0f GB/s" % (us, gbs), flush=True)
+    for N, E in ((243, 1024), (81, 8192), (49, 16384)):
+        for mn in (48, 100000):
+            us, gbs = run(N, E, True, only_step=True, reps=8, env={"FG_ROW_TMA_MIN": mn})
+            print(N, E, "row_tma_min", mn, "%.1f us  %.0f GB/s" % (us, gbs), flush=True)
+    os.environ["FG_FORCE_TILE_KERNEL"] = "1"
+    for N, E in ((27, 65536),):
+        for mn in (48, 100000):
+            us, gbs = run(N, E, True, only_step=True, reps=8, env={"FG_ROW_TMA_MIN": mn})
+            print("tile kernel:", N, E, "row_tma_min", mn, "%.1f us  %.0f GB/s" % (us, gbs), flush=True)
