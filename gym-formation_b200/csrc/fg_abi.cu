@@ -7,6 +7,7 @@
 
 #include "../../include/formation_gym_b200.h"
 #include <cstdlib>
+#include <type_traits>
 
 #include "fg_kernels.cuh"
 #include "fg_warp.cuh"
@@ -92,6 +93,14 @@ int fill_args(fg::KArgs<T>& a, const fg_params* p, const fg_buffers* b, int scen
     a.seed = seed; a.tick = tick; a.env_offset = env_offset;
     // long hd rows of silent agents: static 2/3 of each row bulk-stored from one shared image
     // (measured: N = 243 270 us vs 353 us with plain stores; break-even near N = 50)
+    {
+        const char* slow = getenv("FG_NO_FAST_PAIRS");                 // A/B switch for tests and profiling
+        // measured (scripts/cfg_time.py): without observations the packed loops win from N = 32 up (N = 243:
+        // 93 -> 59 us per 1024 envs); with observations the kernel is bound by its obs writer and the extra
+        // shared memory only pays for large N
+        const char* force = getenv("FG_FORCE_FAST_PAIRS");
+        a.fast_pairs = N >= 32 && (!b->obs || N >= 128 || (force && force[0] == '1')) && !(slow && slow[0] == '1');
+    }
     a.row_tma = scenario == FG_SCENARIO_HD && p->silent && a.IPR >= 144 && b->obs &&
                 ((uintptr_t)b->obs % sizeof(R2)) == 0;
     return FG_OK;
@@ -113,27 +122,44 @@ size_t smem_bytes(const fg::KArgs<T>& a, int scenario, bool het) {
     return (s + 15) & ~(size_t)15;
 }
 
-template <typename T, int SCN, bool PHYS, bool OBSREW, bool HET, int OM>
+// extra shared memory of the fast pair loops: 8 arrays of EPC*roundup(N,32) floats, the per-(env,warp)
+// partial sums and the two max-norm words per env
+template <typename T>
+size_t fast_pairs_bytes(const fg::KArgs<T>& a) {
+    const size_t NP = ((size_t)a.N + 31) & ~(size_t)31;
+    return (8 * (size_t)a.EPC * NP + (size_t)a.EPC * 32) * sizeof(float) + 2 * (size_t)a.EPC * sizeof(unsigned) + 16;
+}
+
+template <typename T, int SCN, bool PHYS, bool OBSREW, bool HET, int OM, bool FP>
 int launch_one(const fg::KArgs<T>& a, size_t smem, cudaStream_t st) {
     const int grid = (a.E + a.EPC - 1) / a.EPC;
+    if (FP) smem += fast_pairs_bytes(a);
     if (smem > 48 * 1024) {
-        cudaError_t e1 = cudaFuncSetAttribute(fg::k_step<T, SCN, PHYS, OBSREW, HET, OM>,
+        cudaError_t e1 = cudaFuncSetAttribute(fg::k_step<T, SCN, PHYS, OBSREW, HET, OM, FP>,
                                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e1 != cudaSuccess) return fail(FG_ERR_CUDA, "cudaFuncSetAttribute failed: %s", cudaGetErrorString(e1));
     }
-    fg::k_step<T, SCN, PHYS, OBSREW, HET, OM><<<grid, fg::kBlock, smem, st>>>(a);
+    fg::k_step<T, SCN, PHYS, OBSREW, HET, OM, FP><<<grid, fg::kBlock, smem, st>>>(a);
     cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess) return fail(FG_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(err));
     return FG_OK;
 }
 
+// Fast pair loops (fg_pairs.cuh): fp32, formation_hd_env, uniform agents, 32 <= N (a warp spans <= 2 envs).
+template <typename T, int SCN, bool PHYS, bool OBSREW, bool HET, int OM>
+int launch_fp(const fg::KArgs<T>& a, size_t smem, cudaStream_t st) {
+    constexpr bool kCan = std::is_same<T, float>::value && SCN == fg::kScnHD && !HET;
+    if (kCan && a.fast_pairs) return launch_one<T, SCN, PHYS, OBSREW, HET, OM, kCan>(a, smem, st);
+    return launch_one<T, SCN, PHYS, OBSREW, HET, OM, false>(a, smem, st);
+}
+
 // observation-writer mode of the tile kernel (fg_kernels.cuh k_step<..., OM>)
 template <typename T, int SCN, bool PHYS, bool OBSREW, bool HET>
 int launch_om(const fg::KArgs<T>& a, size_t smem, cudaStream_t st) {
-    if (!OBSREW) return launch_one<T, SCN, PHYS, OBSREW, HET, 0>(a, smem, st);
-    if (SCN == fg::kScnHD && a.row_tma) return launch_one<T, SCN, PHYS, OBSREW, HET, (SCN == fg::kScnHD ? 2 : 0)>(a, smem, st);
-    if (a.IPR >= 48) return launch_one<T, SCN, PHYS, OBSREW, HET, 1>(a, smem, st);
-    return launch_one<T, SCN, PHYS, OBSREW, HET, 0>(a, smem, st);
+    if (!OBSREW) return launch_fp<T, SCN, PHYS, OBSREW, HET, 0>(a, smem, st);
+    if (SCN == fg::kScnHD && a.row_tma) return launch_fp<T, SCN, PHYS, OBSREW, HET, (SCN == fg::kScnHD ? 2 : 0)>(a, smem, st);
+    if (a.IPR >= 48) return launch_fp<T, SCN, PHYS, OBSREW, HET, 1>(a, smem, st);
+    return launch_fp<T, SCN, PHYS, OBSREW, HET, 0>(a, smem, st);
 }
 
 template <typename T, int SCN, bool PHYS, bool OBSREW>

@@ -14,6 +14,7 @@
 // the kernel is an HBM-store-bound obs writer with the physics riding along.
 #pragma once
 #include "fg_math.cuh"
+#include "fg_pairs.cuh"
 
 namespace fg {
 
@@ -51,6 +52,7 @@ template <typename T> struct KArgs {
     int has_accel, has_vmax, collide, silent, world_length, n_walls, prescaled;
     int mass_one;                    // mass == 1: F / m is exact without the division
     int row_tma;                     // tile kernel: long hd rows leave through TMA bulk stores (see k_step)
+    int fast_pairs;                  // tile kernel: packed pair loops of fg_pairs.cuh (N >= 32; fp32 hd uniform only)
     int n_steps, random_actions, auto_reset;
     uint64_t seed; uint32_t tick; uint32_t env_offset;
     uint32_t* tick_dev;              // (opt) [2]: device tick added to `tick`, arrival counter (CUDA graphs)
@@ -107,8 +109,10 @@ __device__ __forceinline__ void contact_force(T dx, T dy, T dmin, T k, T cf, T* 
     typedef Ops<T> O;
     T dist = O::norm2(dx, dy);                                   // core.py:305
     T tt = O::div(-O::sub(dist, dmin), k);                       // -(dist - dist_min)/k
-    // np.logaddexp(0, tt): stable softplus (core.py:310)
-    T sp = (tt > (T)0) ? O::add(tt, O::log1p_(O::exp_(-tt))) : O::log1p_(O::exp_(tt));
+    // np.logaddexp(0, tt): stable softplus (core.py:310): tt > 0 ? tt + log1p(exp(-tt)) : log1p(exp(tt)).
+    // Both branches share log1p(exp(-|tt|)), evaluated once (bit-identical to either branch).
+    const T lg = O::log1p_(O::exp_(-fabs(tt)));
+    T sp = (tt > (T)0) ? O::add(tt, lg) : lg;
     T pen = O::mul(sp, k);
     *fx = O::mul(O::div(O::mul(cf, dx), dist), pen);             // contact_force*delta/dist*pen
     *fy = O::mul(O::div(O::mul(cf, dy), dist), pen);             // dist == 0 -> NaN, as reference
@@ -148,7 +152,9 @@ __device__ __forceinline__ void wall_force(const WallT<T>& w, T px, T py, T size
 // OM selects the observation writer (one per instantiation keeps registers low): 0 = flat item loop
 // (short rows), 1 = one warp per row with plain streaming stores, 2 = one warp per row, static row part
 // bulk-stored from a shared image (hd, silent agents, long rows).
-template <typename T, int SCN, bool PHYS, bool OBSREW, bool HET, int OM>
+// FP: fast pair loops of fg_pairs.cuh (fp32, hd, uniform agents, N >= 32): structure-of-arrays partner
+// data, packed FFMA2/FADD2/FMUL2 arithmetic, group filters, warp-shuffle centroid and reductions.
+template <typename T, int SCN, bool PHYS, bool OBSREW, bool HET, int OM, bool FP>
 __global__ void __launch_bounds__(kBlock, (OM == 2) ? 4 : 3) k_step(const __grid_constant__ KArgs<T> a) {
     typedef Ops<T> O;
     typedef typename O::R2 R2;
@@ -165,7 +171,15 @@ __global__ void __launch_bounds__(kBlock, (OM == 2) ? 4 : 3) k_step(const __grid
     const int rt_dyn = (N + 3) & ~1;                  // items per staging buffer (16-byte multiple)
     R2* s_rt_img = reinterpret_cast<R2*>(smem_raw);
     R2* s_rt_dyn = s_rt_img + (OM == 2 ? 2 * rt_img * EPC : 0);
-    R2* s_old = s_rt_dyn + (OM == 2 ? 2 * rt_dyn * (kBlock / 32) : 0);   // positions the contact force reads
+    // FP: per local env, arrays of NP = roundup(N, 32) floats (16-byte aligned): old positions and
+    // their squared norms, centred new positions and norms, centred ideal shape.
+    const int NP = (N + 31) & ~31;
+    float* f_base = reinterpret_cast<float*>(s_rt_dyn + (OM == 2 ? 2 * rt_dyn * (kBlock / 32) : 0));
+    float* f_xo = f_base;              float* f_yo = f_xo + EPC * NP;   float* f_no = f_yo + EPC * NP;
+    float* f_cx = f_no + EPC * NP;     float* f_cy = f_cx + EPC * NP;   float* f_nc = f_cy + EPC * NP;
+    float* f_sx = f_nc + EPC * NP;     float* f_sy = f_sx + EPC * NP;
+    float* f_part = f_sy + EPC * NP;                  // [EPC][8 warps][4]: partial sums of pos.xy, vel.xy
+    R2* s_old = reinterpret_cast<R2*>(f_base + (FP ? 8 * EPC * NP + EPC * 32 : 0));   // positions the contact force reads
     R2* s_new = s_old + nA;                           // positions after integration
     R2* s_v = s_new + nA;                             // velocities after integration
     R2* s_s = s_v + nA;                               // hd: centred ideal shape; basic: landmarks
@@ -179,6 +193,7 @@ __global__ void __launch_bounds__(kBlock, (OM == 2) ? 4 : 3) k_step(const __grid
     int* s_col = reinterpret_cast<int*>(s_het + (HET ? 5 * N : 0));
     int* s_dn = s_col + EPC;                                  // episode-end flag per local env
     int* s_bad = s_dn + EPC;                                  // env has a non-finite position (NaN quirk, Q9)
+    unsigned* s_nmax = reinterpret_cast<unsigned*>(s_bad + EPC);   // FP: [2][EPC] max |p|^2 bits (old, centred new)
     __shared__ double s_stat[4];                              // episode statistics of this CTA's envs
     if (threadIdx.x < 4) s_stat[threadIdx.x] = 0.0;
 
@@ -207,6 +222,19 @@ __global__ void __launch_bounds__(kBlock, (OM == 2) ? 4 : 3) k_step(const __grid
         }
     }
 
+    if (FP) {
+        // neutral pad entries (never a candidate, never a minimum); the live entries are written below
+        for (int q = t; q < EPC * NP; q += kBlock) {
+            if (q - (q / NP) * NP >= N) {
+                f_xo[q] = 0.f; f_yo[q] = 0.f; f_no[q] = INFINITY;
+                f_cx[q] = 1e18f; f_cy[q] = 1e18f; f_nc[q] = INFINITY;
+                f_sx[q] = 1e18f; f_sy[q] = 1e18f;
+            }
+        }
+        if (t < 2 * EPC) s_nmax[t] = 0u;
+        __syncthreads();
+    }
+
     // ---- load the tile (coalesced: consecutive threads <-> consecutive agents of consecutive envs)
     R2 p = O::make((T)0, (T)0), v = p, u = p, uc = p;
     int stp = 0;
@@ -219,7 +247,11 @@ __global__ void __launch_bounds__(kBlock, (OM == 2) ? 4 : 3) k_step(const __grid
         }
         if (PHYS) s_old[t] = p; else { s_new[t] = p; s_v[t] = v; }
         if (OBSREW) {
-            if (SCN == kScnHD) s_s[t] = a.shape[g];
+            if (SCN == kScnHD) {
+                const R2 S0 = a.shape[g];
+                s_s[t] = S0;
+                if constexpr (FP) { f_sx[le * NP + i] = (float)S0.x; f_sy[le * NP + i] = (float)S0.y; }
+            }
             if (a.step) stp = a.step[e];
             if (!PHYS) s_c[t] = a.comm ? a.comm[g] : O::make((T)0, (T)0);
         }
@@ -232,8 +264,32 @@ __global__ void __launch_bounds__(kBlock, (OM == 2) ? 4 : 3) k_step(const __grid
         }
     }
 
+    // FP: a warp spans at most two envs (N >= 32): A = the env of lane 0, B = the next one
+    const int lane_ = t & 31, wp_ = t >> 5;
+    const int leA = __shfl_sync(0xffffffffu, le, 0);
+    const bool inA = active && le == leA, inB = active && le != leA;
+    const unsigned maskA = __ballot_sync(0xffffffffu, inA), maskB = __ballot_sync(0xffffffffu, inB);
+    // max / sum over the lanes of my env in this warp, then ONE shared-memory atomic per (warp, env)
+    auto env_atomic_max = [&](unsigned* dst, unsigned val) {
+        if (inA) { unsigned m = __reduce_max_sync(maskA, val); if (lane_ == __ffs(maskA) - 1) atomicMax(&dst[le], m); }
+        if (inB) { unsigned m = __reduce_max_sync(maskB, val); if (lane_ == __ffs(maskB) - 1) atomicMax(&dst[le], m); }
+    };
+    auto env_atomic_add = [&](int* dst, int val) {
+        if (inA) { int m = __reduce_add_sync(maskA, val); if (m && lane_ == __ffs(maskA) - 1) atomicAdd(&dst[le], m); }
+        if (inB) { int m = __reduce_add_sync(maskB, val); if (m && lane_ == __ffs(maskB) - 1) atomicAdd(&dst[le], m); }
+    };
+
     for (int ts = 0; ts < a.n_steps; ++ts) {
-        if (OBSREW && t < EPC) { s_rowmax[t] = 0; s_col[t] = 0; s_bad[t] = 0; }
+        if (OBSREW && t < EPC) { s_rowmax[t] = 0; s_col[t] = 0; s_bad[t] = 0; if (FP) s_nmax[EPC + t] = 0u; }
+        float n_old = 0.f;
+        if constexpr (FP) {
+            if (PHYS) {                                         // partner arrays of the contact filter
+                n_old = (float)p.x * (float)p.x + (float)p.y * (float)p.y;
+                if (active) { f_xo[le * NP + i] = (float)p.x; f_yo[le * NP + i] = (float)p.y; f_no[le * NP + i] = n_old; }
+                env_atomic_max(s_nmax, __float_as_uint(n_old));
+            }
+            if (t < EPC * 32) f_part[t] = 0.f;
+        }
         __syncthreads();
 
         // =============================== World.step (core.py:206-225) ===========================
@@ -261,7 +317,44 @@ __global__ void __launch_bounds__(kBlock, (OM == 2) ? 4 : 3) k_step(const __grid
                 // i in ascending order of the other index, exactly the reference's order.
                 if (a.collide) {
                     const R2* envp = s_old + le * N;
-                    if (!HET) {
+                    if constexpr (FP) {
+                        // candidate groups of four partners from the packed filter, then the reference's exact
+                        // test and force for the members of flagged groups, in ascending j
+                        const T dmin = O::add(a.size, a.size);                  // core.py:307
+                        const float thr = ((float)a.cut2 - n_old) + filter_margin(n_old, __uint_as_float(s_nmax[le]));
+                        u64 near = filter_groups(f_xo + le * NP, f_yo + le * NP, f_no + le * NP, NP >> 2,
+                                                 (float)p.x, (float)p.y, thr);
+                        // Two phases keep the warp converged on the expensive part: (1) cheap exact cut-off test
+                        // of the members of flagged groups, true near partners appended (ascending j) to a
+                        // register list of up to 8 byte-sized indices; (2) the softplus force for the listed
+                        // partners.  Dense clusters alternate between the phases.
+                        u64 list = 0; int cnt = 0;
+                        while (near | (u64)cnt) {
+                            while (near && cnt <= 4) {
+                                const int j4 = (__ffsll((long long)near) - 1) << 2;
+                                near &= near - 1;
+#pragma unroll
+                                for (int jj = 0; jj < 4; ++jj) {
+                                    const int j = j4 + jj;
+                                    R2 q = envp[min(j, N - 1)];
+                                    T dx = O::sub(p.x, q.x), dy = O::sub(p.y, q.y);
+                                    T d2 = dx * dx + dy * dy;
+                                    if (j < N && j != i && !(d2 >= a.cut2)) { list |= (u64)j << (8 * cnt); ++cnt; }
+                                }
+                            }
+                            for (int k = 0; k < cnt; ++k) {
+                                const int j = (int)(list >> (8 * k)) & 255;
+                                R2 q = envp[j];
+                                T dx = (j < i) ? O::sub(q.x, p.x) : O::sub(p.x, q.x);   // delta = p_a - p_b, a<b
+                                T dy = (j < i) ? O::sub(q.y, p.y) : O::sub(p.y, q.y);
+                                T fx, fy;
+                                contact_force<T>(dx, dy, dmin, a.margin, a.cforce, &fx, &fy);
+                                if (j < i) { Fx = O::add(-fx, Fx); Fy = O::add(-fy, Fy); }   // equal masses: ratio 1
+                                else       { Fx = O::add(fx, Fx);  Fy = O::add(fy, Fy); }
+                            }
+                            list = 0; cnt = 0;
+                        }
+                    } else if (!HET) {
                         // uniform agents: per chunk of 32 partners, pass 1 builds a near-pair bitmask
                         // branch-free (7 instructions per pair), pass 2 evaluates the softplus force only
                         // for set bits, in ascending j (the reference's accumulation order).
@@ -335,8 +428,10 @@ __global__ void __launch_bounds__(kBlock, (OM == 2) ? 4 : 3) k_step(const __grid
                 }
                 // integrate_state (core.py:264-277)
                 v.x = O::mul(v.x, a.keep); v.y = O::mul(v.y, a.keep);            // * (1 - damping)
-                v.x = O::add(v.x, O::mul(O::div(Fx, m_i), a.dt));
-                v.y = O::add(v.y, O::mul(O::div(Fy, m_i), a.dt));
+                // F / m: exact without the division when every mass is 1
+                const bool unit_mass = !HET && a.mass_one;
+                v.x = O::add(v.x, O::mul(unit_mass ? Fx : O::div(Fx, m_i), a.dt));
+                v.y = O::add(v.y, O::mul(unit_mass ? Fy : O::div(Fy, m_i), a.dt));
                 T vmax = HET ? s_het[4 * N + i] : (a.has_vmax ? a.vmax : (T)-1);
                 if (vmax >= (T)0) {
                     T sp = O::sqrt_(O::sq2(v.x, v.y));
@@ -371,12 +466,35 @@ __global__ void __launch_bounds__(kBlock, (OM == 2) ? 4 : 3) k_step(const __grid
         // ================= Scenario.reward partials on the NEW state (Q16) ======================
         int col = 0;
         T mvx = 0, mvy = 0;
+        float fcx = 0.f, fcy = 0.f, fnc = 0.f;                                // FP: my centred position, its norm^2
         if (SCN == kScnHD) {
             // a non-finite position makes the centroid, hence the whole shape term, NaN (Q9)
             if (active && (!(fabs(p.x) < (T)INFINITY) || !(fabs(p.y) < (T)INFINITY))) s_bad[le] = 1;
-            // centroid and mean velocity: one thread per (env, {pos, vel}), summed in agent order
-            // like np.mean(axis=0) (formation_hd_env.py:65,68)
-            if (t < 2 * nvalid) {
+            if constexpr (FP) {
+                // centroid and mean velocity (formation_hd_env.py:65,68): butterfly sums over the lanes of
+                // each env in the warp, one partial per (env, warp), combined in warp order after the barrier
+                if (PHYS && t < EPC) s_nmax[t] = 0u;                         // re-arm for the next rollout step
+                float a0 = inA ? (float)p.x : 0.f, a1 = inA ? (float)p.y : 0.f;
+                float a2 = inA ? (float)v.x : 0.f, a3 = inA ? (float)v.y : 0.f;
+#pragma unroll
+                for (int off = 16; off; off >>= 1) {
+                    a0 += __shfl_xor_sync(0xffffffffu, a0, off); a1 += __shfl_xor_sync(0xffffffffu, a1, off);
+                    a2 += __shfl_xor_sync(0xffffffffu, a2, off); a3 += __shfl_xor_sync(0xffffffffu, a3, off);
+                }
+                if (maskA && lane_ == 0)
+                    *reinterpret_cast<float4*>(f_part + (leA * 8 + wp_) * 4) = make_float4(a0, a1, a2, a3);
+                if (maskB) {                                                 // warp-uniform
+                    a0 = inB ? (float)p.x : 0.f; a1 = inB ? (float)p.y : 0.f;
+                    a2 = inB ? (float)v.x : 0.f; a3 = inB ? (float)v.y : 0.f;
+#pragma unroll
+                    for (int off = 16; off; off >>= 1) {
+                        a0 += __shfl_xor_sync(0xffffffffu, a0, off); a1 += __shfl_xor_sync(0xffffffffu, a1, off);
+                        a2 += __shfl_xor_sync(0xffffffffu, a2, off); a3 += __shfl_xor_sync(0xffffffffu, a3, off);
+                    }
+                    if (lane_ == 0)
+                        *reinterpret_cast<float4*>(f_part + ((leA + 1) * 8 + wp_) * 4) = make_float4(a0, a1, a2, a3);
+                }
+            } else if (t < 2 * nvalid) {
                 const int qe = t >> 1;
                 const R2* src = (t & 1) ? (s_v + qe * N) : (s_new + qe * N);
                 T sx = 0, sy = 0;
@@ -385,14 +503,54 @@ __global__ void __launch_bounds__(kBlock, (OM == 2) ? 4 : 3) k_step(const __grid
                 s_mean[t] = O::make(O::div(sx, (T)N), O::div(sy, (T)N));
             }
             __syncthreads();
-            if (active) {
+            if constexpr (FP) {
+                float sx = 0.f, sy = 0.f, svx = 0.f, svy = 0.f;
+                if (active) {
+#pragma unroll
+                    for (int w = 0; w < kBlock / 32; ++w) {
+                        const float4 q = *reinterpret_cast<const float4*>(f_part + (le * 8 + w) * 4);
+                        sx += q.x; sy += q.y; svx += q.z; svy += q.w;
+                    }
+                }
+                mvx = svx / (float)N; mvy = svy / (float)N;
+                fcx = (float)p.x - sx / (float)N; fcy = (float)p.y - sy / (float)N;   // centred agent shape
+                fnc = fcx * fcx + fcy * fcy;
+                if (active) { f_cx[le * NP + i] = fcx; f_cy[le * NP + i] = fcy; f_nc[le * NP + i] = fnc; }
+                env_atomic_max(s_nmax + EPC, __float_as_uint(fnc));
+            } else if (active) {
                 const R2 mp = s_mean[2 * le], mv = s_mean[2 * le + 1];
                 mvx = mv.x; mvy = mv.y;
                 s_cen[t] = O::make(O::sub(p.x, mp.x), O::sub(p.y, mp.y));      // centred agent shape
             }
             __syncthreads();
         }
-        if (active) {
+        if constexpr (FP) {
+            // collision candidates + both Hausdorff minima in one packed pass over the env (fg_pairs.cuh);
+            // flagged groups get the reference's exact test (formation_hd_env.py:119-121; Q18), self excluded
+            unsigned hbits = 0u;
+            if (active) {
+                const R2* envp = s_new + le * N;
+                const R2 Si = s_s[t];
+                const float thr = ((float)a.rthr2_hi - fnc) + filter_margin(fnc, __uint_as_float(s_nmax[EPC + le]));
+                float rowmin, colmin;
+                u64 hit = reward_pass(f_cx + le * NP, f_cy + le * NP, f_nc + le * NP, f_sx + le * NP, f_sy + le * NP,
+                                      NP >> 2, fcx, fcy, (float)Si.x, (float)Si.y, thr, a.collide != 0, &rowmin, &colmin);
+                while (hit) {
+                    const int j4 = (__ffsll((long long)hit) - 1) << 2;
+                    hit &= hit - 1;
+#pragma unroll
+                    for (int jj = 0; jj < 4; ++jj) {
+                        const int j = j4 + jj;
+                        if (j >= N || j == i) continue;
+                        R2 q = envp[j];
+                        if (O::norm2(O::sub(q.x, p.x), O::sub(q.y, p.y)) < a.rthr) ++col;
+                    }
+                }
+                hbits = __float_as_uint(fmaxf(rowmin, colmin));               // d2 >= 0: bit order == value order
+            }
+            env_atomic_max(reinterpret_cast<unsigned*>(s_rowmax), hbits);
+            env_atomic_add(s_col, col);
+        } else if (active) {
             const R2* envp = s_new + le * N;
             // is_collision: hd excludes self, threshold (s1+s2)/2 (formation_hd_env.py:73,119-121);
             // basic includes self, threshold s1+s2 (basic_formation_env.py:48-51,89-91)
@@ -544,6 +702,7 @@ __global__ void __launch_bounds__(kBlock, (OM == 2) ? 4 : 3) k_step(const __grid
                     for (int j = 0; j < N; ++j) { sx = O::add(sx, raw[j].x); sy = O::add(sy, raw[j].y); }
                     R2 S = O::make(O::sub(lraw.x, O::div(sx, (T)N)), O::sub(lraw.y, O::div(sy, (T)N)));  // :93
                     s_s[t] = S; a.shape[g] = S;
+                    if constexpr (FP) { f_sx[le * NP + i] = (float)S.x; f_sy[le * NP + i] = (float)S.y; }
                 }
                 if (dn && ts == a.n_steps - 1) { a.pos[g] = p; a.vel[g] = v; if (a.comm) a.comm[g] = v; }
                 __syncthreads();

@@ -40,7 +40,7 @@
 extern "C" {
 #endif
 
-#define FG_ABI_VERSION 2
+#define FG_ABI_VERSION 3
 #define FG_MAX_AGENTS 256      /* one CTA holds at least one whole env; 3^5 = 243 fits */
 #define FG_MAX_LANDMARKS 256
 #define FG_MAX_WALLS 8
@@ -173,6 +173,21 @@ int fg_random_actions(void* act, int E, int N, uint64_t seed, uint32_t tick, uin
                       const uint32_t* tick_dev, void* stream);
 int fg_random_actions_f64(void* act, int E, int N, uint64_t seed, uint32_t tick,
                           uint32_t env_offset, const uint32_t* tick_dev, void* stream);
+
+/* Diagnostics, not on the step path: FP32 pipe probes used by bench.py to MEASURE the FP32 peak the
+ * large-N step+reward kernel is graded against (BASELINE.json north_star: "% of FP32 peak at 243
+ * agents"; MEASURED_PEAKS.json holds no FP32 figure).  variant 0: scalar FFMA (2 flop/lane/instr),
+ * 1: packed FFMA2 (fma.rn.f32x2; 4 flop/lane/instr), 2: FMNMX (1 op), 3: the pair-loop instruction mix
+ * (FADD2, FADD2, FMUL2, FFMA2, FMNMX3 per two pairs).  Each of ctas x 256 threads runs `iters`
+ * iterations of 32 instructions (variants 0-2) or 8 pair-steps of 7 instructions (variant 3);
+ * `scratch` is a device buffer of >= ctas*256 floats (never written in practice).  Time it with
+ * CUDA events on `stream`. */
+int fg_fp32_probe(int variant, int iters, int ctas, float* scratch, void* stream);
+
+/* Diagnostics: write-only HBM stream over `bytes` of `dst` (what an observation writer can reach at
+ * best).  variant 0: 16-byte streaming stores; 1: TMA bulk stores (cp.async.bulk) of `chunk` bytes from
+ * shared memory; 2: the same with the L2 evict_first policy the step kernels use. */
+int fg_write_probe(int variant, void* dst, unsigned long long bytes, unsigned chunk, int ctas, void* stream);
 
 /* Launch geometry chosen for (N): envs per CTA and threads per CTA (for reporting/tests). */
 int fg_launch_geometry(int N, int* envs_per_cta, int* threads_per_cta);

@@ -13,10 +13,10 @@ import formation_gym  # noqa: E402
 LAST = ''
 
 
-def run(N, E, obs=True, steps=50, reps=4, env=None, only_step=False, warm=0.0):
+def run(N, E, obs=True, steps=50, reps=4, env=None, only_step=False, warm=0.0, scenario="formation_hd_env"):
     for k, v in (env or {}).items():
         os.environ[k] = str(v)
-    e = formation_gym.make_batched_env("formation_hd_env", E, N, 25, write_obs=obs, seed=1)
+    e = formation_gym.make_batched_env(scenario, E, N, 25, write_obs=obs, seed=1)
     e.reset()
     if only_step:
         e.sample_actions()

@@ -355,3 +355,79 @@ def test_graph_replay_equals_stepwise(N, E):
     b.use_device_tick(False)              # fold back: both envs continue identically
     a.step_random(); b.step_random()
     assert torch.equal(a.pos, b.pos)
+
+
+# ------------------------------------------------------------------ packed pair loops vs scalar tile kernel
+def _run_tile(E, N, steps, fast, scale, rollout=False, obs=True, seed=31):
+    """fp32 tile kernel with (fast) or without (FG_NO_FAST_PAIRS=1) the packed pair loops of fg_pairs.cuh."""
+    os.environ["FG_NO_FAST_PAIRS"] = "0" if fast else "1"
+    os.environ["FG_FORCE_FAST_PAIRS"] = "1" if fast else "0"
+    try:
+        env = BatchedFormationEnv("formation_hd_env", E, N, episode_length=5, seed=seed, auto_reset=True,
+                                  write_obs=obs)
+        env.reset()
+        env.pos.mul_(scale)
+        if rollout:
+            env.rollout_random(steps)
+        else:
+            for _ in range(steps):
+                env.step_random()
+        torch.cuda.synchronize()
+        keys = ["pos", "vel", "reward", "indiv", "ideal_shape", "ideal_vel", "step_count", "ep_return",
+                "ep_collisions"] + (["obs"] if obs else [])
+        out = {k: getattr(env, k).clone() for k in keys}
+        out["done"] = env.done.clone()
+        return out
+    finally:
+        os.environ.pop("FG_NO_FAST_PAIRS", None)
+        os.environ.pop("FG_FORCE_FAST_PAIRS", None)
+
+
+@pytest.mark.parametrize("E,N,scale", [(7, 32, 0.3), (5, 81, 0.5), (6, 100, 1.0), (3, 243, 1.0), (2, 243, 0.12),
+                                       (2, 256, 0.6), (9, 33, 0.05)])
+def test_fast_pairs_match_scalar_tile_kernel(E, N, scale):
+    """The group filters only select candidates; flagged pairs get the same exact tests and forces as the
+    scalar loops, in the same order.  Positions/velocities agree to fp32 rounding of the force sums, the
+    integer collision counts exactly.  scale 0.12 / 0.05 packs the agents densely (tens of contact partners
+    per agent: the register list of near partners is flushed several times)."""
+    a = _run_tile(E, N, 7, True, scale)
+    b = _run_tile(E, N, 7, False, scale)
+    assert torch.equal(a["ep_collisions"], b["ep_collisions"])
+    assert torch.equal(a["done"], b["done"]) and torch.equal(a["step_count"], b["step_count"])
+    for k in ("pos", "vel", "obs", "indiv", "reward", "ep_return", "ideal_shape", "ideal_vel"):
+        ref = b[k].double().cpu().numpy()
+        fin = np.isfinite(ref)
+        assert np.array_equal(fin, np.isfinite(a[k].double().cpu().numpy())), k
+        err = np.abs(a[k].double().cpu().numpy()[fin] - ref[fin]).max() if fin.any() else 0.0
+        assert err <= 2e-5 * max(1.0, float(np.abs(ref[fin]).max())), (k, err)
+
+
+def test_fast_pairs_rollout_equals_stepwise():
+    a = _run_tile(5, 81, 12, True, 0.4, rollout=False)
+    b = _run_tile(5, 81, 12, True, 0.4, rollout=True)
+    for k in a:
+        assert torch.equal(a[k], b[k]), k
+
+
+def test_fast_pairs_nan_env_matches_reference_pattern():
+    """Coincident agents (core.py:312) inside a large env: the NaN spreads exactly as in the scalar kernel."""
+    outs = []
+    for fast in (True, False):
+        os.environ["FG_NO_FAST_PAIRS"] = "0" if fast else "1"
+        os.environ["FG_FORCE_FAST_PAIRS"] = "1" if fast else "0"
+        try:
+            env = BatchedFormationEnv("formation_hd_env", 3, 81, episode_length=25, seed=2, auto_reset=False)
+            env.reset()
+            env.pos[1, 40] = env.pos[1, 7]                 # env 1: agents 7 and 40 coincide
+            act = env.sample_actions().clone()
+            for _ in range(3):
+                env.step(act)
+            torch.cuda.synchronize()
+            outs.append({k: getattr(env, k).clone() for k in ("pos", "vel", "reward", "indiv", "obs")})
+        finally:
+            os.environ.pop("FG_NO_FAST_PAIRS", None)
+            os.environ.pop("FG_FORCE_FAST_PAIRS", None)
+    a, b = outs
+    assert bool(torch.isnan(a["pos"][1]).all()) and not bool(torch.isnan(a["pos"][0]).any())
+    for k in a:
+        assert torch.equal(torch.isnan(a[k]), torch.isnan(b[k])), k
