@@ -370,9 +370,24 @@ def run_b200(a):
         dist.destroy_process_group()
 
 
+def flops_per_env_step(N):
+    """Algorithmic flops per env-step, SURVEY.md 8(d): F(N) = 27.5 N^2 + 10 N (dense reference arithmetic,
+    shared reward terms once per env, no credit removed for early-outs)."""
+    return 27.5 * N * N + 10.0 * N
+
+
 def also_configs(formation_gym, torch, device, dtype, peak):
     """Other BASELINE.json configs, measured briefly (informational; not the headline line)."""
     res = []
+    fp32_peak = None
+    try:
+        from formation_gym import probe
+        pk = probe.measure("ffma", device=device)                # scalar FFMA probe, CUDA events
+        fp32_peak = pk["tflops"]
+        res.append({"config": "FP32 peak probe (fg_fp32_probe, scalar FFMA, 8 CTAs/SM)", "tflops": fp32_peak,
+                    "ffma2_tflops": probe.measure("ffma2", device=device)["tflops"]})
+    except Exception as ex:
+        res.append({"config": "FP32 peak probe", "error": repr(ex)[:200]})
     for name, scen, N, E, steps, mode in (
             ("configs[1] hd N=9 E=4096 (launch-bound; per-step launches)", "formation_hd_env", 9, 4096, 500, "step"),
             ("configs[1] hd N=9 E=4096 (CUDA graph of 25 per-step launches)", "formation_hd_env", 9, 4096, 40, "graph"),
@@ -380,8 +395,8 @@ def also_configs(formation_gym, torch, device, dtype, peak):
             ("configs[2] hd N=27 E=65536", "formation_hd_env", 27, 65536, 50, "step"),
             ("configs[3] hd N=243 E=1024 (one GPU's share of 8192)", "formation_hd_env", 243, 1024, 30, "step"),
             ("hd N=243 E=1024 state+reward only (no obs)", "formation_hd_env", 243, 1024, 30, "noobs"),
-            ("hd N=3 E=262144", "formation_hd_env", 3, 262144, 100, "step"),
-            ("basic N=3 L=3 E=262144", "basic_formation_env", 3, 262144, 100, "step")):
+            ("hd N=3 E=1048576", "formation_hd_env", 3, 1048576, 50, "step"),
+            ("basic N=3 L=3 E=1048576", "basic_formation_env", 3, 1048576, 50, "step")):
         try:
             env = formation_gym.make_batched_env(scen, E, N, 25, device=device, dtype=dtype, seed=1,
                                                  write_obs=(mode != "noobs"))
@@ -404,8 +419,17 @@ def also_configs(formation_gym, torch, device, dtype, peak):
             ms = e0.elapsed_time(e1)
             env_steps = steps * (25 if mode in ("rollout", "graph") else 1)
             gbs = env.bytes_per_env_step() * E * env_steps / (ms * 1e-3) / 1e9
-            res.append({"config": name, "agent_steps_per_s": E * N * env_steps / (ms * 1e-3),
-                        "ms_per_env_step": ms / env_steps, "algorithmic_GBps": gbs, "hbm_frac": gbs / peak})
+            row = {"config": name, "agent_steps_per_s": E * N * env_steps / (ms * 1e-3),
+                   "ms_per_env_step": ms / env_steps, "algorithmic_GBps": gbs, "hbm_frac": gbs / peak}
+            if mode == "noobs":
+                # the step+reward kernel without dense observations is pair-compute bound: FP32 roofline
+                tf = flops_per_env_step(N) * E * env_steps / (ms * 1e-3) / 1e12
+                row.update({"bound": "fp32", "algorithmic_TFLOPs": tf, "fp32_peak_TFLOPs": fp32_peak,
+                            "fp32_frac": (tf / fp32_peak) if fp32_peak else None,
+                            "flops_per_env_step": flops_per_env_step(N),
+                            "note": "includes the random-policy kernel of the step; fraction of the MEASURED "
+                                    "scalar-FFMA peak"})
+            res.append(row)
             del env
         except Exception as ex:  # keep the headline line alive
             res.append({"config": name, "error": repr(ex)[:200]})

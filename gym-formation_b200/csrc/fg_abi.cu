@@ -195,7 +195,7 @@ const WarpGeom& warp_geom() {
             const int w = 1 << l;
             const size_t smem = (size_t)w * LY::stride;
             g_.ctas[l] = 0;
-            if (smem > 227 * 1024) continue;
+            if (smem > 227 * 1024 || w > LY::MAXW) continue;
             if (cudaFuncSetAttribute(fg::k_hd_warp<T, N, WOBS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)smem) != cudaSuccess) { cudaGetLastError(); continue; }
             int ctas = 0;

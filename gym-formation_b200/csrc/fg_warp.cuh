@@ -33,6 +33,18 @@ template <typename T, int N, bool WOBS> struct WarpLayout {
     typedef typename Ops<T>::R2 R2;
     typedef typename Ops<T>::Bits Bits;
     static constexpr int EPW = 32 / N;             // envs per warp
+    // Warps per CTA the kernel is compiled for.  N = 27 holds a 17.5 KB observation image per warp, so
+    // shared memory caps the SM at 12 warps anyway: 4-warp CTAs let ptxas use up to 255 registers (with
+    // 256-thread bounds it stopped at 128 and spilled two, and with ~2 KB of L1 left beside the shared
+    // memory every spill reload went to L2 -- 34 % of all stall samples in profiles/r01c_warp27_before).
+    static constexpr int MAXW = (N >= 27) ? 4 : 8;
+    static constexpr int MINB = (N >= 27) ? 0 : 3;
+    // Where the observation image is filled.  LATE (after rewards / auto-reset, from the shared state):
+    // the bulk copy of the previous span has the whole step to finish reading the image, at the price of
+    // re-reading the partner positions (measured: N = 3 91.1 -> 86.9 us per 1 M envs, N = 27 246 -> 241 us
+    // per 65536).  FUSED into the reward loop (the p_j - p_i it already holds): fewest instructions, best
+    // where the kernel is closest to issue-bound (N = 9: 55.0 us fused vs 58.5 us late per 131072 envs).
+    static constexpr bool LATE_FILL = (N != 9);   // N = 3, 9: three 8-warp CTAs per SM (<= 85 registers)
     static constexpr int NA = EPW * N;             // active lanes
     static constexpr int IPR = 3 * N;              // R2 items per observation row (6N scalars)
     static constexpr int OBS_ITEMS = WOBS ? NA * IPR : 0;
@@ -50,28 +62,8 @@ template <typename T, int N, bool WOBS> struct WarpLayout {
     static constexpr size_t stride = (raw + 15) & ~(size_t)15;
 };
 
-// One observation row of formation_hd_env (formation_hd_env.py:52-59) from the warp's shared state:
-// [p_vel | p_j - p_i (j != i ascending) | comm zeros | ideal_shape.flatten() | ideal_vel].
-// Generic (rolled) version, used by the auto-reset path only; the hot path fuses these stores into
-// the reward loop.
-template <typename T, int N>
-__device__ __forceinline__ void fill_row_hd(typename Ops<T>::R2* row, const typename Ops<T>::R2* eP,
-                                            const typename Ops<T>::R2* eS, typename Ops<T>::R2 p,
-                                            typename Ops<T>::R2 v, typename Ops<T>::R2 iv, int i) {
-    typedef Ops<T> O;
-    row[0] = v;
-    for (int k = 1; k < N; ++k) {
-        typename O::R2 q = eP[k];                               // agent (i + k) mod N
-        const int slot = (i + k < N) ? (i + k) : (i + k - N + 1);
-        row[slot] = O::make(O::sub(q.x, p.x), O::sub(q.y, p.y));
-    }
-    for (int k = 0; k < N - 1; ++k) row[N + k] = O::make((T)0, (T)0);
-    for (int k = 0; k < N; ++k) row[2 * N - 1 + k] = eS[k];
-    row[3 * N - 1] = iv;
-}
-
 template <typename T, int N, bool WOBS>
-__global__ void __launch_bounds__(256) k_hd_warp(const __grid_constant__ KArgs<T> a) {
+__global__ void __launch_bounds__(32 * WarpLayout<T, N, WOBS>::MAXW, WarpLayout<T, N, WOBS>::MINB) k_hd_warp(const __grid_constant__ KArgs<T> a) {
     typedef Ops<T> O;
     typedef typename O::R2 R2;
     typedef typename O::Bits Bits;
@@ -110,13 +102,7 @@ __global__ void __launch_bounds__(256) k_hd_warp(const __grid_constant__ KArgs<T
     // Shared-memory image of the span's observation rows.  It starts at the same offset modulo 16
     // as the span does in HBM so that the 16-byte-aligned middle can leave as one bulk copy; with
     // an even warp stride that phase is the same for every span of this warp.
-    uint32_t obs_head = 0;
-    R2* s_obs = nullptr;
-    if (WOBS) {
-        const uintptr_t g0 = (uintptr_t)(a.obs + (size_t)gw * EPW * N * IPR);
-        obs_head = (uint32_t)((16u - ((uint32_t)g0 & 15u)) & 15u);          // 0 or 8 (fp32), 0 (fp64)
-        s_obs = reinterpret_cast<R2*>(wr + LY::off_obs + ((16u - obs_head) & 15u));
-    }
+    // (recomputed per span from the span's address -- cheaper than keeping it live across the loop)
 
     const R2 zero = O::make((T)0, (T)0);
     bool bulk_pending = false;
@@ -147,7 +133,8 @@ __global__ void __launch_bounds__(256) k_hd_warp(const __grid_constant__ KArgs<T
     };
     fetch(gw);
 
-  for (int span = gw; span < nspans; span += nwarps) {
+  int spans_left = (nspans - gw + nwarps - 1) / nwarps;                     // >= 1
+  for (int span = gw; ; span += nwarps) {
     const int env0 = span * EPW;
     const int nval = min(EPW, a.E - env0);
     const bool active = lane < nval * N;
@@ -156,11 +143,13 @@ __global__ void __launch_bounds__(256) k_hd_warp(const __grid_constant__ KArgs<T
     const uint32_t ge = a.env_offset + (uint32_t)e;                         // global env id (Philox counter)
     R2* g_obs = WOBS ? a.obs + (size_t)env0 * N * IPR : nullptr;
     const uint32_t obs_bytes = WOBS ? (uint32_t)(nval * N * IPR) * (uint32_t)sizeof(R2) : 0u;
+    const uint32_t obs_head = WOBS ? (uint32_t)((16u - ((uint32_t)(uintptr_t)g_obs & 15u)) & 15u) : 0u;   // 0 or 8 (fp32), 0 (fp64)
+    R2* s_obs = WOBS ? reinterpret_cast<R2*>(wr + LY::off_obs + ((16u - obs_head) & 15u)) : nullptr;
 
     R2 p = p_n, v = v_n, u = u_n, S = S_n, iv = iv_n;
     T epr = epr_n;
     int stp = stp_n, epc = epc_n;
-    if (span + nwarps < nspans) fetch(span + nwarps);
+    if (spans_left > 1) fetch(span + nwarps);
     __syncwarp();                                                           // previous span's readers of s_shp are done
     if (lane < NA) s_shp[lane] = S;
 
@@ -257,7 +246,7 @@ __global__ void __launch_bounds__(256) k_hd_warp(const __grid_constant__ KArgs<T
         const R2 mp = s_mean[2 * le], mv = s_mean[2 * le + 1];
         const R2 C = O::make(O::sub(p.x, mp.x), O::sub(p.y, mp.y));         // centred agent shape
         if (lane < NA) s_cen[lane] = C;
-        if (WOBS && bulk_pending) {                                         // previous step's image is still being read
+        if (WOBS && !LY::LATE_FILL && bulk_pending) {                       // previous image is still being read
             if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
             bulk_pending = false;
         }
@@ -268,10 +257,11 @@ __global__ void __launch_bounds__(256) k_hd_warp(const __grid_constant__ KArgs<T
             const R2* eS = s_shp + le * N;
             const R2* eC = s_cen + le * N;
             const R2* eP = s_pnew + le * 2 * N + i;                         // eP[k] = agent (i + k) mod N
-            R2* row = WOBS ? (s_obs + lane * IPR) : nullptr;
+            constexpr bool FUSE = WOBS && !LY::LATE_FILL;
+            R2* row = FUSE ? (s_obs + lane * IPR) : nullptr;
             T rowmin = (T)INFINITY, colmin = (T)INFINITY;
             unsigned hit = 0;
-            if (WOBS) row[0] = v;                                           // p_vel
+            if (FUSE) row[0] = v;                                           // p_vel
 #pragma unroll
             for (int k = 0; k < N; ++k) {
                 // symmetric Hausdorff partials (formation_hd_env.py:64-66): row i = min_k |C_i - S_k|^2,
@@ -279,11 +269,11 @@ __global__ void __launch_bounds__(256) k_hd_warp(const __grid_constant__ KArgs<T
                 R2 Sk = eS[k], Ck = eC[k];
                 rowmin = fmin(rowmin, O::sq2(O::sub(C.x, Sk.x), O::sub(C.y, Sk.y)));
                 colmin = fmin(colmin, O::sq2(O::sub(Ck.x, S.x), O::sub(Ck.y, S.y)));
-                if (WOBS) row[2 * N - 1 + k] = Sk;                          // ideal_shape.flatten()
+                if (FUSE) row[2 * N - 1 + k] = Sk;                          // ideal_shape.flatten()
                 if (k >= 1) {
                     R2 q = eP[k];
                     T dx = O::sub(q.x, p.x), dy = O::sub(q.y, p.y);         // other_pos (formation_hd_env.py:55)
-                    if (WOBS) {
+                    if (FUSE) {
                         const int slot = (i + k < N) ? (i + k) : (i + k - N + 1);
                         row[slot] = O::make(dx, dy);
                     }
@@ -291,7 +281,7 @@ __global__ void __launch_bounds__(256) k_hd_warp(const __grid_constant__ KArgs<T
                     hit |= (d2 < a.rthr2_hi) ? (1u << k) : 0u;
                 }
             }
-            if (WOBS) {
+            if (FUSE) {
 #pragma unroll
                 for (int k = 0; k < N - 1; ++k) row[N + k] = zero;          // comm of the others (silent)
                 row[3 * N - 1] = iv;                                        // ideal_vel
@@ -369,13 +359,40 @@ __global__ void __launch_bounds__(256) k_hd_warp(const __grid_constant__ KArgs<T
                 if (ts == a.n_steps - 1) { a.pos[g] = p; a.vel[g] = v; }
             }
             __syncwarp();
-            if (WOBS && dn)                                                 // the RESET observation (env_wrappers.py:16-17)
-                fill_row_hd<T, N>(s_obs + lane * IPR, s_pnew + le * 2 * N + i, s_shp + le * N, p, v, iv, i);
         }
         if (active && i == 0 && a.step) a.step[e] = stp;
 
         // ================= observation rows leave the SM as one bulk copy =======================
+        // LATE_FILL: the image is filled LAST: the bulk copy of the previous span / step has had this whole step's
+        // physics and reward to finish reading it (filling right after the physics left the warp waiting
+        // on that copy for 25 % of its time at N = 27, profiles/r01c_warp27_before).  Rows come from the
+        // shared state, which for an env that was just reset already holds the RESET state
+        // (env_wrappers.py:16-17), so one code path writes both kinds of observation.
         if (WOBS) {
+            if (bulk_pending) {
+                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                bulk_pending = false;
+                __syncwarp();
+            }
+            if (LY::LATE_FILL ? active : dn) {                              // FUSED: only reset envs are rewritten
+                // [p_vel | p_j - p_i (j != i ascending) | comm zeros | ideal_shape.flatten() | ideal_vel]
+                // (formation_hd_env.py:52-59); own row per lane, odd row stride 3N -> conflict-free STS.64
+                R2* row = s_obs + lane * IPR;
+                const R2* eP = s_pnew + le * 2 * N + i;                     // eP[k] = agent (i + k) mod N
+                const R2* eS = s_shp + le * N;
+                row[0] = v;
+#pragma unroll
+                for (int k = 1; k < N; ++k) {
+                    R2 q = eP[k];
+                    const int slot = (i + k < N) ? (i + k) : (i + k - N + 1);
+                    row[slot] = O::make(O::sub(q.x, p.x), O::sub(q.y, p.y));   // other_pos (formation_hd_env.py:55)
+                }
+#pragma unroll
+                for (int k = 0; k < N - 1; ++k) row[N + k] = zero;          // comm of the others (silent)
+#pragma unroll
+                for (int k = 0; k < N; ++k) row[2 * N - 1 + k] = eS[k];
+                row[3 * N - 1] = iv;
+            }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // generic-proxy writes -> async proxy
             __syncwarp();
             const uint32_t head = obs_head < obs_bytes ? obs_head : obs_bytes;
@@ -404,6 +421,7 @@ __global__ void __launch_bounds__(256) k_hd_warp(const __grid_constant__ KArgs<T
             bulk_pending = true;
         }
     }
+    if (--spans_left == 0) break;
   }  // spans
     // the shared-memory image must outlive the bulk copy's reads
     if (WOBS && bulk_pending && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
