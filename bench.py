@@ -193,6 +193,8 @@ def run_b200(a):
     device = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"          # NCCL's version banner goes to stdout; keep it to ONE JSON line
         dist.init_process_group("nccl", device_id=device)
     dtype = torch.float32 if a.dtype == "f32" else torch.float64
     E, N, K, W = a.envs_per_gpu, a.agents, a.steps, max(a.warmup, 3)
@@ -280,42 +282,40 @@ def run_b200(a):
     stats = fgd.all_reduce_stats(env.stats.clone())
     ep = {"episodes": float(stats[0]), "return_mean": float(stats[1] / stats[0]) if float(stats[0]) else None}
 
-    # ---------------- e2e: public API with pinned HOST buffers ----------------
+    # ---------------- e2e: the reference-facing VecEnv API with HOST (numpy) buffers ----------------
+    # formation_gym.make_vec_env(...).step(actions_np) -> (obs_np, rews_np, dones_np, infos): what the
+    # reference's trainers call on SubprocVecEnv (train/maddpg-v2/utils/env_wrappers.py:63-72).  Per step:
+    # H2D of the actions from pinned host memory, the fused step kernel, D2H of obs / rewards / dones /
+    # individual rewards into pinned host memory, host sync -- all inside the timed region.
     e2e = None
     if env.obs is not None:
         Ke = max(1, a.e2e_steps)
-        act_h = torch.empty(hi - lo, N, 2, dtype=dtype).uniform_(-1, 1).pin_memory()
-        obs_h = torch.empty(env.obs.shape, dtype=dtype).pin_memory()
-        rew_h = torch.empty(env.reward.shape, dtype=dtype).pin_memory()
-        done_h = torch.empty(env.done.shape, dtype=torch.bool).pin_memory()
-        act_d = torch.empty_like(env.actions)
-
-        def e2e_step():
-            act_d.copy_(act_h, non_blocking=True)                 # H2D of this step's inputs
-            obs, rew, done, _ = env.step(act_d)
-            obs_h.copy_(obs, non_blocking=True)                   # D2H of what env.step returns
-            rew_h.copy_(rew, non_blocking=True)
-            done_h.copy_(done, non_blocking=True)
-            torch.cuda.synchronize()                              # the host caller needs the result
-
+        del graph
+        venv = formation_gym.make_vec_env(a.scenario, hi - lo, N, a.episode_length, device=device, dtype=dtype,
+                                          seed=0, env_offset=lo, to_numpy=True)
+        venv.reset()
+        act_h = venv.action_buffer                                # pinned host array [E,N,2]
+        act_h[...] = torch.empty(act_h.shape, dtype=dtype).uniform_(-1, 1).numpy()
+        out_bytes = 0
         for _ in range(2):
-            e2e_step()
+            outs = venv.step(act_h)
+        out_bytes = outs[0].nbytes + outs[1].nbytes + outs[2].nbytes + outs[3].individual_reward.nbytes
         barrier(); torch.cuda.synchronize()
         t0 = time.perf_counter()
         for _ in range(Ke):
-            e2e_step()
-        torch.cuda.synchronize()
+            venv.step(act_h)                                      # returns host arrays (synchronises)
         dt_e = time.perf_counter() - t0
         barrier()
         te = torch.tensor([dt_e], dtype=torch.float64, device=device)
         if world > 1:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
         e2e = {"value": total_agents * Ke / float(te.item()), "unit": UNIT,
-               "h2d_bytes_per_step": act_h.numel() * act_h.element_size() * world,
-               "d2h_bytes_per_step": (obs_h.numel() * obs_h.element_size() + rew_h.numel() * rew_h.element_size()
-                                      + done_h.numel()) * world,
-               "steps": Ke, "note": "H2D actions + fused step + D2H obs/reward/done per step, pinned host "
-                                    "buffers, host sync every step (PCIe-bound: obs is 24N^2 B per env)"}
+               "h2d_bytes_per_step": int(act_h.nbytes) * world,
+               "d2h_bytes_per_step": int(out_bytes) * world,
+               "steps": Ke, "api": "formation_gym.make_vec_env(...).step(numpy actions) -> numpy obs/rews/dones/infos",
+               "note": "H2D actions + fused step + D2H obs/reward/done/individual reward per step, pinned host "
+                       "buffers, host sync every step (PCIe-bound: obs is 24N^2 B per env)"}
+        del venv
 
     if rank != 0:
         if world > 1:

@@ -332,10 +332,12 @@ template <typename T>
 int random_actions_impl(void* act, int E, int N, uint64_t seed, uint32_t tick, uint32_t env_offset,
                         const uint32_t* tick_dev, void* stream) {
     if (!act || E < 1 || N < 1) return fail(FG_ERR_ARG, "fg_random_actions: bad argument%s");
-    const size_t n = (size_t)E * N;
-    const int grid = (int)((n + 255) / 256);
-    fg::k_random_actions<T><<<grid, 256, 0, (cudaStream_t)stream>>>((typename fg::Ops<T>::R2*)act, E, N, seed, tick,
-                                                                   env_offset, tick_dev);
+    if ((uint64_t)E * (uint64_t)N >= (1ull << 31)) return fail(FG_ERR_ARG, "E*N must be < 2^31%s");
+    const uint32_t n = (uint32_t)E * (uint32_t)N;
+    int grid = (int)((n + 255u) / 256u);
+    if (grid > 148 * 32) grid = 148 * 32;                           // grid-stride beyond 32 CTAs per SM
+    fg::k_random_actions<T><<<grid, 256, 0, (cudaStream_t)stream>>>((typename fg::Ops<T>::R2*)act, n, (uint32_t)N,
+                                                                   seed, tick, env_offset, tick_dev);
     cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess) return fail(FG_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(err));
     return FG_OK;

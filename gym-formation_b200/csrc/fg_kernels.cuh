@@ -918,16 +918,25 @@ __global__ void k_reset(const __grid_constant__ KArgs<T> a, const uint8_t* __res
     if (a.ep_coll) a.ep_coll[e] = 0;
 }
 
-// Random policy act ~ U(-1,1) (test.py:20); same counters as the in-kernel rollout.
+// Random policy act ~ U(-1,1) (test.py:20); same counters as the in-kernel rollout.  32-bit indices
+// (E*N < 2^31 is checked by the ABI): one exact 32-bit division per thread, then (env, agent) advance
+// incrementally along the grid-stride loop -- the kernel is a pure Philox + store stream (the 64-bit
+// `g / N` per element it used to carry cost more than the ten Philox rounds).
 template <typename T>
-__global__ void k_random_actions(typename Ops<T>::R2* __restrict__ act, int E, int N, uint64_t seed,
-                                 uint32_t tick, uint32_t env_offset, const uint32_t* __restrict__ tick_dev) {
-    const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= (size_t)E * N) return;
+__global__ void __launch_bounds__(256) k_random_actions(typename Ops<T>::R2* __restrict__ act, uint32_t total, uint32_t N,
+                                                        uint64_t seed, uint32_t tick, uint32_t env_offset,
+                                                        const uint32_t* __restrict__ tick_dev) {
     if (tick_dev) tick += tick_dev[0];
-    const uint32_t e = (uint32_t)(g / N), i = (uint32_t)(g - (size_t)e * N);
-    U4 r = philox(seed, env_offset + e, i, tick, kAction);
-    act[g] = Ops<T>::make(uniform_pm1<T>(r.x), uniform_pm1<T>(r.y));
+    const uint32_t stride = gridDim.x * blockDim.x;
+    const uint32_t se = stride / N, si = stride - se * N;
+    uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t e = g / N, i = g - e * N;
+    for (; g < total; g += stride) {
+        U4 r = philox(seed, env_offset + e, i, tick, kAction);
+        act[g] = Ops<T>::make(uniform_pm1<T>(r.x), uniform_pm1<T>(r.y));
+        e += se; i += si;
+        if (i >= N) { i -= N; ++e; }
+    }
 }
 
 }  // namespace fg

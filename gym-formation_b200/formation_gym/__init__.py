@@ -14,7 +14,8 @@ call that needs the device raises).
 """
 import importlib
 
-__all__ = ["make_env", "make_batched_env", "MultiAgentEnv", "BatchedFormationEnv", "SCENARIOS"]
+__all__ = ["make_env", "make_batched_env", "make_vec_env", "MultiAgentEnv", "BatchedFormationEnv", "CudaVecEnv",
+           "SCENARIOS"]
 
 SCENARIOS = ("basic_formation_env", "formation_hd_env")
 
@@ -53,7 +54,17 @@ def make_batched_env(scenario_name='formation_hd_env', num_envs=4096, num_agents
     return BatchedFormationEnv(scenario_name, num_envs, num_agents, episode_length, **kwargs)
 
 
+def make_vec_env(scenario_name='formation_hd_env', num_envs=128, num_agents=9, episode_length=None, **kwargs):
+    """VecEnv-compatible adapter (``SubprocVecEnv`` / ``DummyVecEnv`` interface of the reference's trainers,
+    train/maddpg-v2/utils/env_wrappers.py:40-128) over the batched CUDA env."""
+    from .vec_env import CudaVecEnv
+    return CudaVecEnv(scenario_name, num_envs, num_agents, episode_length, **kwargs)
+
+
 def __getattr__(name):
+    if name == "CudaVecEnv":
+        from .vec_env import CudaVecEnv
+        return CudaVecEnv
     if name == "MultiAgentEnv":
         from .environment import MultiAgentEnv
         return MultiAgentEnv

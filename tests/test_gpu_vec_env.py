@@ -1,0 +1,93 @@
+"""VecEnv adapter: interface and auto-reset semantics of the reference's
+SubprocVecEnv / DummyVecEnv (train/maddpg-v2/utils/env_wrappers.py:9-128) over the CUDA env."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+import formation_gym  # noqa: E402
+from formation_gym.batched import BatchedFormationEnv  # noqa: E402
+from oracle import mpe_oracle as mo  # noqa: E402
+
+
+def test_vec_env_interface_numpy():
+    E, N, T = 6, 9, 4
+    venv = formation_gym.make_vec_env("formation_hd_env", E, N, episode_length=T, seed=3)
+    assert venv.num_envs == E and venv.num_agents == N
+    assert len(venv.action_space) == N and venv.action_space[0].shape == (2,)
+    assert venv.observation_space[0].shape == (6 * N,)
+    assert venv.share_observation_space[0].shape == (6 * N * N,)
+    assert venv.agent_types == ['agent'] * N
+    obs = venv.reset()
+    assert isinstance(obs, np.ndarray) and obs.shape == (E, N, 6 * N) and obs.dtype == np.float32
+    assert venv.share_obs(obs).shape == (E, N * 6 * N)
+    for t in range(1, 2 * T + 1):
+        actions = np.stack([[sp.sample() for sp in venv.action_space] for _ in range(E)])
+        venv.step_async(actions)
+        with pytest.raises(RuntimeError):
+            venv.step_async(actions)
+        obs, rews, dones, infos = venv.step_wait()
+        assert obs.shape == (E, N, 6 * N) and rews.shape == (E, N, 1) and dones.shape == (E, N)
+        assert dones.dtype == np.bool_
+        assert bool(dones.all()) == (t % T == 0) and bool(dones.any()) == (t % T == 0)
+        assert len(infos) == E and len(infos[0]) == N
+        r = infos[2][5]['individual_reward']
+        assert isinstance(r, float)
+        # shared reward = sum of the individual rewards (environment.py:136-138)
+        assert abs(rews[2, 0, 0] - sum(d['individual_reward'] for d in infos[2])) <= 1e-4 * max(1, abs(rews[2, 0, 0]))
+    with pytest.raises(RuntimeError):
+        venv.step_wait()
+    venv.close()
+    assert venv.closed
+
+
+def test_vec_env_matches_batched_env_and_oracle():
+    """Same seed -> same trajectory as BatchedFormationEnv; one step checked against the numpy oracle."""
+    E, N = 33, 9
+    venv = formation_gym.make_vec_env("formation_hd_env", E, N, episode_length=25, seed=7)
+    ref = BatchedFormationEnv("formation_hd_env", E, N, episode_length=25, seed=7)
+    o1 = venv.reset().copy()
+    o2 = ref.reset()
+    assert np.array_equal(o1, o2.cpu().numpy())
+    st = {k: getattr(ref, k).double().cpu().numpy() for k in ("pos", "vel", "ideal_shape", "ideal_vel")}
+    rng = np.random.default_rng(0)
+    act = rng.uniform(-1, 1, (E, N, 2)).astype(np.float32)
+    obs, rews, dones, infos = venv.step(act)
+    obs2, rew2, done2, info2 = ref.step(torch.as_tensor(act, device="cuda"))
+    assert np.array_equal(obs, obs2.cpu().numpy()) and np.array_equal(rews, rew2.cpu().numpy())
+    assert np.array_equal(infos.individual_reward, info2["individual_reward"].cpu().numpy())
+    want = mo.hd_env_step(st["pos"], st["vel"], act.astype(np.float64), st["ideal_shape"], st["ideal_vel"],
+                          np.zeros(E, np.int64), mo.WorldParams(world_length=25))
+    assert np.abs(obs - want["obs"]).max() <= 1e-5
+    assert np.abs(infos.individual_reward - want["indiv"]).max() <= 1e-5
+
+
+def test_vec_env_auto_reset_returns_reset_obs_with_terminal_reward():
+    """worker(): `if all(done): ob = env.reset()` -- terminal reward/done, RESET observation
+    (env_wrappers.py:14-18)."""
+    E, N, T = 5, 3, 3
+    venv = formation_gym.make_vec_env("formation_hd_env", E, N, episode_length=T, seed=11, to_numpy=False)
+    venv.reset()
+    for _ in range(T):
+        obs, rews, dones, infos = venv.step(venv.sample_actions())
+    assert bool(dones.all())
+    env = venv.env
+    assert int(env.step_count.abs().sum()) == 0                      # current_step = 0 after the reset
+    assert float(env.vel.abs().max()) == 0.0                         # reset_world: p_vel = 0
+    obs_kept = obs.clone()
+    assert torch.equal(env.observe(), obs_kept)                      # the returned obs IS the reset state's obs
+    assert float(rews.abs().min()) > 0.0                             # terminal (non-reset) reward came through
+    # device mode returns CUDA tensors without a host round trip
+    assert obs.is_cuda and rews.is_cuda and dones.is_cuda and infos.individual_reward.is_cuda
+
+
+def test_vec_env_pinned_action_buffer_and_basic_scenario():
+    venv = formation_gym.make_vec_env("basic_formation_env", 4, 3, episode_length=5, seed=1)
+    obs = venv.reset()
+    assert obs.shape == (4, 3, 18)
+    buf = venv.action_buffer
+    buf[...] = 0.25
+    obs, rews, dones, infos = venv.step(buf)
+    assert obs.shape == (4, 3, 18) and rews.shape == (4, 3, 1)
+    assert np.isfinite(obs).all() and np.isfinite(rews).all()
