@@ -392,6 +392,8 @@ def also_configs(formation_gym, torch, device, dtype, peak):
             ("configs[1] hd N=9 E=4096 (launch-bound; per-step launches)", "formation_hd_env", 9, 4096, 500, "step"),
             ("configs[1] hd N=9 E=4096 (CUDA graph of 25 per-step launches)", "formation_hd_env", 9, 4096, 40, "graph"),
             ("configs[1] hd N=9 E=4096 (in-kernel 25-step rollouts)", "formation_hd_env", 9, 4096, 40, "rollout"),
+            ("hd N=9 E=131072, device controller get_action_BFS(ezpolicy) instead of the random policy",
+             "formation_hd_env", 9, 131072, 50, "bfs"),
             ("configs[2] hd N=27 E=65536", "formation_hd_env", 27, 65536, 50, "step"),
             ("configs[3] hd N=243 E=1024 (one GPU's share of 8192)", "formation_hd_env", 243, 1024, 30, "step"),
             ("hd N=243 E=1024 state+reward only (no obs)", "formation_hd_env", 243, 1024, 30, "noobs"),
@@ -410,6 +412,8 @@ def also_configs(formation_gym, torch, device, dtype, peak):
                         env.rollout_random(25)
                     elif mode == "graph":
                         graph.replay()
+                    elif mode == "bfs":
+                        env.step(env.bfs_actions(3))
                     else:
                         env.sample_actions(); env.step(env.actions)
             run(5)

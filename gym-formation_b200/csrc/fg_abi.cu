@@ -11,6 +11,7 @@
 
 #include "fg_kernels.cuh"
 #include "fg_warp.cuh"
+#include "fg_policy.cuh"
 
 namespace {
 
@@ -343,9 +344,44 @@ int random_actions_impl(void* act, int E, int N, uint64_t seed, uint32_t tick, u
     return FG_OK;
 }
 
+template <typename T>
+int policy_bfs_impl(const void* pos, const void* shape, const void* ivel, void* act, int E, int N, int n,
+                    void* stream) {
+    typedef typename fg::Ops<T>::R2 R2;
+    if (!pos || !shape || !ivel || !act) return fail(FG_ERR_ARG, "fg_policy_bfs: null pointer%s");
+    if (E < 1 || N < 1 || N > FG_MAX_AGENTS) return fail(FG_ERR_ARG, "fg_policy_bfs: bad E or N%s");
+    if (n < 2 || n > fg::kPolicyMaxFan) return fail(FG_ERR_ARG, "fg_policy_bfs: num_agents_per_layer must be in [2, 8]%s");
+    fg::PArgs<T> a;
+    memset(&a, 0, sizeof(a));
+    int levels = 0, M = N;
+    while (M > 1 && M % n == 0) { M /= n; ++levels; }
+    // the reference asserts log(len(obs))/log(n) is an integer (formation_gym/__init__.py:55-56)
+    if (M != 1 || levels < 1 || levels > fg::kPolicyMaxLevels)
+        return fail(FG_ERR_ARG, "fg_policy_bfs: N must be a power of num_agents_per_layer ('Observation shape error!')%s");
+    a.pos = (const R2*)pos; a.shape = (const R2*)shape; a.ivel = (const R2*)ivel; a.act = (R2*)act;
+    a.E = E; a.N = N; a.n = n; a.levels = levels; a.EPC = fg::kBlock / N; a.magic_n = magic_for(N);
+    M = N;
+    for (int l = 0; l < levels; ++l) { a.mult[l] = (T)(std::log((double)M) / std::log((double)n)); M /= n; }   // :78
+    const size_t smem = (size_t)4 * a.EPC * N * sizeof(R2);
+    const int grid = (E + a.EPC - 1) / a.EPC;
+    fg::k_policy_bfs<T><<<grid, fg::kBlock, smem, (cudaStream_t)stream>>>(a);
+    cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess) return fail(FG_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(err));
+    return FG_OK;
+}
+
 }  // namespace
 
 extern "C" {
+
+int fg_policy_bfs(const void* pos, const void* ideal_shape, const void* ideal_vel, void* act, int E, int N,
+                  int num_agents_per_layer, void* stream) {
+    return policy_bfs_impl<float>(pos, ideal_shape, ideal_vel, act, E, N, num_agents_per_layer, stream);
+}
+int fg_policy_bfs_f64(const void* pos, const void* ideal_shape, const void* ideal_vel, void* act, int E, int N,
+                      int num_agents_per_layer, void* stream) {
+    return policy_bfs_impl<double>(pos, ideal_shape, ideal_vel, act, E, N, num_agents_per_layer, stream);
+}
 
 int fg_abi_version(void) { return FG_ABI_VERSION; }
 

@@ -1,0 +1,155 @@
+// fg_policy.cuh -- the reference's hand-written controller on the device (sm_100a):
+// ezpolicy (formation_gym/__init__.py:19-47) expanded hierarchically by get_action_BFS
+// (formation_gym/__init__.py:49-98), for every env of a batch in one launch.
+//
+// The reference walks per-agent observation lists on the host; every value it slices out of an
+// observation is pos[b] - pos[a], ideal_shape or ideal_vel (formation_hd_env.py:52-59; p_vel is read but
+// unused), so the kernel works from the env STATE and never touches the [E,N,6N] observation tensor:
+// 16N + 8 bytes read and 8N written per env instead of 24N^2 read.
+//
+// Mapping: one CTA owns EPC = floor(256 / N) envs, thread <-> (local env, agent).  The BFS tree has
+// `levels` = log_n(N) layers; at the layer with groups of M agents, the first agent of each of the n
+// subgroups of a group (the "leader", :61) builds the n-agent layer observation from subgroup centroids
+// (:65-74), runs ezpolicy, scales by the layer number (:78-79) and hands the result down as the subgroup's
+// target velocity (:84-97) through shared memory; the last layer writes the actions (:81-83).
+#pragma once
+#include "fg_math.cuh"
+
+namespace fg {
+
+constexpr int kPolicyMaxFan = 8;        // agents per layer n <= 8
+constexpr int kPolicyMaxLevels = 8;
+
+template <typename T> struct PArgs {
+    typedef typename Ops<T>::R2 R2;
+    const R2* pos; const R2* shape; const R2* ivel; R2* act;
+    int E, N, n, levels, EPC;
+    uint32_t magic_n;
+    T mult[kPolicyMaxLevels];           // log(M)/log(n) per layer, top first (:78)
+};
+
+// formation_gym/__init__.py:19-47 on the sliced inputs: others [n-1] (other_pos), tgt [n] (ideal_shape
+// before re-centring), tvel (ideal_vel).
+template <typename T>
+__device__ __forceinline__ typename Ops<T>::R2 ezpolicy_dev(const typename Ops<T>::R2* others,
+                                                            const typename Ops<T>::R2* tgt,
+                                                            typename Ops<T>::R2 tvel, int n) {
+    typedef Ops<T> O;
+    typedef typename O::R2 R2;
+    R2 ideal[kPolicyMaxFan], cur[kPolicyMaxFan];
+    T d[kPolicyMaxFan];
+    int order[kPolicyMaxFan];
+    // ideal_shape - mean (:28); current_shape = [other_pos, (0,0)] - mean (:31-33): sums in row order
+    T sx = 0, sy = 0, cx = 0, cy = 0;
+    for (int k = 0; k < n; ++k) {
+        sx = O::add(sx, tgt[k].x); sy = O::add(sy, tgt[k].y);
+        const R2 c = (k < n - 1) ? others[k] : O::make((T)0, (T)0);
+        cur[k] = c;
+        cx = O::add(cx, c.x); cy = O::add(cy, c.y);
+    }
+    sx = O::div(sx, (T)n); sy = O::div(sy, (T)n); cx = O::div(cx, (T)n); cy = O::div(cy, (T)n);
+    for (int k = 0; k < n; ++k) {
+        ideal[k] = O::make(O::sub(tgt[k].x, sx), O::sub(tgt[k].y, sy));
+        cur[k] = O::make(O::sub(cur[k].x, cx), O::sub(cur[k].y, cy));
+    }
+    const R2 self = cur[n - 1];
+    // argsort of the distances from me to the landmarks (:35); insertion sort = numpy's small-n path
+    for (int k = 0; k < n; ++k) {
+        d[k] = O::norm2(O::sub(self.x, ideal[k].x), O::sub(self.y, ideal[k].y));
+        int j = k;
+        while (j > 0 && d[order[j - 1]] > d[k]) { order[j] = order[j - 1]; --j; }
+        order[j] = k;
+    }
+    R2 act = O::make((T)0, (T)0);
+    for (int r = 0; r < n; ++r) {                                             // :36-40
+        const int idx = order[r];
+        int closest = 0;
+        T best = O::norm2(O::sub(cur[0].x, ideal[idx].x), O::sub(cur[0].y, ideal[idx].y));
+        for (int m = 1; m < n; ++m) {
+            const T dm = O::norm2(O::sub(cur[m].x, ideal[idx].x), O::sub(cur[m].y, ideal[idx].y));
+            if (dm < best) { best = dm; closest = m; }                        // np.argmin: first minimum
+        }
+        if (closest == n - 1 || r == n - 1) {
+            T ax = O::mul((T)0.5, O::sub(ideal[idx].x, self.x));
+            T ay = O::mul((T)0.5, O::sub(ideal[idx].y, self.y));
+            act = O::make(fmin(fmax(ax, (T)-1), (T)1), fmin(fmax(ay, (T)-1), (T)1));   // np.clip
+            break;
+        }
+    }
+    // done = ||ideal_shape - current_shape||_F < 0.01 (:42)
+    T fro = 0;
+    for (int k = 0; k < n; ++k) {
+        const T ex = O::sub(ideal[k].x, cur[k].x), ey = O::sub(ideal[k].y, cur[k].y);
+        fro = O::add(fro, O::add(O::mul(ex, ex), O::mul(ey, ey)));
+    }
+    const bool done = O::sqrt_(fro) < (T)0.01;
+    const T g = done ? (T)1 : (T)0.3;                                         // :43-46
+    return O::make(O::add(act.x, done ? tvel.x : O::mul(tvel.x, g)), O::add(act.y, done ? tvel.y : O::mul(tvel.y, g)));
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_policy_bfs(const __grid_constant__ PArgs<T> a) {
+    typedef Ops<T> O;
+    typedef typename O::R2 R2;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int N = a.N, n = a.n, nA = a.EPC * N;
+    R2* s_p = reinterpret_cast<R2*>(smem_raw);
+    R2* s_s = s_p + nA;
+    R2* s_tv0 = s_s + nA;                 // target velocity of the group each agent is in (ping-pong)
+    R2* s_tv1 = s_tv0 + nA;
+    const int t = threadIdx.x;
+    const int le = (int)fastdiv((uint32_t)t, a.magic_n);
+    const int i = t - le * N;
+    const int e = blockIdx.x * a.EPC + le;
+    const bool active = t < nA && e < a.E;
+    const size_t g = (size_t)e * N + i;
+    if (active) {
+        s_p[t] = a.pos[g];
+        s_s[t] = a.shape[g];
+        s_tv0[t] = a.ivel[e];                                                 // top layer: the env's ideal_vel (:74)
+    }
+    __syncthreads();
+    const R2* P = s_p + le * N;
+    const R2* S = s_s + le * N;
+    int M = N;
+    for (int l = 0; l < a.levels; ++l) {
+        const int nxt = M / n;
+        if (active && (i % nxt) == 0) {                                       // leaders of this layer (:61)
+            const int gb = (i / M) * M;                                       // first agent of my group
+            const int si = (i - gb) / nxt;                                    // my subgroup within the group
+            const R2 pi = P[i];
+            R2 cur[kPolicyMaxFan], tgt[kPolicyMaxFan], others[kPolicyMaxFan];
+            for (int k = 0; k < n; ++k) {
+                // centroid of subgroup k in my frame (:65-66) and of its target points (:70-71): np.mean sums
+                // the rows in order and divides by the count
+                T cx = 0, cy = 0, tx = 0, ty = 0;
+                const int b0 = gb + k * nxt;
+                for (int b = b0; b < b0 + nxt; ++b) {
+                    const R2 q = P[b];
+                    const T rx = (b == i) ? (T)0 : O::sub(q.x, pi.x);         // own slot is the inserted (0,0)
+                    const T ry = (b == i) ? (T)0 : O::sub(q.y, pi.y);
+                    cx = O::add(cx, rx); cy = O::add(cy, ry);
+                    const R2 sb = S[b];
+                    tx = O::add(tx, sb.x); ty = O::add(ty, sb.y);
+                }
+                cur[k] = O::make(O::div(cx, (T)nxt), O::div(cy, (T)nxt));
+                tgt[k] = O::make(O::div(tx, (T)nxt), O::div(ty, (T)nxt));
+            }
+            const R2 own = cur[si];                                           // :67-68
+            int w = 0;
+            for (int k = 0; k < n; ++k) {
+                if (k == si) continue;
+                others[w++] = O::make(O::sub(cur[k].x, own.x), O::sub(cur[k].y, own.y));
+            }
+            R2 out = ezpolicy_dev<T>(others, tgt, s_tv0[t], n);               // :76-79
+            out = O::make(O::mul(out.x, a.mult[l]), O::mul(out.y, a.mult[l]));
+            if (nxt == 1) a.act[g] = out;                                     // :81-83
+            else for (int b = 0; b < nxt; ++b) s_tv1[t + b] = out;            // tar_vel of my subgroup (:84-97)
+        }
+        __syncthreads();
+        R2* tmp = s_tv0; s_tv0 = s_tv1; s_tv1 = tmp;
+        M = nxt;
+    }
+}
+
+}  // namespace fg

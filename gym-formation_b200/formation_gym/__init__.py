@@ -14,8 +14,8 @@ call that needs the device raises).
 """
 import importlib
 
-__all__ = ["make_env", "make_batched_env", "make_vec_env", "MultiAgentEnv", "BatchedFormationEnv", "CudaVecEnv",
-           "SCENARIOS"]
+__all__ = ["make_env", "make_batched_env", "make_vec_env", "ezpolicy", "get_action_BFS", "MultiAgentEnv",
+           "BatchedFormationEnv", "CudaVecEnv", "SCENARIOS"]
 
 SCENARIOS = ("basic_formation_env", "formation_hd_env")
 
@@ -59,6 +59,86 @@ def make_vec_env(scenario_name='formation_hd_env', num_envs=128, num_agents=9, e
     train/maddpg-v2/utils/env_wrappers.py:40-128) over the batched CUDA env."""
     from .vec_env import CudaVecEnv
     return CudaVecEnv(scenario_name, num_envs, num_agents, episode_length, **kwargs)
+
+
+def _policy_device(pos, shape, ivel, n):
+    """One env through the device controller (fg_policy_bfs_f64): pos/shape [N,2], ivel [2] -> act [N,2]."""
+    import ctypes as C
+    import numpy as np
+    import torch
+    from . import _native as nat
+    lib = nat.load()
+    if not torch.cuda.is_available():
+        raise nat.NativeError("no CUDA device: formation_gym has no CPU fallback")
+    kw = dict(dtype=torch.float64, device="cuda")
+    p = torch.as_tensor(np.ascontiguousarray(pos, dtype=np.float64), **kw).reshape(1, -1, 2)
+    s_ = torch.as_tensor(np.ascontiguousarray(shape, dtype=np.float64), **kw).reshape(1, -1, 2)
+    v = torch.as_tensor(np.ascontiguousarray(ivel, dtype=np.float64), **kw).reshape(1, 2)
+    act = torch.empty_like(p)
+    rc = lib.fg_policy_bfs_f64(p.data_ptr(), s_.data_ptr(), v.data_ptr(), act.data_ptr(), 1, p.shape[1], int(n),
+                               C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    nat.check(rc, "fg_policy_bfs_f64")
+    return act[0].cpu().numpy()
+
+
+def ezpolicy(obs):
+    """Reference signature (formation_gym/__init__.py:19-47): the hand-written controller of ONE agent from
+    its formation_hd_env observation (length 6n).  Evaluated by the device kernel behind ``fg_policy_bfs``:
+    the observation is unpacked into an n-agent state in which this agent is the last one (its
+    ``current_shape`` row, :31), whose action is the result."""
+    import numpy as np
+    obs = np.asarray(obs, dtype=np.float64)
+    n = len(obs) / 6
+    assert n.is_integer(), n
+    n = int(n)
+    pos = np.concatenate([obs[2:2 * n], [0.0, 0.0]]).reshape(n, 2)          # others, then me at the origin
+    shape = obs[4 * n - 2:6 * n - 2].reshape(n, 2)
+    return _policy_device(pos, shape, obs[-2:], n)[n - 1]
+
+
+def get_action_BFS(policy, obs, num_agents_per_layer):
+    """Reference signature (formation_gym/__init__.py:49-98): expand ``policy`` hierarchically over the
+    per-agent observation list ``obs`` and return the list of actions.
+
+    With ``policy is formation_gym.ezpolicy`` (the reference's demo, test.py:23) the whole tree runs in ONE
+    device launch (``fg_policy_bfs_f64``): agent 0's observation gives every position relative to agent 0,
+    the ideal shape and the ideal velocity (formation_hd_env.py:52-59).  Any other callable is user code:
+    the tree is walked on the host exactly like the reference does and only ``policy`` itself is called."""
+    import numpy as np
+    n = int(num_agents_per_layer)
+    N = len(obs)
+    num_layer = np.log(N) / np.log(n)
+    assert num_layer.is_integer(), 'Observation shape error!'
+    if policy is ezpolicy:
+        o0 = np.asarray(obs[0], dtype=np.float64)
+        pos = np.concatenate([[0.0, 0.0], o0[2:2 * N]]).reshape(N, 2)         # agent 0 at the origin
+        act = _policy_device(pos, o0[4 * N - 2:6 * N - 2].reshape(N, 2), o0[-2:], n)
+        return [act[i] for i in range(N)]
+    queue, act = [[np.asarray(o, dtype=np.float64) for o in obs]], []
+    while queue:
+        layer_obs = queue.pop(0)
+        M = len(layer_obs)
+        nxt = M // n
+        for i in range(n):
+            lead = layer_obs[i * nxt]
+            cur = np.insert(lead[2:2 * M], 2 * i * nxt, [0, 0]).reshape(-1, 2)
+            cur = np.array([cur[nxt * k:nxt * (k + 1)].mean(axis=0) for k in range(n)])
+            cur = np.delete(cur - cur[i], i, 0).flatten()
+            ideal = lead[4 * M - 2:6 * M - 2].reshape(-1, 2)
+            tgt = np.array([ideal[nxt * k:nxt * (k + 1)].mean(axis=0) for k in range(n)]).flatten()
+            obs_in = np.concatenate((lead[:2], cur, [0] * 2 * (n - 1), tgt, lead[-2:]))
+            tar_vel = policy(obs_in) * (np.log(M) / np.log(n))
+            if nxt == 1:
+                act.append(tar_vel)
+                continue
+            sub = []
+            for j in range(i * nxt, (i + 1) * nxt):
+                o = layer_obs[j]
+                sub.append(np.concatenate((o[:2], o[2:2 * M][2 * i * nxt:2 * (i + 1) * nxt - 2],
+                                           [0] * 2 * (nxt - 1),
+                                           o[4 * M - 2:6 * M - 2][2 * i * nxt:2 * (i + 1) * nxt], tar_vel)))
+            queue.append(sub)
+    return act
 
 
 def __getattr__(name):

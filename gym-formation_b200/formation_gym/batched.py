@@ -265,6 +265,23 @@ class BatchedFormationEnv:
             self.launches += 1
         return out
 
+    def bfs_actions(self, num_agents_per_layer=3, out=None):
+        """``get_action_BFS(ezpolicy, obs_n, num_agents_per_layer)`` of the reference
+        (formation_gym/__init__.py:19-98; the demo policy of test.py:23) for every env, on the device, from
+        the current state.  Writes and returns ``self.actions`` (or ``out``) [E,N,2]."""
+        if self.scn != nat.FG_SCENARIO_HD:
+            raise nat.NativeError("the hand-written controller is defined for formation_hd_env observations")
+        if not self.silent:
+            raise nat.NativeError("bfs_actions supports silent agents only (action = [u])")
+        out = self.actions if out is None else out
+        with self._on_device():
+            rc = self._fn("fg_policy_bfs")(nat.ptr(self.pos), nat.ptr(self.ideal_shape), nat.ptr(self.ideal_vel),
+                                           nat.ptr(out), self.E, self.N, int(num_agents_per_layer),
+                                           self._stream())
+            nat.check(rc, "fg_policy_bfs")
+            self.launches += 1
+        return out
+
     def rollout_random(self, n_steps):
         """``n_steps`` random-policy steps in ONE launch with the state held on chip; obs / reward /
         done buffers hold the last step's values afterwards."""

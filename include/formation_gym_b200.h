@@ -174,6 +174,18 @@ int fg_random_actions(void* act, int E, int N, uint64_t seed, uint32_t tick, uin
 int fg_random_actions_f64(void* act, int E, int N, uint64_t seed, uint32_t tick,
                           uint32_t env_offset, const uint32_t* tick_dev, void* stream);
 
+/* The reference's hand-written controller for formation_hd_env, for every env of a batch in one launch:
+ * get_action_BFS(ezpolicy, obs_n, num_agents_per_layer) (formation_gym/__init__.py:19-47,49-98; the default
+ * policy of the reference's demo loop, test.py:23).  Works from the env STATE -- every value the reference
+ * slices out of the per-agent observations is pos[b] - pos[a], ideal_shape or ideal_vel
+ * (formation_hd_env.py:52-59) -- and writes act [E,N,2], ready for fg_step_fused.  N must be a power of
+ * num_agents_per_layer (2..8), as the reference asserts (:55-56); unlike the reference, N = 243 with
+ * 3 agents per layer is accepted (its floating-point log ratio 4.999999999999999 fails that assertion). */
+int fg_policy_bfs(const void* pos, const void* ideal_shape, const void* ideal_vel, void* act, int E, int N,
+                  int num_agents_per_layer, void* stream);
+int fg_policy_bfs_f64(const void* pos, const void* ideal_shape, const void* ideal_vel, void* act, int E, int N,
+                      int num_agents_per_layer, void* stream);
+
 /* Diagnostics, not on the step path: FP32 pipe probes used by bench.py to MEASURE the FP32 peak the
  * large-N step+reward kernel is graded against (BASELINE.json north_star: "% of FP32 peak at 243
  * agents"; MEASURED_PEAKS.json holds no FP32 figure).  variant 0: scalar FFMA (2 flop/lane/instr),

@@ -1,0 +1,88 @@
+"""Device controller: fg_policy_bfs against get_action_BFS(ezpolicy, obs_n, 3) of the
+unmodified reference (tests/golden/policy_bfs_*.npz) and against the numpy oracle."""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+import formation_gym  # noqa: E402
+from formation_gym.batched import BatchedFormationEnv  # noqa: E402
+from oracle import policy_oracle as po  # noqa: E402
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+FILES = sorted(glob.glob(os.path.join(GOLD, "policy_bfs_*.npz")))
+
+
+def _run(pos, shape, ivel, dtype, n=3):
+    E, N = pos.shape[:2]
+    env = BatchedFormationEnv("formation_hd_env", E, N, episode_length=25, dtype=dtype, auto_reset=False)
+    env.pos.copy_(torch.as_tensor(pos, dtype=dtype, device="cuda"))
+    env.ideal_shape.copy_(torch.as_tensor(shape, dtype=dtype, device="cuda"))
+    env.ideal_vel.copy_(torch.as_tensor(ivel, dtype=dtype, device="cuda"))
+    return env, env.bfs_actions(n).double().cpu().numpy()
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64], ids=["f32", "f64"])
+@pytest.mark.parametrize("path", FILES, ids=[os.path.basename(f) for f in FILES])
+def test_policy_bfs_golden(path, dtype):
+    g = np.load(path)
+    _, act = _run(g["pos"], g["shape"], g["ivel"], dtype)
+    err = np.abs(act - g["act"]).max(axis=(1, 2))                   # per sample
+    if dtype == torch.float64:
+        assert err.max() <= 1e-12
+    else:
+        # fp32: 1e-5, except that a sample sitting on a decision boundary of the controller (argsort /
+        # argmin / the 0.01 `done` threshold) may take the other branch; such samples must be rare
+        bad = err > 1e-5
+        assert bad.mean() <= 0.05, (bad.sum(), err[bad])
+
+
+@pytest.mark.parametrize("E,N,n", [(40, 243, 3), (300, 9, 3), (17, 81, 3), (64, 16, 4), (64, 8, 2), (9, 64, 8)])
+def test_policy_bfs_vs_oracle(E, N, n):
+    """Sizes the goldens do not hold, including N = 243 (the reference's own assertion rejects it) and other
+    fan-outs; fp64 build."""
+    rng = np.random.default_rng(N * 7 + n)
+    f32 = lambda x: x.astype(np.float32).astype(np.float64)  # noqa: E731
+    lm = rng.uniform(-1, 1, (E, N, 2))
+    shape = f32(lm - lm.mean(1, keepdims=True))
+    pos = f32(rng.uniform(-1, 1, (E, N, 2)))
+    ivel = f32(rng.uniform(-1, 1, (E, 2)))
+    want = po.bfs_actions_batch(pos, shape, ivel, n)
+    _, act = _run(pos, shape, ivel, torch.float64, n)
+    assert np.abs(act - want).max() <= 1e-11
+
+
+def test_policy_bfs_rejects_non_power():
+    env = BatchedFormationEnv("formation_hd_env", 4, 10, episode_length=25, auto_reset=False)
+    with pytest.raises(Exception, match="power of num_agents_per_layer"):
+        env.bfs_actions(3)
+
+
+def test_policy_drives_formation_and_facade_functions():
+    """Closed loop: the controller reduces the formation error (the reference's demo, test.py:14-28), and the
+    reference-signature host functions agree with the batched kernel."""
+    E, N = 64, 9
+    env = BatchedFormationEnv("formation_hd_env", E, N, episode_length=200, dtype=torch.float64, seed=5,
+                              auto_reset=False)
+    obs = env.reset()
+    first = None
+    for t in range(150):
+        obs, rew, done, info = env.step(env.bfs_actions(3))
+        if t == 0:
+            first = float(rew.mean())
+    assert float(rew.mean()) > first + 1.0                         # reward = -(shape error) - ... improves
+    # facade functions on one env's observations
+    o = obs[3].cpu().numpy()
+    obs_n = [o[i] for i in range(N)]
+    want = env.bfs_actions(3)[3].cpu().numpy()
+    got = formation_gym.get_action_BFS(formation_gym.ezpolicy, obs_n, 3)
+    assert np.abs(np.stack(got) - want).max() <= 1e-9
+    # a user-supplied callable walks the tree on the host and calls only the callable
+    calls = []
+    got2 = formation_gym.get_action_BFS(lambda ob: (calls.append(len(ob)), formation_gym.ezpolicy(ob))[1], obs_n, 3)
+    assert len(calls) == 3 + 9 and set(calls) == {18}
+    assert np.abs(np.stack(got2) - want).max() <= 1e-9
