@@ -396,6 +396,7 @@ def also_configs(formation_gym, torch, device, dtype, peak):
              "formation_hd_env", 9, 131072, 50, "bfs"),
             ("configs[2] hd N=27 E=65536", "formation_hd_env", 27, 65536, 50, "step"),
             ("configs[3] hd N=243 E=1024 (one GPU's share of 8192)", "formation_hd_env", 243, 1024, 30, "step"),
+            ("configs[3] hd N=243 E=8192 (all 8192 envs on one GPU: steady state, no wave tail)", "formation_hd_env", 243, 8192, 8, "step"),
             ("hd N=243 E=1024 state+reward only (no obs)", "formation_hd_env", 243, 1024, 30, "noobs"),
             ("hd N=3 E=1048576", "formation_hd_env", 3, 1048576, 50, "step"),
             ("basic N=3 L=3 E=1048576", "basic_formation_env", 3, 1048576, 50, "step")):

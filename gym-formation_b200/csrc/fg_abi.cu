@@ -104,6 +104,15 @@ int fill_args(fg::KArgs<T>& a, const fg_params* p, const fg_buffers* b, int scen
     }
     a.row_tma = scenario == FG_SCENARIO_HD && p->silent && a.IPR >= 144 && b->obs &&
                 ((uintptr_t)b->obs % sizeof(R2)) == 0;
+    {
+        const char* nb = getenv("FG_ROW_NBUF");
+        a.row_nbuf = (nb && nb[0] == '1') ? 1 : 2;
+    }
+    {
+        const char* late = getenv("FG_NO_EARLY_ROWS");                 // A/B switch for tests and profiling
+        a.row_early = a.row_tma && sizeof(R2) == 8 && (N & 1) && ((uintptr_t)b->obs % 16) == 0 &&
+                      !(late && late[0] == '1');
+    }
     return FG_OK;
 }
 
@@ -119,7 +128,7 @@ size_t smem_bytes(const fg::KArgs<T>& a, int scenario, bool het) {
     if (het) s += 5 * (size_t)a.N * sizeof(T);
     s += 3 * a.EPC * sizeof(int);
     if (a.row_tma)                                                      // static row images + per-warp staging
-        s += ((size_t)2 * (2 * a.N + 1) * a.EPC + (size_t)2 * ((a.N + 3) & ~1) * (fg::kBlock / 32)) * sizeof(R2);
+        s += ((size_t)2 * (2 * a.N + 1) * a.EPC + (size_t)a.row_nbuf * ((a.N + 3) & ~1) * (fg::kBlock / 32)) * sizeof(R2);
     return (s + 15) & ~(size_t)15;
 }
 

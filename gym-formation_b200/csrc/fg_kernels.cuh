@@ -52,6 +52,9 @@ template <typename T> struct KArgs {
     int has_accel, has_vmax, collide, silent, world_length, n_walls, prescaled;
     int mass_one;                    // mass == 1: F / m is exact without the division
     int row_tma;                     // tile kernel: long hd rows leave through TMA bulk stores (see k_step)
+    int row_nbuf;                    // OM == 2: staging buffers per warp (2; 1 when that lets one more CTA fit per SM)
+    int row_early;                   // OM == 2, fp32, odd N, 16-byte aligned obs: rows leave as aligned bulk pieces, the
+                                     // static 2/3 before the physics and the dynamic 1/3 before the reward pass
     int fast_pairs;                  // tile kernel: packed pair loops of fg_pairs.cuh (N >= 32; fp32 hd uniform only)
     int n_steps, random_actions, auto_reset;
     uint64_t seed; uint32_t tick; uint32_t env_offset;
@@ -174,7 +177,8 @@ __global__ void __launch_bounds__(kBlock, (OM == 2) ? 4 : 3) k_step(const __grid
     // FP: per local env, arrays of NP = roundup(N, 32) floats (16-byte aligned): old positions and
     // their squared norms, centred new positions and norms, centred ideal shape.
     const int NP = (N + 31) & ~31;
-    float* f_base = reinterpret_cast<float*>(s_rt_dyn + (OM == 2 ? 2 * rt_dyn * (kBlock / 32) : 0));
+    const int NB = a.row_nbuf;
+    float* f_base = reinterpret_cast<float*>(s_rt_dyn + (OM == 2 ? NB * rt_dyn * (kBlock / 32) : 0));
     float* f_xo = f_base;              float* f_yo = f_xo + EPC * NP;   float* f_no = f_yo + EPC * NP;
     float* f_cx = f_no + EPC * NP;     float* f_cy = f_cx + EPC * NP;   float* f_nc = f_cy + EPC * NP;
     float* f_sx = f_nc + EPC * NP;     float* f_sy = f_sx + EPC * NP;
@@ -251,6 +255,14 @@ __global__ void __launch_bounds__(kBlock, (OM == 2) ? 4 : 3) k_step(const __grid
                 const R2 S0 = a.shape[g];
                 s_s[t] = S0;
                 if constexpr (FP) { f_sx[le * NP + i] = (float)S0.x; f_sy[le * NP + i] = (float)S0.y; }
+                if constexpr (OM == 2) {
+                    if (a.row_early) {        // static row images [comm zeros (N-1) | ideal_shape (N) | ideal_vel], both phases
+                        R2* im0 = s_rt_img + (size_t)le * 2 * rt_img;
+                        R2* im1 = im0 + rt_img;
+                        im0[N - 1 + i] = S0; im1[N - 1 + i] = S0;
+                        if (i < N - 1) { im0[i] = O::make((T)0, (T)0); im1[i] = O::make((T)0, (T)0); }
+                    }
+                }
             }
             if (a.step) stp = a.step[e];
             if (!PHYS) s_c[t] = a.comm ? a.comm[g] : O::make((T)0, (T)0);
@@ -258,7 +270,16 @@ __global__ void __launch_bounds__(kBlock, (OM == 2) ? 4 : 3) k_step(const __grid
     }
     if (OBSREW) {
         if (SCN == kScnHD) {
-            if (active && i == 0) s_iv[le] = a.ivel[e];
+            if (active && i == 0) {
+                const R2 iv0 = a.ivel[e];
+                s_iv[le] = iv0;
+                if constexpr (OM == 2) {
+                    if (a.row_early) {
+                        R2* im0 = s_rt_img + (size_t)le * 2 * rt_img;
+                        im0[2 * N - 1] = iv0; im0[rt_img + 2 * N - 1] = iv0;
+                    }
+                }
+            }
         } else {
             for (int q = t; q < nvalid * L; q += kBlock) s_s[q] = a.lm[(size_t)tile0 * L + q];
         }
@@ -290,7 +311,21 @@ __global__ void __launch_bounds__(kBlock, (OM == 2) ? 4 : 3) k_step(const __grid
             }
             if (t < EPC * 32) f_part[t] = 0.f;
         }
-        __syncthreads();
+        // Early observation rows (OM == 2, a.row_early): unless an env of this tile ends its episode in this
+        // step (then the rows must show the RESET state and everything is written after the reset, below),
+        // the static 2/3 of every row is sent NOW, from the shared images, and drains while the physics runs.
+        bool early = false;
+        if constexpr (OM == 2 && sizeof(R2) == 8) {
+            if (a.obs && a.row_early) {
+                const bool will_reset = active && a.auto_reset && a.step && (stp + 1 >= a.world_length);
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // images (generic proxy) -> async proxy
+                early = !__syncthreads_or(will_reset ? 1 : 0);
+            } else {
+                __syncthreads();
+            }
+        } else {
+            __syncthreads();
+        }
 
         // =============================== World.step (core.py:206-225) ===========================
         if (PHYS) {
@@ -461,6 +496,66 @@ __global__ void __launch_bounds__(kBlock, (OM == 2) ? 4 : 3) k_step(const __grid
             }
             if (!OBSREW) { tick_arrive(a.tick_dev, gridDim.x, a.n_steps, t == 0); return; }
             __syncthreads();
+        }
+        if constexpr (OM == 2 && sizeof(R2) == 8) {
+            if (early) {
+                // Dynamic 1/3 of every row, one warp per row, BEFORE the reward pass so that the stores drain
+                // under it.  Pieces are 16-byte aligned on both ends: an even row sends [p_vel | other_pos | first
+                // comm zero] (N+1 items) from its start; an odd row starts 8 bytes early with the previous
+                // row's ideal_vel.  Only the first row of the tile (if odd) and the last (if even) need one
+                // plain 8-byte store.
+                R2* dyn2 = s_rt_dyn + wp_ * NB * rt_dyn;                         // NB staging buffers per warp
+                const int nrows = nvalid * N;
+                uint64_t pol;
+                asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+                int pending = 0;
+                for (int row = wp_; row < nrows; row += kBlock / 32) {
+                    R2* img = dyn2 + (NB == 2 ? (pending & 1) : 0) * rt_dyn;
+                    const int rle = (int)fastdiv((uint32_t)row, a.magic_n);
+                    const int ri = row - rle * N;
+                    const size_t grow = (size_t)tile0 * N + row;
+                    R2* out = a.obs + grow * a.IPR;
+                    const bool odd = (grow & 1) != 0;
+                    if (lane_ == 0) {            // the buffer being refilled must have been read by its bulk copy
+                        if (NB == 2) { if (pending >= 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+                        else if (pending >= 1) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                    }
+                    __syncwarp();
+                    const R2* P = s_new + rle * N;
+                    const R2 pi = P[ri];
+                    // layout of the staged piece: even [v, rel(N-1), 0]; odd (row > 0) [iv_prev, v, rel(N-1)];
+                    // odd first row of the tile: [rel(N-1)] (p_vel goes out as a plain store)
+                    const int off = odd ? (row > 0 ? 2 : 0) : 1;
+                    for (int k = lane_; k < N - 1; k += 32) {                    // other_pos (formation_hd_env.py:55)
+                        R2 pj = P[k + (k >= ri)];
+                        img[off + k] = O::make(O::sub(pj.x, pi.x), O::sub(pj.y, pi.y));
+                    }
+                    if (lane_ == 0) {
+                        if (!odd) { img[0] = s_v[row]; img[N] = O::make((T)0, (T)0); }
+                        else if (row > 0) { img[0] = s_iv[(int)fastdiv((uint32_t)(row - 1), a.magic_n)]; img[1] = s_v[row]; }
+                        else O::stcs(out, s_v[row]);
+                        if (!odd && row == nrows - 1) O::stcs(out + 3 * N - 1, s_iv[rle]);   // nobody follows
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    __syncwarp();
+                    if (lane_ == 0) {
+                        R2* dst = odd ? (row > 0 ? out - 1 : out + 1) : out;
+                        const uint32_t bytes = (uint32_t)(((odd && row == 0) ? N - 1 : N + 1) * sizeof(R2));
+                        asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;"
+                                     :: "l"(dst), "r"(smem_u32(img)), "r"(bytes), "l"(pol) : "memory");
+                        // static 2/3 from the env's shared image: even row items 1 .. 2N-2 (item 0 rode with the
+                        // dynamic piece, item 2N-1 rides with the next row), odd row all 2N items
+                        const R2* im0 = s_rt_img + (size_t)rle * 2 * rt_img;
+                        R2* sdst = odd ? out + N : out + N + 1;
+                        const R2* ssrc = odd ? im0 : im0 + rt_img + 1;
+                        const uint32_t sbytes = (uint32_t)((odd ? 2 * N : 2 * N - 2) * sizeof(R2));
+                        asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;"
+                                     :: "l"(sdst), "r"(smem_u32(ssrc)), "r"(sbytes), "l"(pol) : "memory");
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    }
+                    ++pending;
+                }
+            }
         }
 
         // ================= Scenario.reward partials on the NEW state (Q16) ======================
@@ -734,7 +829,12 @@ __global__ void __launch_bounds__(kBlock, (OM == 2) ? 4 : 3) k_step(const __grid
         // ================= observation rows (formation_hd_env.py:52-59 / basic :29-41) ==========
         // The tile's rows form ONE contiguous span of nvalid*N*IPR R2 items in HBM; consecutive
         // threads write consecutive items (8 B fp32 / 16 B fp64 each): fully coalesced stores.
-        if (a.obs) {
+        if (early) {
+            // the shared images / staging buffers must outlive the bulk copies' reads (kernel exit, or the next
+            // rollout step that restages them)
+            if (lane_ == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            __syncwarp();
+        } else if (a.obs) {
             const int IPR = a.IPR;
             if (OM == 2) {
                 // Long hd rows, silent agents: 2/3 of every row ([comm zeros | ideal_shape | ideal_vel]) is the
@@ -752,18 +852,21 @@ __global__ void __launch_bounds__(kBlock, (OM == 2) ? 4 : 3) k_step(const __grid
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 __syncthreads();
-                R2* dyn2 = s_rt_dyn + wp * 2 * rt_dyn;                           // two staging buffers per warp
+                R2* dyn2 = s_rt_dyn + wp * NB * rt_dyn;                          // NB staging buffers per warp
                 const int nrows = nvalid * N;
                 int pending = 0;
                 for (int row = wp; row < nrows; row += kBlock / 32) {
-                    R2* dyn = dyn2 + (pending & 1) * rt_dyn;
+                    R2* dyn = dyn2 + (NB == 2 ? (pending & 1) : 0) * rt_dyn;
                     const int rle = (int)fastdiv((uint32_t)row, a.magic_n);
                     const int ri = row - rle * N;
                     R2* out = a.obs + ((size_t)tile0 * N + row) * IPR;
                     const uint32_t ph = ((uint32_t)(uintptr_t)out & 15u) ? 1u : 0u;     // odd 8-byte slot (fp32 only)
                     R2* img = dyn + ph;                                                 // same phase as `out`
                     // the buffer being refilled was sent two rows ago: at most one younger group may be in flight
-                    if (pending >= 2 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                    if (lane == 0) {
+                        if (NB == 2) { if (pending >= 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+                        else if (pending >= 1) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                    }
                     __syncwarp();
                     const R2* P = s_new + rle * N;
                     const R2 pi = P[ri];
