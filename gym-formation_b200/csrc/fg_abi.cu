@@ -373,7 +373,13 @@ int policy_bfs_impl(const void* pos, const void* shape, const void* ivel, void* 
     for (int l = 0; l < levels; ++l) { a.mult[l] = (T)(std::log((double)M) / std::log((double)n)); M /= n; }   // :78
     const size_t smem = (size_t)4 * a.EPC * N * sizeof(R2);
     const int grid = (E + a.EPC - 1) / a.EPC;
-    fg::k_policy_bfs<T><<<grid, fg::kBlock, smem, (cudaStream_t)stream>>>(a);
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (n) {                                                    // compile-time fan-out for the usual group sizes
+        case 2: fg::k_policy_bfs<T, 2><<<grid, fg::kBlock, smem, st>>>(a); break;
+        case 3: fg::k_policy_bfs<T, 3><<<grid, fg::kBlock, smem, st>>>(a); break;
+        case 4: fg::k_policy_bfs<T, 4><<<grid, fg::kBlock, smem, st>>>(a); break;
+        default: fg::k_policy_bfs<T, 0><<<grid, fg::kBlock, smem, st>>>(a); break;
+    }
     cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess) return fail(FG_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(err));
     return FG_OK;

@@ -313,7 +313,9 @@ __global__ void __launch_bounds__(kBlock, (OM == 2) ? 4 : 3) k_step(const __grid
         }
         // Early observation rows (OM == 2, a.row_early): unless an env of this tile ends its episode in this
         // step (then the rows must show the RESET state and everything is written after the reset, below),
-        // the static 2/3 of every row is sent NOW, from the shared images, and drains while the physics runs.
+        // the rows are sent right after the physics, BEFORE the reward pass, and drain under it.  (Sending the
+        // static 2/3 even earlier, before the physics, was measured slower: 327 vs 260 us per 1024 envs of
+        // 243 agents -- the burst fills the SM's TMA queue and the warps block on issuing.)
         bool early = false;
         if constexpr (OM == 2 && sizeof(R2) == 8) {
             if (a.obs && a.row_early) {

@@ -30,6 +30,11 @@ template <> struct Ops<float> {
     static __device__ __forceinline__ void sincos_(float a, float* s, float* c) { sincosf(a, s, c); }
     static __device__ __forceinline__ float sq2(float x, float y) { return x * x + y * y; }
     static __device__ __forceinline__ float norm2(float x, float y) { return sqrtf(x * x + y * y); }
+    // Ordering key of a 2-vector's length for argsort / argmin decisions: the squared length (sqrt is
+    // monotonic, so the order is the same except for sub-ulp ties the fp32 build cannot reproduce anyway).
+    static __device__ __forceinline__ float lenkey(float x, float y) { return x * x + y * y; }
+    // x / n for a small integer count n: multiply by the reciprocal (<= 1 ulp; the fp64 build divides).
+    static __device__ __forceinline__ float div_count(float x, int n) { return x * (1.0f / (float)n); }
     static __device__ __forceinline__ Bits bits(float a) { return __float_as_uint(a); }
     static __device__ __forceinline__ float from_bits(Bits b) { return __uint_as_float(b); }
     static __device__ __forceinline__ R2 make(float x, float y) { return make_float2(x, y); }
@@ -57,6 +62,8 @@ template <> struct Ops<double> {
     static __device__ __forceinline__ double norm2(double x, double y) {
         return __dsqrt_rn(__fma_rn(y, y, __dmul_rn(x, x)));
     }
+    static __device__ __forceinline__ double lenkey(double x, double y) { return norm2(x, y); }   // as np.linalg.norm
+    static __device__ __forceinline__ double div_count(double x, int n) { return __ddiv_rn(x, (double)n); }
     static __device__ __forceinline__ Bits bits(double a) { return (Bits)__double_as_longlong(a); }
     static __device__ __forceinline__ double from_bits(Bits b) { return __longlong_as_double((long long)b); }
     static __device__ __forceinline__ R2 make(double x, double y) { return make_double2(x, y); }

@@ -30,69 +30,100 @@ template <typename T> struct PArgs {
 
 // formation_gym/__init__.py:19-47 on the sliced inputs: others [n-1] (other_pos), tgt [n] (ideal_shape
 // before re-centring), tvel (ideal_vel).
-template <typename T>
+// NF > 0: compile-time fan-out (loops unrolled, arrays in registers); NF == 0: runtime n <= 8.
+template <typename T, int NF>
 __device__ __forceinline__ typename Ops<T>::R2 ezpolicy_dev(const typename Ops<T>::R2* others,
                                                             const typename Ops<T>::R2* tgt,
-                                                            typename Ops<T>::R2 tvel, int n) {
+                                                            typename Ops<T>::R2 tvel, int n_rt) {
     typedef Ops<T> O;
     typedef typename O::R2 R2;
-    R2 ideal[kPolicyMaxFan], cur[kPolicyMaxFan];
-    T d[kPolicyMaxFan];
-    int order[kPolicyMaxFan];
+    constexpr int CAP = NF > 0 ? NF : kPolicyMaxFan;
+    const int n = NF > 0 ? NF : n_rt;
+    R2 ideal[CAP], cur[CAP];
+    T d[CAP];
     // ideal_shape - mean (:28); current_shape = [other_pos, (0,0)] - mean (:31-33): sums in row order
     T sx = 0, sy = 0, cx = 0, cy = 0;
-    for (int k = 0; k < n; ++k) {
-        sx = O::add(sx, tgt[k].x); sy = O::add(sy, tgt[k].y);
-        const R2 c = (k < n - 1) ? others[k] : O::make((T)0, (T)0);
-        cur[k] = c;
-        cx = O::add(cx, c.x); cy = O::add(cy, c.y);
+#pragma unroll
+    for (int k = 0; k < CAP; ++k) {
+        if (k < n) {
+            sx = O::add(sx, tgt[k].x); sy = O::add(sy, tgt[k].y);
+            const R2 c = (k < n - 1) ? others[k] : O::make((T)0, (T)0);
+            cur[k] = c;
+            cx = O::add(cx, c.x); cy = O::add(cy, c.y);
+        }
     }
-    sx = O::div(sx, (T)n); sy = O::div(sy, (T)n); cx = O::div(cx, (T)n); cy = O::div(cy, (T)n);
-    for (int k = 0; k < n; ++k) {
-        ideal[k] = O::make(O::sub(tgt[k].x, sx), O::sub(tgt[k].y, sy));
-        cur[k] = O::make(O::sub(cur[k].x, cx), O::sub(cur[k].y, cy));
+    sx = O::div_count(sx, n); sy = O::div_count(sy, n); cx = O::div_count(cx, n); cy = O::div_count(cy, n);
+#pragma unroll
+    for (int k = 0; k < CAP; ++k) {
+        if (k < n) {
+            ideal[k] = O::make(O::sub(tgt[k].x, sx), O::sub(tgt[k].y, sy));
+            cur[k] = O::make(O::sub(cur[k].x, cx), O::sub(cur[k].y, cy));
+        }
     }
     const R2 self = cur[n - 1];
-    // argsort of the distances from me to the landmarks (:35); insertion sort = numpy's small-n path
-    for (int k = 0; k < n; ++k) {
-        d[k] = O::norm2(O::sub(self.x, ideal[k].x), O::sub(self.y, ideal[k].y));
-        int j = k;
-        while (j > 0 && d[order[j - 1]] > d[k]) { order[j] = order[j - 1]; --j; }
-        order[j] = k;
-    }
+    // Distances from me to every landmark (:35).  np.argsort's small-n path is an insertion sort (stable), so
+    // landmark k has rank = #{j : d[j] < d[k] or (d[j] == d[k] and j < k)}; walking the ranks in order is the
+    // reference's `for idx in sort_mark_idx` without an index array.
+#pragma unroll
+    for (int k = 0; k < CAP; ++k)
+        if (k < n) d[k] = O::lenkey(O::sub(self.x, ideal[k].x), O::sub(self.y, ideal[k].y));
     R2 act = O::make((T)0, (T)0);
-    for (int r = 0; r < n; ++r) {                                             // :36-40
-        const int idx = order[r];
-        int closest = 0;
-        T best = O::norm2(O::sub(cur[0].x, ideal[idx].x), O::sub(cur[0].y, ideal[idx].y));
-        for (int m = 1; m < n; ++m) {
-            const T dm = O::norm2(O::sub(cur[m].x, ideal[idx].x), O::sub(cur[m].y, ideal[idx].y));
-            if (dm < best) { best = dm; closest = m; }                        // np.argmin: first minimum
-        }
-        if (closest == n - 1 || r == n - 1) {
-            T ax = O::mul((T)0.5, O::sub(ideal[idx].x, self.x));
-            T ay = O::mul((T)0.5, O::sub(ideal[idx].y, self.y));
-            act = O::make(fmin(fmax(ax, (T)-1), (T)1), fmin(fmax(ay, (T)-1), (T)1));   // np.clip
-            break;
+    bool found = false;
+#pragma unroll
+    for (int r = 0; r < CAP; ++r) {                                           // :36-40
+        if (r < n && !found) {
+            int idx = 0;
+#pragma unroll
+            for (int k = 0; k < CAP; ++k) {
+                if (k < n) {
+                    int rank = 0;
+#pragma unroll
+                    for (int j = 0; j < CAP; ++j)
+                        if (j < n) rank += (d[j] < d[k] || (d[j] == d[k] && j < k)) ? 1 : 0;
+                    if (rank == r) idx = k;
+                }
+            }
+            R2 tg = ideal[0];
+#pragma unroll
+            for (int k = 1; k < CAP; ++k) if (k < n && k == idx) tg = ideal[k];
+            int closest = 0;
+            T best = O::lenkey(O::sub(cur[0].x, tg.x), O::sub(cur[0].y, tg.y));
+#pragma unroll
+            for (int m = 1; m < CAP; ++m) {
+                if (m < n) {
+                    const T dm = O::lenkey(O::sub(cur[m].x, tg.x), O::sub(cur[m].y, tg.y));
+                    if (dm < best) { best = dm; closest = m; }                // np.argmin: first minimum
+                }
+            }
+            if (closest == n - 1 || r == n - 1) {
+                T ax = O::mul((T)0.5, O::sub(tg.x, self.x));
+                T ay = O::mul((T)0.5, O::sub(tg.y, self.y));
+                act = O::make(fmin(fmax(ax, (T)-1), (T)1), fmin(fmax(ay, (T)-1), (T)1));   // np.clip
+                found = true;
+            }
         }
     }
     // done = ||ideal_shape - current_shape||_F < 0.01 (:42)
     T fro = 0;
-    for (int k = 0; k < n; ++k) {
-        const T ex = O::sub(ideal[k].x, cur[k].x), ey = O::sub(ideal[k].y, cur[k].y);
-        fro = O::add(fro, O::add(O::mul(ex, ex), O::mul(ey, ey)));
+#pragma unroll
+    for (int k = 0; k < CAP; ++k) {
+        if (k < n) {
+            const T ex = O::sub(ideal[k].x, cur[k].x), ey = O::sub(ideal[k].y, cur[k].y);
+            fro = O::add(fro, O::add(O::mul(ex, ex), O::mul(ey, ey)));
+        }
     }
     const bool done = O::sqrt_(fro) < (T)0.01;
     const T g = done ? (T)1 : (T)0.3;                                         // :43-46
     return O::make(O::add(act.x, done ? tvel.x : O::mul(tvel.x, g)), O::add(act.y, done ? tvel.y : O::mul(tvel.y, g)));
 }
 
-template <typename T>
+template <typename T, int NF>
 __global__ void __launch_bounds__(256) k_policy_bfs(const __grid_constant__ PArgs<T> a) {
     typedef Ops<T> O;
     typedef typename O::R2 R2;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int N = a.N, n = a.n, nA = a.EPC * N;
+    constexpr int CAP = NF > 0 ? NF : kPolicyMaxFan;
+    const int N = a.N, n = NF > 0 ? NF : a.n, nA = a.EPC * N;
     R2* s_p = reinterpret_cast<R2*>(smem_raw);
     R2* s_s = s_p + nA;
     R2* s_tv0 = s_s + nA;                 // target velocity of the group each agent is in (ping-pong)
@@ -118,8 +149,10 @@ __global__ void __launch_bounds__(256) k_policy_bfs(const __grid_constant__ PArg
             const int gb = (i / M) * M;                                       // first agent of my group
             const int si = (i - gb) / nxt;                                    // my subgroup within the group
             const R2 pi = P[i];
-            R2 cur[kPolicyMaxFan], tgt[kPolicyMaxFan], others[kPolicyMaxFan];
-            for (int k = 0; k < n; ++k) {
+            R2 cur[CAP], tgt[CAP], others[CAP];
+#pragma unroll
+            for (int k = 0; k < CAP; ++k) {
+                if (k >= n) continue;
                 // centroid of subgroup k in my frame (:65-66) and of its target points (:70-71): np.mean sums
                 // the rows in order and divides by the count
                 T cx = 0, cy = 0, tx = 0, ty = 0;
@@ -132,16 +165,20 @@ __global__ void __launch_bounds__(256) k_policy_bfs(const __grid_constant__ PArg
                     const R2 sb = S[b];
                     tx = O::add(tx, sb.x); ty = O::add(ty, sb.y);
                 }
-                cur[k] = O::make(O::div(cx, (T)nxt), O::div(cy, (T)nxt));
-                tgt[k] = O::make(O::div(tx, (T)nxt), O::div(ty, (T)nxt));
+                cur[k] = O::make(O::div_count(cx, nxt), O::div_count(cy, nxt));
+                tgt[k] = O::make(O::div_count(tx, nxt), O::div_count(ty, nxt));
             }
-            const R2 own = cur[si];                                           // :67-68
-            int w = 0;
-            for (int k = 0; k < n; ++k) {
-                if (k == si) continue;
-                others[w++] = O::make(O::sub(cur[k].x, own.x), O::sub(cur[k].y, own.y));
+            R2 own = cur[0];                                                  // :67-68
+#pragma unroll
+            for (int k = 1; k < CAP; ++k) if (k < n && k == si) own = cur[k];
+#pragma unroll
+            for (int k = 0; k < CAP - 1; ++k) {                               // np.delete(cur - cur[si], si, 0)
+                if (k < n - 1) {
+                    const R2 c = (k < si) ? cur[k] : cur[k + 1];
+                    others[k] = O::make(O::sub(c.x, own.x), O::sub(c.y, own.y));
+                }
             }
-            R2 out = ezpolicy_dev<T>(others, tgt, s_tv0[t], n);               // :76-79
+            R2 out = ezpolicy_dev<T, NF>(others, tgt, s_tv0[t], n);           // :76-79
             out = O::make(O::mul(out.x, a.mult[l]), O::mul(out.y, a.mult[l]));
             if (nxt == 1) a.act[g] = out;                                     // :81-83
             else for (int b = 0; b < nxt; ++b) s_tv1[t + b] = out;            // tar_vel of my subgroup (:84-97)
