@@ -45,8 +45,11 @@ int fill_args(fg::KArgs<T>& a, const fg_params* p, const fg_buffers* b, int scen
     if (scenario == FG_SCENARIO_HD) {
         if (N < 3) return fail(FG_ERR_ARG, "formation_hd_env needs N >= 3 (formation_hd_env.py:58)%s");
         L = N;
-    } else if (scenario == FG_SCENARIO_BASIC) {
+    } else if (scenario == FG_SCENARIO_BASIC || scenario == FG_SCENARIO_HD_PARTIAL ||
+               scenario == FG_SCENARIO_HD_PARTIAL_RANGE) {
         if (L < 1 || L > FG_MAX_LANDMARKS) return fail(FG_ERR_ARG, "L must be in [1, FG_MAX_LANDMARKS]%s");
+        if (scenario == FG_SCENARIO_HD_PARTIAL && (p->num_obs < 0 || p->num_obs > 4 * FG_MAX_AGENTS))
+            return fail(FG_ERR_ARG, "num_obs out of range%s");
     } else {
         return fail(FG_ERR_ARG, "unknown scenario id%s");
     }
@@ -62,7 +65,11 @@ int fill_args(fg::KArgs<T>& a, const fg_params* p, const fg_buffers* b, int scen
     a.a_accel = (const T*)p->agent_accel; a.a_vmax = (const T*)p->agent_max_speed;
     a.E = E; a.N = N; a.L = L;
     a.EPC = fg::kBlock / N;
-    a.IPR = scenario == FG_SCENARIO_HD ? 3 * N : 2 + L + 2 * (N - 1);
+    a.IPR = scenario == FG_SCENARIO_HD ? 3 * N
+          : scenario == FG_SCENARIO_BASIC ? 2 + L + 2 * (N - 1)
+          : scenario == FG_SCENARIO_HD_PARTIAL ? 1 + L + p->num_obs + (N - 1)
+          : 1 + L + 2 * (N - 1);
+    a.num_obs = p->num_obs; a.obs_range = (T)p->obs_range;
     a.magic_n = magic_for(N); a.magic_ipr = magic_for(a.IPR);
     a.act_r2 = p->silent ? 1 : 2;
     a.dt = (T)p->dt; a.keep = (T)(1.0 - p->damping); a.cforce = (T)p->contact_force;
@@ -122,7 +129,7 @@ size_t smem_bytes(const fg::KArgs<T>& a, int scenario, bool het) {
     typedef typename fg::Ops<T>::Bits Bits;
     const size_t nA = (size_t)a.EPC * a.N;
     const size_t nS = scenario == FG_SCENARIO_HD ? nA : (size_t)a.EPC * a.L;
-    size_t s = (4 * nA + nS + 3 * a.EPC + (scenario == FG_SCENARIO_HD ? nA : 0)) * sizeof(R2)
+    size_t s = (4 * nA + nS + 3 * a.EPC + (scenario != FG_SCENARIO_BASIC ? nA : 0)) * sizeof(R2)
                + a.EPC * sizeof(Bits);
     if (scenario == FG_SCENARIO_BASIC) s += (size_t)a.EPC * a.L * sizeof(T);
     if (het) s += 5 * (size_t)a.N * sizeof(T);
@@ -166,7 +173,7 @@ int launch_fp(const fg::KArgs<T>& a, size_t smem, cudaStream_t st) {
 // observation-writer mode of the tile kernel (fg_kernels.cuh k_step<..., OM>)
 template <typename T, int SCN, bool PHYS, bool OBSREW, bool HET>
 int launch_om(const fg::KArgs<T>& a, size_t smem, cudaStream_t st) {
-    if (!OBSREW) return launch_fp<T, SCN, PHYS, OBSREW, HET, 0>(a, smem, st);
+    if (!OBSREW || SCN >= fg::kScnPartial) return launch_fp<T, SCN, PHYS, OBSREW, HET, 0>(a, smem, st);
     if (SCN == fg::kScnHD && a.row_tma) return launch_fp<T, SCN, PHYS, OBSREW, HET, (SCN == fg::kScnHD ? 2 : 0)>(a, smem, st);
     if (a.IPR >= 48) return launch_fp<T, SCN, PHYS, OBSREW, HET, 1>(a, smem, st);
     return launch_fp<T, SCN, PHYS, OBSREW, HET, 0>(a, smem, st);
@@ -183,6 +190,8 @@ int launch(const fg::KArgs<T>& a, int scenario, const fg_params* p, void* stream
     const size_t smem = smem_bytes<T>(a, scenario, het);
     cudaStream_t st = (cudaStream_t)stream;
     if (scenario == FG_SCENARIO_HD) return launch_het<T, fg::kScnHD, PHYS, OBSREW>(a, het, smem, st);
+    if (OBSREW && scenario == FG_SCENARIO_HD_PARTIAL) return launch_het<T, fg::kScnPartial, PHYS, OBSREW>(a, het, smem, st);
+    if (OBSREW && scenario == FG_SCENARIO_HD_PARTIAL_RANGE) return launch_het<T, fg::kScnRange, PHYS, OBSREW>(a, het, smem, st);
     return launch_het<T, fg::kScnBasic, PHYS, OBSREW>(a, het, smem, st);
 }
 
@@ -281,8 +290,8 @@ int obs_reward_impl(const fg_params* p, const fg_buffers* b, int scenario, int E
     if (!b->pos || !b->vel || !b->reward) return fail(FG_ERR_ARG, "fg_obs_reward: pos/vel/reward must be non-null%s");
     if (scenario == FG_SCENARIO_HD && (!b->ideal_shape || !b->ideal_vel))
         return fail(FG_ERR_ARG, "fg_obs_reward(hd): ideal_shape/ideal_vel must be non-null%s");
-    if (scenario == FG_SCENARIO_BASIC && !b->landmarks)
-        return fail(FG_ERR_ARG, "fg_obs_reward(basic): landmarks must be non-null%s");
+    if (scenario != FG_SCENARIO_HD && !b->landmarks)
+        return fail(FG_ERR_ARG, "fg_obs_reward: landmarks must be non-null for this scenario%s");
     a.step = nullptr; a.done = nullptr; a.ep_return = nullptr; a.ep_coll = nullptr; a.stats = nullptr;
     return launch<T, false, true>(a, scenario, p, stream);
 }
@@ -304,8 +313,8 @@ int step_fused_impl(const fg_params* p, const fg_buffers* b, int scenario, int E
         return fail(FG_ERR_ARG, "fg_step_fused: random_actions supports silent agents only%s");
     if (scenario == FG_SCENARIO_HD && (!b->ideal_shape || !b->ideal_vel))
         return fail(FG_ERR_ARG, "fg_step_fused(hd): ideal_shape/ideal_vel must be non-null%s");
-    if (scenario == FG_SCENARIO_BASIC && !b->landmarks)
-        return fail(FG_ERR_ARG, "fg_step_fused(basic): landmarks must be non-null%s");
+    if (scenario != FG_SCENARIO_HD && !b->landmarks)
+        return fail(FG_ERR_ARG, "fg_step_fused: landmarks must be non-null for this scenario%s");
     a.n_steps = n_steps; a.random_actions = random_actions; a.auto_reset = auto_reset;
     if (warp_path_ok<T>(a, scenario, p, b)) {
         cudaStream_t st = (cudaStream_t)stream;
@@ -327,8 +336,8 @@ int reset_impl(const fg_params* p, const fg_buffers* b, int scenario, int E, int
     if (!b->pos || !b->vel) return fail(FG_ERR_ARG, "fg_reset: pos/vel must be non-null%s");
     if (scenario == FG_SCENARIO_HD && (!b->ideal_shape || !b->ideal_vel))
         return fail(FG_ERR_ARG, "fg_reset(hd): ideal_shape/ideal_vel must be non-null%s");
-    if (scenario == FG_SCENARIO_BASIC && !b->landmarks)
-        return fail(FG_ERR_ARG, "fg_reset(basic): landmarks must be non-null%s");
+    if (scenario != FG_SCENARIO_HD && !b->landmarks)
+        return fail(FG_ERR_ARG, "fg_reset: landmarks must be non-null for this scenario%s");
     cudaStream_t st = (cudaStream_t)stream;
     const int grid = (E + 127) / 128;
     if (scenario == FG_SCENARIO_HD) fg::k_reset<T, fg::kScnHD><<<grid, 128, 0, st>>>(a, mask);

@@ -22,6 +22,8 @@ constexpr int kBlock = 256;
 constexpr int kMaxWalls = 8;
 constexpr int kScnHD = 0;
 constexpr int kScnBasic = 1;
+constexpr int kScnPartial = 2;      // formation_hd_partial_env: landmarks absolute, the next num_obs agents
+constexpr int kScnRange = 3;        // formation_hd_partial_range_env: landmarks absolute, other_pos clipped to a range
 
 template <typename T> struct WallT {
     int orient, hard;
@@ -56,6 +58,8 @@ template <typename T> struct KArgs {
     int row_early;                   // OM == 2, fp32, odd N, 16-byte aligned obs: rows leave as aligned bulk pieces, the
                                      // static 2/3 before the physics and the dynamic 1/3 before the reward pass
     int fast_pairs;                  // tile kernel: packed pair loops of fg_pairs.cuh (N >= 32; fp32 hd uniform only)
+    int num_obs;                     // partial: observed neighbours (formation_hd_partial_env.py:15,53)
+    T obs_range;                     // range: clip bound of other_pos (formation_hd_partial_range_env.py:15,53)
     int n_steps, random_actions, auto_reset;
     uint64_t seed; uint32_t tick; uint32_t env_offset;
     uint32_t* tick_dev;              // (opt) [2]: device tick added to `tick`, arrival counter (CUDA graphs)
@@ -191,7 +195,7 @@ __global__ void __launch_bounds__(kBlock, (OM == 2) ? 4 : 3) k_step(const __grid
     R2* s_iv = s_c + nA;                              // hd: ideal velocity per env
     R2* s_mean = s_iv + EPC;                          // hd: [EPC][2] centroid, mean velocity
     R2* s_cen = s_mean + 2 * EPC;                     // hd: centred new positions [nA]
-    Bits* s_rowmax = reinterpret_cast<Bits*>(s_cen + ((SCN == kScnHD) ? nA : 0));   // max of the Hausdorff minima
+    Bits* s_rowmax = reinterpret_cast<Bits*>(s_cen + ((SCN != kScnBasic) ? nA : 0));   // max of the Hausdorff minima
     T* s_lmin = reinterpret_cast<T*>(s_rowmax + EPC);         // basic: min_a |p_a - l_k| [EPC*L]
     T* s_het = s_lmin + ((SCN == kScnBasic) ? EPC * L : 0);   // HET: mass,size,sens,gain,vmax [5N]
     int* s_col = reinterpret_cast<int*>(s_het + (HET ? 5 * N : 0));
@@ -564,6 +568,24 @@ __global__ void __launch_bounds__(kBlock, (OM == 2) ? 4 : 3) k_step(const __grid
         int col = 0;
         T mvx = 0, mvy = 0;
         float fcx = 0.f, fcy = 0.f, fnc = 0.f;                                // FP: my centred position, its norm^2
+        if (SCN >= kScnPartial) {
+            // formation_hd_partial_env.py:70-75: u - mean(u), v - mean(v) (agents / landmarks), summed in order
+            if (active && (!(fabs(p.x) < (T)INFINITY) || !(fabs(p.y) < (T)INFINITY))) s_bad[le] = 1;
+            if (t < 2 * nvalid) {
+                const int qe = t >> 1;
+                const int cnt = (t & 1) ? L : N;
+                const R2* src = (t & 1) ? (s_s + qe * L) : (s_new + qe * N);
+                T sx = 0, sy = 0;
+                for (int j = 0; j < cnt; ++j) { R2 q = src[j]; sx = O::add(sx, q.x); sy = O::add(sy, q.y); }
+                s_mean[t] = O::make(O::div(sx, (T)cnt), O::div(sy, (T)cnt));
+            }
+            __syncthreads();
+            if (active) {
+                const R2 mp = s_mean[2 * le];
+                s_cen[t] = O::make(O::sub(p.x, mp.x), O::sub(p.y, mp.y));
+            }
+            __syncthreads();
+        }
         if (SCN == kScnHD) {
             // a non-finite position makes the centroid, hence the whole shape term, NaN (Q9)
             if (active && (!(fabs(p.x) < (T)INFINITY) || !(fabs(p.y) < (T)INFINITY))) s_bad[le] = 1;
@@ -664,7 +686,7 @@ __global__ void __launch_bounds__(kBlock, (OM == 2) ? 4 : 3) k_step(const __grid
                             T d2 = dx * dx + dy * dy;
                             hit |= (d2 < a.rthr2_hi) ? (1u << jj) : 0u;
                         }
-                        if (SCN == kScnHD && (unsigned)(i - j0) < 32u) hit &= ~(1u << (i - j0));
+                        if (SCN != kScnBasic && (unsigned)(i - j0) < 32u) hit &= ~(1u << (i - j0));
                         while (hit) {
                             const int j = j0 + __ffs(hit) - 1;
                             hit &= hit - 1;
@@ -675,7 +697,7 @@ __global__ void __launch_bounds__(kBlock, (OM == 2) ? 4 : 3) k_step(const __grid
                 } else {
                     const T size_i = s_het[N + i];
                     for (int j = 0; j < N; ++j) {
-                        if (SCN == kScnHD && j == i) continue;
+                        if (SCN != kScnBasic && j == i) continue;
                         R2 q = envp[j];
                         T dx = O::sub(q.x, p.x), dy = O::sub(q.y, p.y);
                         T d2 = dx * dx + dy * dy;
@@ -701,7 +723,35 @@ __global__ void __launch_bounds__(kBlock, (OM == 2) ? 4 : 3) k_step(const __grid
                 }
                 atomicMax(&s_rowmax[le], O::bits(fmax(rowmin, colmin)));   // d2 >= 0: bit order == value order
             }
+            if (SCN >= kScnPartial) {
+                // rows of the symmetric Hausdorff distance (formation_hd_partial_env.py:75): agent i against the
+                // centred landmarks
+                const R2 Ci = s_cen[t], ml = s_mean[2 * le + 1];
+                const R2* envl = s_s + le * L;
+                T rowmin = (T)INFINITY;
+                for (int k = 0; k < L; ++k) {
+                    R2 l = envl[k];
+                    rowmin = fmin(rowmin, O::sq2(O::sub(Ci.x, O::sub(l.x, ml.x)), O::sub(Ci.y, O::sub(l.y, ml.y))));
+                }
+                atomicMax(&s_rowmax[le], O::bits(rowmin));
+            }
             if (col) atomicAdd(&s_col[le], col);
+        }
+        if (SCN >= kScnPartial) {
+            // columns: centred landmark k against all centred agents (one thread per (env, landmark))
+            for (int q = t; q < nvalid * L; q += kBlock) {
+                const int qe = q / L;
+                const R2 ml = s_mean[2 * qe + 1];
+                const R2 l = s_s[q];
+                const R2 V = O::make(O::sub(l.x, ml.x), O::sub(l.y, ml.y));
+                const R2* envc = s_cen + qe * N;
+                T colmin = (T)INFINITY;
+                for (int j = 0; j < N; ++j) {
+                    R2 Cj = envc[j];
+                    colmin = fmin(colmin, O::sq2(O::sub(Cj.x, V.x), O::sub(Cj.y, V.y)));
+                }
+                atomicMax(&s_rowmax[qe], O::bits(colmin));
+            }
         }
         if (SCN == kScnBasic) {
             // reward part 1 (basic_formation_env.py:45-47): min over agents of |p_a - l_k| per landmark
@@ -733,6 +783,9 @@ __global__ void __launch_bounds__(kBlock, (OM == 2) ? 4 : 3) k_step(const __grid
                 if (s_bad[le]) form = O::from_bits(~(Bits)0 >> 1);              // NaN, as the reference
                 T velr = O::norm2(O::sub(s_iv[le].x, mvx), O::sub(s_iv[le].y, mvy));   // :68-69
                 base = O::sub(form, velr);
+            } else if (SCN >= kScnPartial) {
+                base = -O::sqrt_(O::from_bits(s_rowmax[le]));                   // no velocity term (:75)
+                if (s_bad[le]) base = O::from_bits(~(Bits)0 >> 1);
             } else {
                 base = (T)0;
                 for (int k = 0; k < L; ++k) base = O::sub(base, s_lmin[le * L + k]);
@@ -782,7 +835,7 @@ __global__ void __launch_bounds__(kBlock, (OM == 2) ? 4 : 3) k_step(const __grid
                     }
                     stp = 0;
                 }
-                if (SCN == kScnBasic) {
+                if (SCN != kScnHD) {
                     for (int q = t; q < nvalid * L; q += kBlock) {
                         int qe = q / L, k = q - qe * L;
                         if (s_dn[qe]) {
@@ -948,6 +1001,33 @@ __global__ void __launch_bounds__(kBlock, (OM == 2) ? 4 : 3) k_step(const __grid
                             val = s_c[rle * N + j];
                         } else if (k < 3 * N - 1) val = s_s[rle * N + (k - (2 * N - 1))];  // ideal_shape
                         else val = s_iv[rle];                                              // ideal_vel
+                    } else if (SCN >= kScnPartial) {
+                        // [p_vel | landmark positions (absolute) | other_pos | comm of the others]
+                        // (formation_hd_partial_env.py:42-66, formation_hd_partial_range_env.py:42-54)
+                        const int nob = (SCN == kScnPartial) ? a.num_obs : N - 1;
+                        if (k == 0) val = s_v[row];
+                        else if (k < 1 + L) val = s_s[rle * L + (k - 1)];
+                        else if (k < 1 + L + nob) {
+                            const int m = k - (1 + L);
+                            const R2 pi = s_new[row];
+                            if (SCN == kScnPartial) {                      // agents i+1 .. i+num_obs, cyclic (:53-55)
+                                int j = ri + 1 + m;
+                                j -= (j / N) * N;
+                                R2 pj = s_new[rle * N + j];
+                                val = O::make(O::sub(pj.x, pi.x), O::sub(pj.y, pi.y));
+                            } else {                                       // all others, clipped to the range (:53)
+                                const int j = m + (m >= ri);
+                                R2 pj = s_new[rle * N + j];
+                                T dx = O::sub(pj.x, pi.x), dy = O::sub(pj.y, pi.y);
+                                const T lo = -a.obs_range, hi = a.obs_range;   // np.clip keeps NaN
+                                dx = (dx < lo) ? lo : ((dx > hi) ? hi : dx);
+                                dy = (dy < lo) ? lo : ((dy > hi) ? hi : dy);
+                                val = O::make(dx, dy);
+                            }
+                        } else {
+                            int j = k - (1 + L + nob); j += (j >= ri);
+                            val = s_c[rle * N + j];
+                        }
                     } else {
                         if (k == 0) val = s_v[row];                                        // p_vel
                         else if (k == 1) val = s_new[row];                                 // p_pos

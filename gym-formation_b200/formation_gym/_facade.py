@@ -63,7 +63,7 @@ class FacadeBackend(object):
         a = np.ascontiguousarray(arr, dtype=self.np_dtype).reshape(tuple(dst.shape))
         dst.copy_(torch.from_numpy(a))
 
-    def _params(self, world, scenario_kind, prescaled):
+    def _params(self, world, scenario_kind, prescaled, scenario=None):
         agents = world.agents
         if not all(a.movable for a in agents):
             raise NotImplementedError("immovable agents are not supported by the accelerated path")
@@ -94,7 +94,8 @@ class FacadeBackend(object):
             accel=accel if accel_arr is None else None,
             max_speed=vmax if vmax_arr is None else None,
             u_noise=u_noise, c_noise=c_noise, collide=collide, silent=silent,
-            world_length=world.world_length, walls=walls, action_prescaled=prescaled)
+            world_length=world.world_length, walls=walls, action_prescaled=prescaled,
+            num_obs=getattr(scenario, "num_obs", 0) or 0, obs_range=getattr(scenario, "obs_range", 0.0) or 0.0)
         self._keep = []
         for field, arr in (("agent_mass", mass_arr), ("agent_size_arr", size_arr),
                            ("agent_accel", accel_arr), ("agent_max_speed", vmax_arr)):
@@ -127,7 +128,9 @@ class FacadeBackend(object):
         b.landmarks = nat.ptr(self.lm) if self.L > 0 else None
         b.step = nat.ptr(self.step)
         if with_obs:
-            D = 6 * self.N if scenario_kind == nat.FG_SCENARIO_HD else 4 + 2 * self.L + 4 * (self.N - 1)
+            from .batched import obs_dim, SCENARIOS
+            name = [k for k, v in SCENARIOS.items() if v == scenario_kind][0]
+            D = obs_dim(name, self.N, self.L, getattr(self, "_num_obs", 3))
             if self.obs is None or self.obs.shape[2] != D:
                 self.obs = torch.zeros(1, self.N, D, device=self.device, dtype=self.dtype)
             b.obs = nat.ptr(self.obs)
@@ -183,7 +186,8 @@ class FacadeBackend(object):
                np.asarray(getattr(scenario, "ideal_vel", 0.0), np.float64).tobytes())
         if key == self._cache_key:
             return self._cache_val
-        p, _ = self._params(world, kind, False)
+        p, _ = self._params(world, kind, False, scenario)
+        self._num_obs = int(getattr(scenario, "num_obs", 3) or 0)
         self._up(self.pos, P)
         self._up(self.vel, V)
         self._up(self.comm, Cm)
@@ -209,7 +213,8 @@ class FacadeBackend(object):
     # ------------------------------------------------------------------ fused env.step
     def step_fused(self, world, scenario, kind, acts, current_step, acts_c=None):
         """environment.py:113-142 in one launch.  ``current_step`` is the value BEFORE the step."""
-        p, silent = self._params(world, kind, False)
+        p, silent = self._params(world, kind, False, scenario)
+        self._num_obs = int(getattr(scenario, "num_obs", 3) or 0)
         P, V = self._gather_state(world)
         self._up(self.pos, P)
         self._up(self.vel, V)

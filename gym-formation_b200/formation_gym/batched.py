@@ -22,17 +22,27 @@ from . import _native as nat
 
 _NULL_CTX = contextlib.nullcontext()
 
-SCENARIOS = {"formation_hd_env": nat.FG_SCENARIO_HD, "basic_formation_env": nat.FG_SCENARIO_BASIC}
+SCENARIOS = {"formation_hd_env": nat.FG_SCENARIO_HD, "basic_formation_env": nat.FG_SCENARIO_BASIC,
+             "formation_hd_partial_env": nat.FG_SCENARIO_HD_PARTIAL,
+             "formation_hd_partial_range_env": nat.FG_SCENARIO_HD_PARTIAL_RANGE}
 # scenario defaults: agent size, episode length (formation_hd_env.py:13,26; basic_formation_env.py:18,
 # core.py:113)
 _DEFAULTS = {"formation_hd_env": dict(agent_size=0.03, world_length=100),
-             "basic_formation_env": dict(agent_size=0.1, world_length=50)}
+             "basic_formation_env": dict(agent_size=0.1, world_length=50),
+             # formation_hd_partial_env.py:15,29 / formation_hd_partial_range_env.py:15,29
+             "formation_hd_partial_env": dict(agent_size=0.04, world_length=25, num_landmarks=5),
+             "formation_hd_partial_range_env": dict(agent_size=0.04, world_length=25, num_landmarks=4)}
 
 
-def obs_dim(scenario, num_agents, num_landmarks=3):
-    """Observation length per agent (hd: 6N, formation_hd_env.py:59; basic: 4+2L+4(N-1))."""
+def obs_dim(scenario, num_agents, num_landmarks=3, num_obs=3):
+    """Observation length per agent (hd: 6N, formation_hd_env.py:59; basic: 4+2L+4(N-1); partial:
+    2+2L+2*num_obs+2(N-1), formation_hd_partial_env.py:66; partial range: 2+2L+4(N-1))."""
     if scenario == "formation_hd_env":
         return 6 * num_agents
+    if scenario == "formation_hd_partial_env":
+        return 2 + 2 * num_landmarks + 2 * num_obs + 2 * (num_agents - 1)
+    if scenario == "formation_hd_partial_range_env":
+        return 2 + 2 * num_landmarks + 4 * (num_agents - 1)
     return 4 + 2 * num_landmarks + 4 * (num_agents - 1)
 
 
@@ -45,12 +55,12 @@ class BatchedFormationEnv:
     """
 
     def __init__(self, scenario="formation_hd_env", num_envs=4096, num_agents=9, episode_length=None,
-                 num_landmarks=3, device="cuda", dtype=torch.float32, seed=0, auto_reset=True,
+                 num_landmarks=None, device="cuda", dtype=torch.float32, seed=0, auto_reset=True,
                  env_offset=0, write_obs=True, track_landmarks=False, u_noise=None, c_noise=None,
                  silent=True, collide=True, accel=None, max_speed=None, mass=1.0, agent_size=None,
                  agent_mass=None, agent_sizes=None, agent_accel=None, agent_max_speed=None,
                  walls=(), dt=0.1, damping=0.25, contact_force=1e2, contact_margin=1e-3,
-                 sensitivity=5.0):
+                 sensitivity=5.0, num_obs=3, obs_range=0.7):
         if scenario not in SCENARIOS:
             raise ValueError("unknown scenario %r (supported: %s)" % (scenario, sorted(SCENARIOS)))
         if dtype not in (torch.float32, torch.float64):
@@ -61,12 +71,15 @@ class BatchedFormationEnv:
         self.scenario = scenario
         self.scn = SCENARIOS[scenario]
         self.E, self.N = int(num_envs), int(num_agents)
+        if num_landmarks is None:
+            num_landmarks = _DEFAULTS[scenario].get("num_landmarks", 3)
         self.L = self.N if self.scn == nat.FG_SCENARIO_HD else int(num_landmarks)
+        self.num_obs, self.obs_range = int(num_obs), float(obs_range)
         if self.scn == nat.FG_SCENARIO_HD and self.N < 3:
             raise ValueError("formation_hd_env needs num_agents >= 3 (formation_hd_env.py:58)")
         if not (1 <= self.N <= nat.FG_MAX_AGENTS):
             raise ValueError("num_agents must be in [1, %d]" % nat.FG_MAX_AGENTS)
-        self.D = obs_dim(scenario, self.N, self.L)
+        self.D = obs_dim(scenario, self.N, self.L, self.num_obs)
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise nat.NativeError("device must be a CUDA device: there is no CPU fallback")
@@ -86,7 +99,8 @@ class BatchedFormationEnv:
             dt=dt, damping=damping, contact_force=contact_force, contact_margin=contact_margin,
             sensitivity=sensitivity, agent_size=d["agent_size"] if agent_size is None else agent_size,
             mass=mass, accel=accel, max_speed=max_speed, u_noise=u_noise, c_noise=c_noise,
-            collide=collide, silent=silent, world_length=self.world_length, walls=walls)
+            collide=collide, silent=silent, world_length=self.world_length, walls=walls,
+            num_obs=self.num_obs, obs_range=self.obs_range)
         kw = dict(device=self.device, dtype=dtype)
         E, N, L = self.E, self.N, self.L
         # optional per-agent arrays (kept alive here; the params struct stores raw pointers)
@@ -106,7 +120,7 @@ class BatchedFormationEnv:
         self.pos = torch.zeros(E, N, 2, **kw)
         self.vel = torch.zeros(E, N, 2, **kw)
         self.comm = torch.zeros(E, N, 2, **kw)
-        self.landmarks = torch.zeros(E, L, 2, **kw) if (self.scn == nat.FG_SCENARIO_BASIC or track_landmarks) else None
+        self.landmarks = torch.zeros(E, L, 2, **kw) if (self.scn != nat.FG_SCENARIO_HD or track_landmarks) else None
         self.ideal_shape = torch.zeros(E, N, 2, **kw) if self.scn == nat.FG_SCENARIO_HD else None
         self.ideal_vel = torch.zeros(E, 2, **kw) if self.scn == nat.FG_SCENARIO_HD else None
         self.step_count = torch.zeros(E, dtype=torch.int32, device=self.device)

@@ -80,9 +80,10 @@ class MultiAgentEnv(object):
         constructing an env needs no device call."""
         sc = self._native_scenario()
         if sc is not None:
-            from .batched import obs_dim
-            name = "formation_hd_env" if sc.native_kind == 0 else "basic_formation_env"
-            return obs_dim(name, len(self.world.agents), len(self.world.landmarks))
+            from .batched import obs_dim, SCENARIOS
+            name = [k for k, v in SCENARIOS.items() if v == sc.native_kind][0]
+            return obs_dim(name, len(self.world.agents), len(self.world.landmarks),
+                           int(getattr(sc, "num_obs", 3) or 0))
         return len(self.observation_callback(agent, self.world))
 
     def seed(self, seed=None):
@@ -102,8 +103,10 @@ class MultiAgentEnv(object):
         if kind is None:
             return None
         cls = type(sc)
-        from .envs import formation_hd_env, basic_formation_env
-        for stock in (formation_hd_env.Scenario, basic_formation_env.Scenario):
+        from .envs import (formation_hd_env, basic_formation_env, formation_hd_partial_env,
+                           formation_hd_partial_range_env)
+        for stock in (formation_hd_env.Scenario, basic_formation_env.Scenario,
+                      formation_hd_partial_env.Scenario, formation_hd_partial_range_env.Scenario):
             if isinstance(sc, stock):
                 if cls.observation is not stock.observation or cls.reward is not stock.reward:
                     return None

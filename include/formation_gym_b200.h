@@ -17,6 +17,7 @@
  *    env-major, contiguous:  pos/vel [E,N,2]  act [E,N,act_dim]  comm [E,N,2]  obs [E,N,D]
  *    reward [E,N,1]  indiv [E,N]  done [E,N] (uint8)  step [E] (int32)  ideal_shape [E,N,2]
  *    ideal_vel [E,2]  landmarks [E,L,2].   hd: L = N, D = 6N.  basic: D = 4 + 2L + 4(N-1).
+ *    hd_partial: D = 2 + 2L + 2 num_obs + 2(N-1).  hd_partial_range: D = 2 + 2L + 4(N-1).
  *    act_dim = 2 for silent agents (both target scenarios), 2 + 2 when params.silent == 0.
  *  - `float` entry points compute in fp32, the `_f64` twins in fp64 with FMA contraction
  *    disabled (the 25-step 1e-9 parity build).  Same semantics otherwise.
@@ -40,7 +41,7 @@
 extern "C" {
 #endif
 
-#define FG_ABI_VERSION 3
+#define FG_ABI_VERSION 4
 #define FG_MAX_AGENTS 256      /* one CTA holds at least one whole env; 3^5 = 243 fits */
 #define FG_MAX_LANDMARKS 256
 #define FG_MAX_WALLS 8
@@ -52,6 +53,11 @@ extern "C" {
 /* scenario ids */
 #define FG_SCENARIO_HD 0       /* formation_gym/envs/formation_hd_env.py */
 #define FG_SCENARIO_BASIC 1    /* formation_gym/envs/basic_formation_env.py */
+#define FG_SCENARIO_HD_PARTIAL 2        /* formation_gym/envs/formation_hd_partial_env.py: obs = [p_vel, landmark
+                                           positions (absolute), p_j - p_i of the next num_obs agents (cyclic), comm];
+                                           reward = -Hausdorff(agents - mean, landmarks - mean) - #collisions (s1+s2) */
+#define FG_SCENARIO_HD_PARTIAL_RANGE 3  /* formation_gym/envs/formation_hd_partial_range_env.py: as above with
+                                           other_pos of ALL others clipped to [-obs_range, obs_range] */
 
 /* core.Wall (formation_gym/core.py:27-41) */
 typedef struct fg_wall {
@@ -73,6 +79,7 @@ typedef struct fg_params {
     double max_speed;          /* core.py:64  used iff has_max_speed */
     double u_noise;            /* core.py:97  0 = off (None) */
     double c_noise;            /* core.py:99  0 = off (None) */
+    double obs_range;          /* FG_SCENARIO_HD_PARTIAL_RANGE: Scenario.obs_range (formation_hd_partial_range_env.py:15) */
     int32_t has_accel;
     int32_t has_max_speed;
     int32_t collide;           /* agents collide (formation_hd_env.py:24) */
@@ -81,7 +88,7 @@ typedef struct fg_params {
     int32_t n_walls;
     int32_t action_prescaled;  /* 1: `act` already is agent.action.u (after _set_action), i.e. World.step()
                                   called on its own (core.py:206); the sensitivity multiply is skipped */
-    int32_t reserved_;
+    int32_t num_obs;           /* FG_SCENARIO_HD_PARTIAL: Scenario.num_obs (formation_hd_partial_env.py:15) */
     /* optional per-agent DEVICE arrays [N] in the entry point's real type; NULL = scalar above.
        agent_accel / agent_max_speed entries < 0 mean "None" for that agent. */
     const void* agent_mass;

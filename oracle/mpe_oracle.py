@@ -7,6 +7,8 @@ relative to /root/reference):
   * ``World.step`` and helpers                          formation_gym/core.py:206-322 (+325-362 walls)
   * hd scenario ``observation/reward/reset_world``      formation_gym/envs/formation_hd_env.py:38-95,119-121
   * basic scenario ``observation/reward/reset_world``   formation_gym/envs/basic_formation_env.py:29-65,89-91
+  * partial-observation scenarios                       formation_gym/envs/formation_hd_partial_env.py:41-125,
+                                                        formation_gym/envs/formation_hd_partial_range_env.py:41-113
 
 Third-party arithmetic restated here (the reference pins no versions --
 ``setup.py:4-17`` has no install_requires; this container has numpy 2.3.5 / scipy 1.18.1):
@@ -287,6 +289,77 @@ def basic_reward(pos, landmarks, prm=BASIC_PARAMS):
                 r = np.where(dist < (size[i] + size[j]), r - 1, r)
             rew[:, i] = r
     return rew
+
+
+# ------------------------------------------------------------------------------------------
+# formation_hd_partial_env / formation_hd_partial_range_env scenario hooks
+# ------------------------------------------------------------------------------------------
+PARTIAL_PARAMS = WorldParams(agent_size=0.04, world_length=25)   # formation_hd_partial_env.py:15,29
+
+
+def partial_observation(pos, vel, landmarks, num_obs):
+    """formation_hd_partial_env.py:41-66: [v_i, landmark positions (absolute), p_j - p_i for
+    j = i+1 .. i+num_obs (cyclic), comm of the others (zeros)]."""
+    E, N, _ = pos.shape
+    L = landmarks.shape[1]
+    D = 2 + 2 * L + 2 * num_obs + 2 * (N - 1)
+    obs = np.zeros((E, N, D), np.float64)
+    for i in range(N):
+        obs[:, i, 0:2] = vel[:, i]
+        obs[:, i, 2:2 + 2 * L] = landmarks.reshape(E, 2 * L)
+        idx = [j % N for j in range(i + 1, i + 1 + num_obs)]                 # :53
+        obs[:, i, 2 + 2 * L:2 + 2 * L + 2 * num_obs] = (pos[:, idx] - pos[:, i:i + 1]).reshape(E, 2 * num_obs)
+    return obs
+
+
+def range_observation(pos, vel, landmarks, obs_range):
+    """formation_hd_partial_range_env.py:41-54: other_pos of ALL others clipped to +-obs_range."""
+    E, N, _ = pos.shape
+    L = landmarks.shape[1]
+    D = 2 + 2 * L + 4 * (N - 1)
+    obs = np.zeros((E, N, D), np.float64)
+    for i in range(N):
+        obs[:, i, 0:2] = vel[:, i]
+        obs[:, i, 2:2 + 2 * L] = landmarks.reshape(E, 2 * L)
+        others = [j for j in range(N) if j != i]
+        rel = np.clip(pos[:, others] - pos[:, i:i + 1], -obs_range, obs_range)   # :53
+        obs[:, i, 2 + 2 * L:2 + 2 * L + 2 * (N - 1)] = rel.reshape(E, 2 * (N - 1))
+    return obs
+
+
+def partial_reward(pos, landmarks, prm=PARTIAL_PARAMS):
+    """formation_hd_partial_env.py:68-87,123-125 (same in the range variant :56-75,111-113):
+    -max(dH(u, v), dH(v, u)) with u = agents - mean, v = landmarks - mean; -1 per other agent closer
+    than s_a + s_i."""
+    E, N, _ = pos.shape
+    _, size, _, _ = prm.per_agent(N)
+    u = pos - np.mean(pos, 1)[:, None, :]
+    v = landmarks - np.mean(landmarks, 1)[:, None, :]
+    base = -np.sqrt(np.maximum(directed_hausdorff_sq(u, v), directed_hausdorff_sq(v, u)))
+    rew = np.repeat(base[:, None], N, 1)
+    if prm.collide:
+        for i in range(N):
+            r = rew[:, i].copy()
+            for j in range(N):
+                if j == i:
+                    continue
+                d = pos[:, j] - pos[:, i]
+                dist = norm2(d[:, 0], d[:, 1])
+                r = np.where(dist < (size[i] + size[j]), r - 1, r)
+            rew[:, i] = r
+    return rew
+
+
+def partial_env_step(pos, vel, act, landmarks, step, num_obs=None, obs_range=None, prm=PARTIAL_PARAMS,
+                     noise=None):
+    """env.step for formation_hd_partial_env (num_obs given) or formation_hd_partial_range_env (obs_range)."""
+    p, v = world_step(pos, vel, act, prm, noise)
+    obs = partial_observation(p, v, landmarks, num_obs) if num_obs is not None \
+        else range_observation(p, v, landmarks, obs_range)
+    indiv = partial_reward(p, landmarks, prm)
+    new_step = np.asarray(step) + 1
+    return dict(pos=p, vel=v, obs=obs, indiv=indiv, reward=shared_reward(indiv),
+                done=new_step >= prm.world_length, step=new_step)
 
 
 # ------------------------------------------------------------------------------------------

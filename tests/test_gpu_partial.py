@@ -1,0 +1,92 @@
+"""formation_hd_partial_env / formation_hd_partial_range_env on the CUDA path, against
+fixtures frozen from the unmodified reference (tests/golden/{partial,range}_n*.npz) and the numpy oracle."""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+import formation_gym  # noqa: E402
+from formation_gym.batched import BatchedFormationEnv  # noqa: E402
+from oracle import mpe_oracle as mo  # noqa: E402
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+FILES = sorted(glob.glob(os.path.join(GOLD, "partial_n*.npz")) + glob.glob(os.path.join(GOLD, "range_n*.npz")))
+
+
+def _env(name, g, dtype, E=None, N=None, L=None, **kw):
+    scen = "formation_hd_partial_env" if name.startswith("partial") else "formation_hd_partial_range_env"
+    extra = dict(num_obs=int(g["num_obs"])) if name.startswith("partial") else dict(obs_range=float(g["obs_range"]))
+    extra.update(kw)
+    return BatchedFormationEnv(scen, E, N, episode_length=25, num_landmarks=L, dtype=dtype, auto_reset=False, **extra)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64], ids=["f32", "f64"])
+@pytest.mark.parametrize("path", FILES, ids=[os.path.basename(f) for f in FILES])
+def test_partial_single_step_golden(path, dtype):
+    g = np.load(path)
+    name = os.path.basename(path)
+    E, N = g["pos0"].shape[:2]
+    L = g["lm"].shape[1]
+    env = _env(name, g, dtype, E, N, L)
+    dev = lambda x: torch.as_tensor(np.ascontiguousarray(x), dtype=dtype, device="cuda")  # noqa: E731
+    env.pos.copy_(dev(g["pos0"])); env.vel.copy_(dev(g["vel0"])); env.landmarks.copy_(dev(g["lm"]))
+    env.step_count.copy_(torch.as_tensor(g["step0"], dtype=torch.int32, device="cuda"))
+    obs, rew, done, info = env.step(dev(g["act"]))
+    tol = 1e-5 if dtype == torch.float32 else 1e-12
+    err = lambda a, b: float(np.abs(a.double().cpu().numpy() - b).max())  # noqa: E731
+    assert obs.shape[2] == g["obs"].shape[2]
+    assert err(env.pos, g["pos"]) <= tol and err(env.vel, g["vel"]) <= tol
+    assert err(obs, g["obs"]) <= tol
+    assert err(info["individual_reward"], g["indiv"]) <= tol * (1 if dtype == torch.float32 else 10)
+    assert err(rew[:, :, 0], g["reward"]) <= tol * (4 if dtype == torch.float32 else 100)
+    assert np.array_equal(done.cpu().numpy(), g["done"])
+
+
+@pytest.mark.parametrize("scen,E,N,L,kw", [("formation_hd_partial_env", 300, 9, 5, dict(num_obs=3)),
+                                           ("formation_hd_partial_env", 33, 40, 7, dict(num_obs=12)),
+                                           ("formation_hd_partial_env", 5, 243, 243, dict(num_obs=2)),
+                                           ("formation_hd_partial_range_env", 300, 9, 4, dict(obs_range=0.7)),
+                                           ("formation_hd_partial_range_env", 17, 81, 81, dict(obs_range=0.25))])
+def test_partial_vs_oracle_random(scen, E, N, L, kw):
+    rng = np.random.default_rng(N * 13 + L)
+    f32 = lambda x: x.astype(np.float32).astype(np.float64)  # noqa: E731
+    pos = f32(rng.uniform(-0.4, 0.4, (E, N, 2))); vel = f32(rng.uniform(-0.5, 0.5, (E, N, 2)))
+    act = f32(rng.uniform(-1, 1, (E, N, 2))); lm = f32(rng.uniform(-1, 1, (E, L, 2)))
+    step0 = rng.integers(0, 25, E)
+    ref = mo.partial_env_step(pos, vel, act, lm, step0, num_obs=kw.get("num_obs"), obs_range=kw.get("obs_range"))
+    for dtype, tol in ((torch.float32, 1e-5), (torch.float64, 1e-11)):
+        env = BatchedFormationEnv(scen, E, N, episode_length=25, num_landmarks=L, dtype=dtype, auto_reset=False, **kw)
+        dev = lambda x: torch.as_tensor(np.ascontiguousarray(x), dtype=dtype, device="cuda")  # noqa: E731
+        env.pos.copy_(dev(pos)); env.vel.copy_(dev(vel)); env.landmarks.copy_(dev(lm))
+        env.step_count.copy_(torch.as_tensor(step0, dtype=torch.int32, device="cuda"))
+        obs, rew, done, info = env.step(dev(act))
+        err = lambda a, b: float(np.abs(a.double().cpu().numpy() - b).max())  # noqa: E731
+        assert err(env.pos, ref["pos"]) <= tol and err(obs, ref["obs"]) <= tol
+        assert err(info["individual_reward"], ref["indiv"]) <= tol * (1 if dtype == torch.float32 else 10)
+        R = ref["reward"]
+        assert np.all(np.abs(rew[:, 0, 0].double().cpu().numpy() - R) <= tol + 1e-6 * np.abs(R))
+        assert np.array_equal(done[:, 0].cpu().numpy(), ref["done"])
+
+
+def test_partial_rollout_auto_reset_and_facade():
+    """Batched rollout with auto-reset (landmarks redrawn, step counter reset) and the single-env facade
+    through the reference API."""
+    env = BatchedFormationEnv("formation_hd_partial_env", 64, 5, episode_length=4, seed=3)
+    env.reset()
+    lm0 = env.landmarks.clone()
+    for t in range(4):
+        obs, rew, done, info = env.step_random()
+    assert bool(done.all()) and int(env.step_count.abs().sum()) == 0
+    assert not torch.equal(lm0, env.landmarks)                      # reset_world drew new landmarks
+    assert torch.equal(env.observe(), obs)                          # the returned obs is the reset state's obs
+    fenv = formation_gym.make_env("formation_hd_partial_range_env", False, 4, episode_length=6)
+    fenv.seed(1)
+    obs_n = fenv.reset()
+    assert len(obs_n) == 4 and obs_n[0].shape == (2 + 2 * 4 + 4 * 3,)
+    obs_n, reward_n, done_n, info_n = fenv.step([np.array([0.1, -0.2])] * 4)
+    assert len(reward_n) == 4 and reward_n[0] is reward_n[1] and done_n == [False] * 4
+    assert 'individual_reward' in info_n[0]
