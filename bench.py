@@ -397,7 +397,8 @@ def also_configs(formation_gym, torch, device, dtype, peak):
             ("configs[2] hd N=27 E=65536", "formation_hd_env", 27, 65536, 50, "step"),
             ("configs[3] hd N=243 E=1024 (one GPU's share of 8192)", "formation_hd_env", 243, 1024, 30, "step"),
             ("configs[3] hd N=243 E=8192 (all 8192 envs on one GPU: steady state, no wave tail)", "formation_hd_env", 243, 8192, 8, "step"),
-            ("hd N=243 E=1024 state+reward only (no obs)", "formation_hd_env", 243, 1024, 30, "noobs"),
+            ("hd N=243 E=1024 state+reward only (no obs; random policy drawn in the step kernel)", "formation_hd_env", 243, 1024, 30, "noobs"),
+            ("hd N=243 E=8192 state+reward only (no obs; steady state)", "formation_hd_env", 243, 8192, 8, "noobs"),
             ("hd N=3 E=1048576", "formation_hd_env", 3, 1048576, 50, "step"),
             ("basic N=3 L=3 E=1048576", "basic_formation_env", 3, 1048576, 50, "step")):
         try:
@@ -415,6 +416,8 @@ def also_configs(formation_gym, torch, device, dtype, peak):
                         graph.replay()
                     elif mode == "bfs":
                         env.step(env.bfs_actions(3))
+                    elif mode == "noobs":
+                        env.step_random()                     # one launch per step: Philox actions in-kernel
                     else:
                         env.sample_actions(); env.step(env.actions)
             run(5)
@@ -432,8 +435,8 @@ def also_configs(formation_gym, torch, device, dtype, peak):
                 row.update({"bound": "fp32", "algorithmic_TFLOPs": tf, "fp32_peak_TFLOPs": fp32_peak,
                             "fp32_frac": (tf / fp32_peak) if fp32_peak else None,
                             "flops_per_env_step": flops_per_env_step(N),
-                            "note": "includes the random-policy kernel of the step; fraction of the MEASURED "
-                                    "scalar-FFMA peak"})
+                            "note": "one fused launch per step (actions from Philox inside the kernel); "
+                                    "fraction of the MEASURED scalar-FFMA peak"})
             res.append(row)
             del env
         except Exception as ex:  # keep the headline line alive

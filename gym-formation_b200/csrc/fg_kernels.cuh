@@ -162,7 +162,7 @@ __device__ __forceinline__ void wall_force(const WallT<T>& w, T px, T py, T size
 // FP: fast pair loops of fg_pairs.cuh (fp32, hd, uniform agents, N >= 32): structure-of-arrays partner
 // data, packed FFMA2/FADD2/FMUL2 arithmetic, group filters, warp-shuffle centroid and reductions.
 template <typename T, int SCN, bool PHYS, bool OBSREW, bool HET, int OM, bool FP>
-__global__ void __launch_bounds__(kBlock, (OM == 2) ? 4 : 3) k_step(const __grid_constant__ KArgs<T> a) {
+__global__ void __launch_bounds__(kBlock, (OM == 2 || FP) ? 4 : 3) k_step(const __grid_constant__ KArgs<T> a) {
     typedef Ops<T> O;
     typedef typename O::R2 R2;
     typedef typename O::Bits Bits;
@@ -662,10 +662,13 @@ __global__ void __launch_bounds__(kBlock, (OM == 2) ? 4 : 3) k_step(const __grid
                         const int j = j4 + jj;
                         if (j >= N || j == i) continue;
                         R2 q = envp[j];
-                        if (O::norm2(O::sub(q.x, p.x), O::sub(q.y, p.y)) < a.rthr) ++col;
+                        const T dx = O::sub(q.x, p.x), dy = O::sub(q.y, p.y);
+                        // the thread's own group is always flagged: guarded squared test first, the
+                        // reference's sqrt-then-compare (Q18) only for true candidates
+                        if (dx * dx + dy * dy < a.rthr2_hi) { if (O::norm2(dx, dy) < a.rthr) ++col; }
                     }
                 }
-                hbits = __float_as_uint(fmaxf(rowmin, colmin));               // d2 >= 0: bit order == value order
+                hbits =__float_as_uint(fmaxf(rowmin, colmin));               // d2 >= 0: bit order == value order
             }
             env_atomic_max(reinterpret_cast<unsigned*>(s_rowmax), hbits);
             env_atomic_add(s_col, col);
