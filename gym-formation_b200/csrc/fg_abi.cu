@@ -11,6 +11,7 @@
 
 #include "fg_kernels.cuh"
 #include "fg_warp.cuh"
+#include "fg_obstacle.cuh"
 #include "fg_policy.cuh"
 
 namespace {
@@ -50,6 +51,15 @@ int fill_args(fg::KArgs<T>& a, const fg_params* p, const fg_buffers* b, int scen
         if (L < 1 || L > FG_MAX_LANDMARKS) return fail(FG_ERR_ARG, "L must be in [1, FG_MAX_LANDMARKS]%s");
         if (scenario == FG_SCENARIO_HD_PARTIAL && (p->num_obs < 0 || p->num_obs > 4 * FG_MAX_AGENTS))
             return fail(FG_ERR_ARG, "num_obs out of range%s");
+    } else if (scenario == FG_SCENARIO_HD_OBSTACLE) {
+        if (L < 1 || L > FG_MAX_LANDMARKS) return fail(FG_ERR_ARG, "L must be in [1, FG_MAX_LANDMARKS]%s");
+        if (p->num_obstacles < 0 || p->num_obstacles >= L)
+            return fail(FG_ERR_ARG, "num_obstacles must be in [0, L): L counts goal landmarks + obstacles%s");
+        if (!p->silent) return fail(FG_ERR_ARG, "formation_hd_obs_env: silent agents only (formation_hd_obs_env.py:28)%s");
+        if (p->agent_mass || p->agent_size_arr || p->agent_accel || p->agent_max_speed)
+            return fail(FG_ERR_ARG, "formation_hd_obs_env: per-agent mass/size/accel/max_speed arrays are not supported%s");
+        if (!(p->obstacle_size > 0.0) || !(p->obstacle_mass > 0.0))
+            return fail(FG_ERR_ARG, "formation_hd_obs_env: obstacle_size and obstacle_mass must be positive%s");
     } else {
         return fail(FG_ERR_ARG, "unknown scenario id%s");
     }
@@ -68,7 +78,10 @@ int fill_args(fg::KArgs<T>& a, const fg_params* p, const fg_buffers* b, int scen
     a.IPR = scenario == FG_SCENARIO_HD ? 3 * N
           : scenario == FG_SCENARIO_BASIC ? 2 + L + 2 * (N - 1)
           : scenario == FG_SCENARIO_HD_PARTIAL ? 1 + L + p->num_obs + (N - 1)
-          : 1 + L + 2 * (N - 1);
+          : 1 + L + 2 * (N - 1);                    // partial range; obstacle: 1 + goals + obstacles + 2(N-1)
+    a.lmv = (R2*)b->landmark_vel; a.n_obst = scenario == FG_SCENARIO_HD_OBSTACLE ? p->num_obstacles : 0;
+    a.osize = (T)p->obstacle_size; a.omass = (T)p->obstacle_mass;
+    a.ofloor = (T)p->obstacle_floor; a.ofall = (T)p->obstacle_fall_vy;
     a.num_obs = p->num_obs; a.obs_range = (T)p->obs_range;
     a.magic_n = magic_for(N); a.magic_ipr = magic_for(a.IPR);
     a.act_r2 = p->silent ? 1 : 2;
@@ -196,6 +209,26 @@ int launch(const fg::KArgs<T>& a, int scenario, const fg_params* p, void* stream
 }
 
 
+// formation_hd_obs_env (fg_obstacle.cuh)
+template <typename T, bool PHYS>
+int launch_obstacle(const fg::KArgs<T>& a, void* stream) {
+    typedef typename fg::Ops<T>::R2 R2;
+    typedef typename fg::Ops<T>::Bits Bits;
+    const size_t nA = (size_t)a.EPC * a.N;
+    size_t smem = (4 * nA + (size_t)a.EPC * a.L + 2 * (size_t)a.EPC * a.n_obst + 2 * a.EPC) * sizeof(R2)
+                  + a.EPC * sizeof(Bits) + 3 * a.EPC * sizeof(int);
+    smem = (smem + 15) & ~(size_t)15;
+    if (smem > 48 * 1024) {
+        cudaError_t e1 = cudaFuncSetAttribute(fg::k_step_obst<T, PHYS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e1 != cudaSuccess) return fail(FG_ERR_CUDA, "cudaFuncSetAttribute failed: %s", cudaGetErrorString(e1));
+    }
+    const int grid = (a.E + a.EPC - 1) / a.EPC;
+    fg::k_step_obst<T, PHYS><<<grid, fg::kBlock, smem, (cudaStream_t)stream>>>(a);
+    cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess) return fail(FG_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(err));
+    return FG_OK;
+}
+
 // ---- warp-autonomous fast path (fg_warp.cuh) ----------------------------------------------------
 // Resident CTAs per SM for w warps per CTA (occupancy API; shared memory is the limiter: one
 // observation-span image per warp).  Computed once per instantiation; all GPUs of a box are alike.
@@ -293,6 +326,7 @@ int obs_reward_impl(const fg_params* p, const fg_buffers* b, int scenario, int E
     if (scenario != FG_SCENARIO_HD && !b->landmarks)
         return fail(FG_ERR_ARG, "fg_obs_reward: landmarks must be non-null for this scenario%s");
     a.step = nullptr; a.done = nullptr; a.ep_return = nullptr; a.ep_coll = nullptr; a.stats = nullptr;
+    if (scenario == FG_SCENARIO_HD_OBSTACLE) return launch_obstacle<T, false>(a, stream);
     return launch<T, false, true>(a, scenario, p, stream);
 }
 
@@ -316,6 +350,7 @@ int step_fused_impl(const fg_params* p, const fg_buffers* b, int scenario, int E
     if (scenario != FG_SCENARIO_HD && !b->landmarks)
         return fail(FG_ERR_ARG, "fg_step_fused: landmarks must be non-null for this scenario%s");
     a.n_steps = n_steps; a.random_actions = random_actions; a.auto_reset = auto_reset;
+    if (scenario == FG_SCENARIO_HD_OBSTACLE) return launch_obstacle<T, true>(a, stream);
     if (warp_path_ok<T>(a, scenario, p, b)) {
         cudaStream_t st = (cudaStream_t)stream;
         switch (N) {
@@ -341,6 +376,7 @@ int reset_impl(const fg_params* p, const fg_buffers* b, int scenario, int E, int
     cudaStream_t st = (cudaStream_t)stream;
     const int grid = (E + 127) / 128;
     if (scenario == FG_SCENARIO_HD) fg::k_reset<T, fg::kScnHD><<<grid, 128, 0, st>>>(a, mask);
+    else if (scenario == FG_SCENARIO_HD_OBSTACLE) fg::k_reset_obst<T><<<grid, 128, 0, st>>>(a, mask);
     else                            fg::k_reset<T, fg::kScnBasic><<<grid, 128, 0, st>>>(a, mask);
     cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess) return fail(FG_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(err));

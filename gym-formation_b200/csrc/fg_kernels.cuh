@@ -58,6 +58,9 @@ template <typename T> struct KArgs {
     int row_early;                   // OM == 2, fp32, odd N, 16-byte aligned obs: rows leave as aligned bulk pieces, the
                                      // static 2/3 before the physics and the dynamic 1/3 before the reward pass
     int fast_pairs;                  // tile kernel: packed pair loops of fg_pairs.cuh (N >= 32; fp32 hd uniform only)
+    R2* lmv;                         // obstacle scenario: landmark velocities [E,L,2] (obstacle entries used)
+    int n_obst;                      // obstacle scenario: the last n_obst landmarks are movable colliding obstacles
+    T osize, omass, ofloor, ofall;   // obstacle size / mass, floor y and fall velocity of the reward hook's rule
     int num_obs;                     // partial: observed neighbours (formation_hd_partial_env.py:15,53)
     T obs_range;                     // range: clip bound of other_pos (formation_hd_partial_range_env.py:15,53)
     int n_steps, random_actions, auto_reset;

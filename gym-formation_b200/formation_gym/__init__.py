@@ -18,7 +18,7 @@ __all__ = ["make_env", "make_batched_env", "make_vec_env", "ezpolicy", "get_acti
            "BatchedFormationEnv", "CudaVecEnv", "SCENARIOS"]
 
 SCENARIOS = ("basic_formation_env", "formation_hd_env", "formation_hd_partial_env",
-             "formation_hd_partial_range_env")
+             "formation_hd_partial_range_env", "formation_hd_obs_env")
 
 
 def _load_scenario(scenario_name):
@@ -37,7 +37,8 @@ def make_env(scenario_name='basic_formation_env', benchmark=False, num_agents=3,
     scenario = _load_scenario(scenario_name)
     if scenario_name == "formation_hd_env" and episode_length is not None:
         world = scenario.make_world(num_agents, episode_length)
-    elif scenario_name.startswith("formation_hd_partial") and episode_length is not None:
+    elif scenario_name in ("formation_hd_partial_env", "formation_hd_partial_range_env", "formation_hd_obs_env") \
+            and episode_length is not None:
         world = scenario.make_world(num_agents, world_length=episode_length)
     else:
         world = scenario.make_world(num_agents)

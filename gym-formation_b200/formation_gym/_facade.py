@@ -44,6 +44,8 @@ class FacadeBackend(object):
         self.shape = torch.zeros(1, N, 2, **kw)
         self.ivel = torch.zeros(1, 2, **kw)
         self.lm = torch.zeros(1, max(L, 1), 2, **kw)
+        self.lmv = torch.zeros(1, max(L, 1), 2, **kw)          # landmark.state.p_vel (obstacle scenario)
+        self._n_obst = 0
         self.step = torch.zeros(1, dtype=torch.int32, device=self.device)
         self.obs = None
         self.reward = torch.zeros(1, N, 1, **kw)
@@ -67,11 +69,21 @@ class FacadeBackend(object):
         agents = world.agents
         if not all(a.movable for a in agents):
             raise NotImplementedError("immovable agents are not supported by the accelerated path")
-        for l in world.landmarks:
-            if l.movable or l.collide:
+        obstacles = [l for l in world.landmarks if l.movable or l.collide]
+        n_obst = len(obstacles)
+        if n_obst:
+            # formation_hd_obs_env: trailing landmarks that are movable AND collide, uniform size / mass
+            tail = world.landmarks[len(world.landmarks) - n_obst:]
+            ok = (scenario_kind == nat.FG_SCENARIO_HD_OBSTACLE and n_obst < len(world.landmarks)
+                  and all(a is b for a, b in zip(tail, obstacles))
+                  and all(l.movable and l.collide and l.max_speed is None for l in obstacles)
+                  and len({(float(l.size), float(l.mass)) for l in obstacles}) == 1)
+            if not ok:
                 raise NotImplementedError(
-                    "movable / colliding landmarks (formation_hd_obs_env) are outside the "
-                    "accelerated hot path (SURVEY.md 8f)")
+                    "movable / colliding landmarks are supported as the trailing, uniform obstacles of the "
+                    "formation_hd_obs_env scenario hooks only (fg_step_fused / fg_obs_reward)")
+        elif scenario_kind == nat.FG_SCENARIO_HD_OBSTACLE and len(world.landmarks) < 1:
+            raise NotImplementedError("formation_hd_obs_env needs at least one goal landmark")
         collide, _ = _uniform([bool(a.collide) for a in agents], "collide")
         silent, _ = _uniform([bool(a.silent) for a in agents], "silent")
         u_noise, _ = _uniform([a.u_noise or None for a in agents], "u_noise")
@@ -95,7 +107,10 @@ class FacadeBackend(object):
             max_speed=vmax if vmax_arr is None else None,
             u_noise=u_noise, c_noise=c_noise, collide=collide, silent=silent,
             world_length=world.world_length, walls=walls, action_prescaled=prescaled,
-            num_obs=getattr(scenario, "num_obs", 0) or 0, obs_range=getattr(scenario, "obs_range", 0.0) or 0.0)
+            num_obs=getattr(scenario, "num_obs", 0) or 0, obs_range=getattr(scenario, "obs_range", 0.0) or 0.0,
+            num_obstacles=n_obst, obstacle_size=float(obstacles[0].size) if n_obst else 0.15,
+            obstacle_mass=float(obstacles[0].mass) if n_obst else 1.0)
+        self._n_obst = n_obst
         self._keep = []
         for field, arr in (("agent_mass", mass_arr), ("agent_size_arr", size_arr),
                            ("agent_accel", accel_arr), ("agent_max_speed", vmax_arr)):
@@ -126,6 +141,7 @@ class FacadeBackend(object):
         b.pos, b.vel, b.act, b.comm = nat.ptr(self.pos), nat.ptr(self.vel), nat.ptr(self.act), nat.ptr(self.comm)
         b.ideal_shape, b.ideal_vel = nat.ptr(self.shape), nat.ptr(self.ivel)
         b.landmarks = nat.ptr(self.lm) if self.L > 0 else None
+        b.landmark_vel = nat.ptr(self.lmv) if (self.L > 0 and scenario_kind == nat.FG_SCENARIO_HD_OBSTACLE) else None
         b.step = nat.ptr(self.step)
         if with_obs:
             from .batched import obs_dim, SCENARIOS
@@ -173,6 +189,22 @@ class FacadeBackend(object):
             self._up(self.ivel, np.asarray(scenario.ideal_vel, np.float64))
         if self.L > 0:
             self._up(self.lm, np.stack([np.asarray(l.state.p_pos, np.float64) for l in world.landmarks]))
+        if kind == nat.FG_SCENARIO_HD_OBSTACLE:
+            self._up(self.lmv, np.stack([np.zeros(2) if l.state.p_vel is None else np.asarray(l.state.p_vel, np.float64)
+                                         for l in world.landmarks]))
+
+    def _scatter_obstacles(self, world, with_pos):
+        """Obstacle state back to the host records: positions after a fused step, velocities as the reward
+        hook's rule leaves them (formation_hd_obs_env.py:85-88)."""
+        n = self._n_obst
+        if not n:
+            return
+        lm = self.lm[0].cpu().numpy().astype(np.float64)
+        lv = self.lmv[0].cpu().numpy().astype(np.float64)
+        for k in range(self.L - n, self.L):
+            if with_pos:
+                world.landmarks[k].state.p_pos = lm[k].copy()
+            world.landmarks[k].state.p_vel = lv[k].copy()
 
     def scenario_eval(self, world, scenario, kind):
         """observation + reward of every agent from the CURRENT host state (one launch, cached on
@@ -185,6 +217,8 @@ class FacadeBackend(object):
                np.asarray(getattr(scenario, "ideal_shape", 0.0), np.float64).tobytes(),
                np.asarray(getattr(scenario, "ideal_vel", 0.0), np.float64).tobytes())
         if key == self._cache_key:
+            if kind == nat.FG_SCENARIO_HD_OBSTACLE:
+                self._scatter_obstacles(world, with_pos=False)
             return self._cache_val
         p, _ = self._params(world, kind, False, scenario)
         self._num_obs = int(getattr(scenario, "num_obs", 3) or 0)
@@ -207,6 +241,8 @@ class FacadeBackend(object):
                 l.state.p_pos = lm[k].copy()
             lmh = lm
             key = key[:3] + (lmh.tobytes(),) + key[4:]
+        if kind == nat.FG_SCENARIO_HD_OBSTACLE:
+            self._scatter_obstacles(world, with_pos=False)       # the reward hook's velocity rule
         self._cache_key, self._cache_val = key, val
         return val
 
@@ -233,6 +269,8 @@ class FacadeBackend(object):
             lm = self.lm[0].cpu().numpy().astype(np.float64)
             for k, l in enumerate(world.landmarks):
                 l.state.p_pos = lm[k].copy()
+        if kind == nat.FG_SCENARIO_HD_OBSTACLE:
+            self._scatter_obstacles(world, with_pos=True)
         self._cache_key = None
         return dict(obs=self.obs[0].cpu().numpy().astype(np.float64),
                     indiv=self.indiv[0].cpu().numpy().astype(np.float64),

@@ -8,7 +8,7 @@ import os
 
 from . import _build
 
-FG_ABI_VERSION = 4
+FG_ABI_VERSION = 5
 FG_MAX_AGENTS = 256
 FG_MAX_LANDMARKS = 256
 FG_MAX_WALLS = 8
@@ -16,6 +16,7 @@ FG_SCENARIO_HD = 0
 FG_SCENARIO_BASIC = 1
 FG_SCENARIO_HD_PARTIAL = 2
 FG_SCENARIO_HD_PARTIAL_RANGE = 3
+FG_SCENARIO_HD_OBSTACLE = 4
 
 EXPORTS = [
     "fg_abi_version", "fg_last_error", "fg_device_info", "fg_launch_geometry",
@@ -40,9 +41,11 @@ class fg_params(C.Structure):
         ("contact_margin", C.c_double), ("sensitivity", C.c_double), ("agent_size", C.c_double),
         ("mass", C.c_double), ("accel", C.c_double), ("max_speed", C.c_double),
         ("u_noise", C.c_double), ("c_noise", C.c_double), ("obs_range", C.c_double),
+        ("obstacle_size", C.c_double), ("obstacle_mass", C.c_double), ("obstacle_floor", C.c_double),
+        ("obstacle_fall_vy", C.c_double),
         ("has_accel", C.c_int32), ("has_max_speed", C.c_int32), ("collide", C.c_int32),
         ("silent", C.c_int32), ("world_length", C.c_int32), ("n_walls", C.c_int32),
-        ("action_prescaled", C.c_int32), ("num_obs", C.c_int32),
+        ("action_prescaled", C.c_int32), ("num_obs", C.c_int32), ("num_obstacles", C.c_int32),
         ("agent_mass", C.c_void_p), ("agent_size_arr", C.c_void_p),
         ("agent_accel", C.c_void_p), ("agent_max_speed", C.c_void_p),
         ("walls", fg_wall * FG_MAX_WALLS),
@@ -55,7 +58,7 @@ class fg_buffers(C.Structure):
         ("ideal_shape", C.c_void_p), ("ideal_vel", C.c_void_p), ("landmarks", C.c_void_p),
         ("step", C.c_void_p), ("obs", C.c_void_p), ("reward", C.c_void_p), ("indiv", C.c_void_p),
         ("done", C.c_void_p), ("ep_return", C.c_void_p), ("ep_collisions", C.c_void_p),
-        ("stats", C.c_void_p), ("tick_dev", C.c_void_p),
+        ("stats", C.c_void_p), ("landmark_vel", C.c_void_p), ("tick_dev", C.c_void_p),
     ]
 
 
@@ -113,7 +116,8 @@ def check(rc, what):
 def make_params(dt=0.1, damping=0.25, contact_force=1e2, contact_margin=1e-3, sensitivity=5.0,
                 agent_size=0.03, mass=1.0, accel=None, max_speed=None, u_noise=None, c_noise=None,
                 collide=True, silent=True, world_length=100, walls=(), action_prescaled=False,
-                num_obs=0, obs_range=0.0):
+                num_obs=0, obs_range=0.0, num_obstacles=0, obstacle_size=0.15, obstacle_mass=1.0,
+                obstacle_floor=-2.2, obstacle_fall_vy=-1.0):
     """fg_params from World/Agent attributes (formation_gym/core.py:45-139 defaults)."""
     p = fg_params()
     p.dt, p.damping, p.contact_force, p.contact_margin = dt, damping, contact_force, contact_margin
@@ -127,6 +131,8 @@ def make_params(dt=0.1, damping=0.25, contact_force=1e2, contact_margin=1e-3, se
     p.collide, p.silent, p.world_length = int(bool(collide)), int(bool(silent)), int(world_length)
     p.action_prescaled = int(bool(action_prescaled))
     p.num_obs, p.obs_range = int(num_obs), float(obs_range)
+    p.num_obstacles, p.obstacle_size, p.obstacle_mass = int(num_obstacles), float(obstacle_size), float(obstacle_mass)
+    p.obstacle_floor, p.obstacle_fall_vy = float(obstacle_floor), float(obstacle_fall_vy)
     walls = list(walls)
     if len(walls) > FG_MAX_WALLS:
         raise NativeError("at most %d walls are supported" % FG_MAX_WALLS)

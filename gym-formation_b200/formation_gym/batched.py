@@ -24,19 +24,25 @@ _NULL_CTX = contextlib.nullcontext()
 
 SCENARIOS = {"formation_hd_env": nat.FG_SCENARIO_HD, "basic_formation_env": nat.FG_SCENARIO_BASIC,
              "formation_hd_partial_env": nat.FG_SCENARIO_HD_PARTIAL,
-             "formation_hd_partial_range_env": nat.FG_SCENARIO_HD_PARTIAL_RANGE}
+             "formation_hd_partial_range_env": nat.FG_SCENARIO_HD_PARTIAL_RANGE,
+             "formation_hd_obs_env": nat.FG_SCENARIO_HD_OBSTACLE}
 # scenario defaults: agent size, episode length (formation_hd_env.py:13,26; basic_formation_env.py:18,
 # core.py:113)
 _DEFAULTS = {"formation_hd_env": dict(agent_size=0.03, world_length=100),
              "basic_formation_env": dict(agent_size=0.1, world_length=50),
              # formation_hd_partial_env.py:15,29 / formation_hd_partial_range_env.py:15,29
              "formation_hd_partial_env": dict(agent_size=0.04, world_length=25, num_landmarks=5),
-             "formation_hd_partial_range_env": dict(agent_size=0.04, world_length=25, num_landmarks=4)}
+             "formation_hd_partial_range_env": dict(agent_size=0.04, world_length=25, num_landmarks=4),
+             # formation_hd_obs_env.py:14,29: 4 goal landmarks + 3 obstacles
+             "formation_hd_obs_env": dict(agent_size=0.1, world_length=50, num_landmarks=4)}
 
 
 def obs_dim(scenario, num_agents, num_landmarks=3, num_obs=3):
     """Observation length per agent (hd: 6N, formation_hd_env.py:59; basic: 4+2L+4(N-1); partial:
-    2+2L+2*num_obs+2(N-1), formation_hd_partial_env.py:66; partial range: 2+2L+4(N-1))."""
+    2+2L+2*num_obs+2(N-1), formation_hd_partial_env.py:66; partial range: 2+2L+4(N-1); obstacle:
+    2+2L+4(N-1) with L = goal landmarks + obstacles, formation_hd_obs_env.py:68)."""
+    if scenario == "formation_hd_obs_env":
+        return 2 + 2 * num_landmarks + 4 * (num_agents - 1)
     if scenario == "formation_hd_env":
         return 6 * num_agents
     if scenario == "formation_hd_partial_env":
@@ -60,7 +66,8 @@ class BatchedFormationEnv:
                  silent=True, collide=True, accel=None, max_speed=None, mass=1.0, agent_size=None,
                  agent_mass=None, agent_sizes=None, agent_accel=None, agent_max_speed=None,
                  walls=(), dt=0.1, damping=0.25, contact_force=1e2, contact_margin=1e-3,
-                 sensitivity=5.0, num_obs=3, obs_range=0.7):
+                 sensitivity=5.0, num_obs=3, obs_range=0.7, num_obstacles=3, obstacle_size=0.15,
+                 obstacle_mass=1.0, obstacle_floor=-2.2, obstacle_fall_vy=-1.0):
         if scenario not in SCENARIOS:
             raise ValueError("unknown scenario %r (supported: %s)" % (scenario, sorted(SCENARIOS)))
         if dtype not in (torch.float32, torch.float64):
@@ -74,6 +81,11 @@ class BatchedFormationEnv:
         if num_landmarks is None:
             num_landmarks = _DEFAULTS[scenario].get("num_landmarks", 3)
         self.L = self.N if self.scn == nat.FG_SCENARIO_HD else int(num_landmarks)
+        # formation_hd_obs_env: `landmarks` holds the goal landmarks, then the obstacles (world.landmarks order,
+        # formation_hd_obs_env.py:31-44); L counts both
+        self.num_obstacles = int(num_obstacles) if self.scn == nat.FG_SCENARIO_HD_OBSTACLE else 0
+        self.num_goals = self.L
+        self.L += self.num_obstacles
         self.num_obs, self.obs_range = int(num_obs), float(obs_range)
         if self.scn == nat.FG_SCENARIO_HD and self.N < 3:
             raise ValueError("formation_hd_env needs num_agents >= 3 (formation_hd_env.py:58)")
@@ -100,7 +112,9 @@ class BatchedFormationEnv:
             sensitivity=sensitivity, agent_size=d["agent_size"] if agent_size is None else agent_size,
             mass=mass, accel=accel, max_speed=max_speed, u_noise=u_noise, c_noise=c_noise,
             collide=collide, silent=silent, world_length=self.world_length, walls=walls,
-            num_obs=self.num_obs, obs_range=self.obs_range)
+            num_obs=self.num_obs, obs_range=self.obs_range, num_obstacles=self.num_obstacles,
+            obstacle_size=obstacle_size, obstacle_mass=obstacle_mass, obstacle_floor=obstacle_floor,
+            obstacle_fall_vy=obstacle_fall_vy)
         kw = dict(device=self.device, dtype=dtype)
         E, N, L = self.E, self.N, self.L
         # optional per-agent arrays (kept alive here; the params struct stores raw pointers)
@@ -121,6 +135,8 @@ class BatchedFormationEnv:
         self.vel = torch.zeros(E, N, 2, **kw)
         self.comm = torch.zeros(E, N, 2, **kw)
         self.landmarks = torch.zeros(E, L, 2, **kw) if (self.scn != nat.FG_SCENARIO_HD or track_landmarks) else None
+        # landmark.state.p_vel; only the obstacle entries [:, num_goals:] are live
+        self.landmark_vel = torch.zeros(E, L, 2, **kw) if self.scn == nat.FG_SCENARIO_HD_OBSTACLE else None
         self.ideal_shape = torch.zeros(E, N, 2, **kw) if self.scn == nat.FG_SCENARIO_HD else None
         self.ideal_vel = torch.zeros(E, 2, **kw) if self.scn == nat.FG_SCENARIO_HD else None
         self.step_count = torch.zeros(E, dtype=torch.int32, device=self.device)
@@ -151,6 +167,7 @@ class BatchedFormationEnv:
         b.comm = nat.ptr(self.comm)
         b.ideal_shape, b.ideal_vel = nat.ptr(self.ideal_shape), nat.ptr(self.ideal_vel)
         b.landmarks = nat.ptr(self.landmarks)
+        b.landmark_vel = nat.ptr(self.landmark_vel)
         b.step = nat.ptr(self.step_count)
         b.obs = nat.ptr(self.obs) if obs == "default" else nat.ptr(obs)
         b.reward, b.indiv, b.done = nat.ptr(self.reward), nat.ptr(self.indiv), nat.ptr(self._done_u8)
@@ -371,7 +388,7 @@ class BatchedFormationEnv:
     def state_dict(self):
         sd = {k: getattr(self, k).clone() for k in
               ("pos", "vel", "comm", "step_count", "ep_return", "ep_collisions", "stats")}
-        for k in ("landmarks", "ideal_shape", "ideal_vel"):
+        for k in ("landmarks", "landmark_vel", "ideal_shape", "ideal_vel"):
             if getattr(self, k) is not None:
                 sd[k] = getattr(self, k).clone()
         sd["rng"] = {"seed": self.seed_value, "env_offset": self.env_offset,

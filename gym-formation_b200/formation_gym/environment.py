@@ -104,9 +104,10 @@ class MultiAgentEnv(object):
             return None
         cls = type(sc)
         from .envs import (formation_hd_env, basic_formation_env, formation_hd_partial_env,
-                           formation_hd_partial_range_env)
+                           formation_hd_partial_range_env, formation_hd_obs_env)
         for stock in (formation_hd_env.Scenario, basic_formation_env.Scenario,
-                      formation_hd_partial_env.Scenario, formation_hd_partial_range_env.Scenario):
+                      formation_hd_partial_env.Scenario, formation_hd_partial_range_env.Scenario,
+                      formation_hd_obs_env.Scenario):
             if isinstance(sc, stock):
                 if cls.observation is not stock.observation or cls.reward is not stock.reward:
                     return None

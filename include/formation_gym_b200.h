@@ -18,6 +18,7 @@
  *    reward [E,N,1]  indiv [E,N]  done [E,N] (uint8)  step [E] (int32)  ideal_shape [E,N,2]
  *    ideal_vel [E,2]  landmarks [E,L,2].   hd: L = N, D = 6N.  basic: D = 4 + 2L + 4(N-1).
  *    hd_partial: D = 2 + 2L + 2 num_obs + 2(N-1).  hd_partial_range: D = 2 + 2L + 4(N-1).
+ *    hd_obstacle: D = 2 + 2L + 4(N-1) (L = goal landmarks + obstacles).
  *    act_dim = 2 for silent agents (both target scenarios), 2 + 2 when params.silent == 0.
  *  - `float` entry points compute in fp32, the `_f64` twins in fp64 with FMA contraction
  *    disabled (the 25-step 1e-9 parity build).  Same semantics otherwise.
@@ -41,7 +42,7 @@
 extern "C" {
 #endif
 
-#define FG_ABI_VERSION 4
+#define FG_ABI_VERSION 5
 #define FG_MAX_AGENTS 256      /* one CTA holds at least one whole env; 3^5 = 243 fits */
 #define FG_MAX_LANDMARKS 256
 #define FG_MAX_WALLS 8
@@ -58,6 +59,14 @@ extern "C" {
                                            reward = -Hausdorff(agents - mean, landmarks - mean) - #collisions (s1+s2) */
 #define FG_SCENARIO_HD_PARTIAL_RANGE 3  /* formation_gym/envs/formation_hd_partial_range_env.py: as above with
                                            other_pos of ALL others clipped to [-obs_range, obs_range] */
+
+#define FG_SCENARIO_HD_OBSTACLE 4       /* formation_gym/envs/formation_hd_obs_env.py: the last num_obstacles entries of
+                                           `landmarks` are movable COLLIDING obstacles (agent-obstacle and
+                                           obstacle-obstacle contact forces, integrated like agents, core.py:240-277);
+                                           obs = [p_vel, goal landmarks (absolute), obstacles - p_i, p_j - p_i, comm];
+                                           reward = -Hausdorff(agents - mean, goals - mean) - 2 per agent collision
+                                           (s1+s2) - 2 per obstacle collision; the reward hook's side effect sets every
+                                           obstacle's velocity to (0, obstacle_fall_vy) above obstacle_floor, else 0 */
 
 /* core.Wall (formation_gym/core.py:27-41) */
 typedef struct fg_wall {
@@ -80,6 +89,10 @@ typedef struct fg_params {
     double u_noise;            /* core.py:97  0 = off (None) */
     double c_noise;            /* core.py:99  0 = off (None) */
     double obs_range;          /* FG_SCENARIO_HD_PARTIAL_RANGE: Scenario.obs_range (formation_hd_partial_range_env.py:15) */
+    double obstacle_size;      /* FG_SCENARIO_HD_OBSTACLE: 0.15 (formation_hd_obs_env.py:44) */
+    double obstacle_mass;      /* Entity.initial_mass 1.0 (core.py:69) */
+    double obstacle_floor;     /* -2.2 (formation_hd_obs_env.py:86) */
+    double obstacle_fall_vy;   /* -1.0 (formation_hd_obs_env.py:87) */
     int32_t has_accel;
     int32_t has_max_speed;
     int32_t collide;           /* agents collide (formation_hd_env.py:24) */
@@ -89,6 +102,8 @@ typedef struct fg_params {
     int32_t action_prescaled;  /* 1: `act` already is agent.action.u (after _set_action), i.e. World.step()
                                   called on its own (core.py:206); the sensitivity multiply is skipped */
     int32_t num_obs;           /* FG_SCENARIO_HD_PARTIAL: Scenario.num_obs (formation_hd_partial_env.py:15) */
+    int32_t num_obstacles;     /* FG_SCENARIO_HD_OBSTACLE: Scenario.num_obstacles (formation_hd_obs_env.py:14); the
+                                  entry points' L counts goal landmarks + obstacles */
     /* optional per-agent DEVICE arrays [N] in the entry point's real type; NULL = scalar above.
        agent_accel / agent_max_speed entries < 0 mean "None" for that agent. */
     const void* agent_mass;
@@ -119,6 +134,8 @@ typedef struct fg_buffers {
     int32_t* ep_collisions;    /* (opt) [E] in/out running count of reward-collisions */
     double* stats;             /* (opt) [4] in/out: n_episodes, sum return, sum return^2,
                                   sum collisions -- updated atomically at episode ends */
+    void* landmark_vel;        /* FG_SCENARIO_HD_OBSTACLE: (opt) [E,L,2] in/out landmark.state.p_vel; only the obstacle
+                                  entries are read and written (NULL: obstacles start the step at rest) */
     uint32_t* tick_dev;        /* (opt) [2] in/out, zero-initialised by the caller: [0] is ADDED to the
                                   `tick` argument of every entry point; fg_world_step / fg_step_fused
                                   advance it by the number of env steps they ran ([1] is their arrival

@@ -9,6 +9,7 @@ relative to /root/reference):
   * basic scenario ``observation/reward/reset_world``   formation_gym/envs/basic_formation_env.py:29-65,89-91
   * partial-observation scenarios                       formation_gym/envs/formation_hd_partial_env.py:41-125,
                                                         formation_gym/envs/formation_hd_partial_range_env.py:41-113
+  * obstacle scenario (movable colliding landmarks)     formation_gym/envs/formation_hd_obs_env.py:14-149
 
 Third-party arithmetic restated here (the reference pins no versions --
 ``setup.py:4-17`` has no install_requires; this container has numpy 2.3.5 / scipy 1.18.1):
@@ -360,6 +361,140 @@ def partial_env_step(pos, vel, act, landmarks, step, num_obs=None, obs_range=Non
     new_step = np.asarray(step) + 1
     return dict(pos=p, vel=v, obs=obs, indiv=indiv, reward=shared_reward(indiv),
                 done=new_step >= prm.world_length, step=new_step)
+
+
+# ------------------------------------------------------------------------------------------
+# formation_hd_obs_env: movable colliding obstacle landmarks
+# ------------------------------------------------------------------------------------------
+OBSTACLE_PARAMS = WorldParams(agent_size=0.1, world_length=50)    # formation_hd_obs_env.py:14,29
+OBSTACLE_SIZE = 0.15                                               # formation_hd_obs_env.py:44
+OBSTACLE_FLOOR = -2.2                                              # formation_hd_obs_env.py:86
+
+
+def obstacle_world_step(pos, vel, act, obst, obst_vel, prm=OBSTACLE_PARAMS, obstacle_size=OBSTACLE_SIZE,
+                        obstacle_mass=1.0, noise=None):
+    """``World.step`` with movable colliding landmarks (core.py:206-277): the entity list is agents,
+    goal landmarks, obstacles (core.py:143-144, formation_hd_obs_env.py:31-44); goal landmarks do not collide
+    (core.py:292) and drop out.  Pairs a<b over [agents, obstacles]: agent-agent, agent-obstacle,
+    obstacle-obstacle, all "both movable" (core.py:314-318).  Obstacles get no action force, are damped and
+    integrated like agents (core.py:264-277), never speed-clamped (max_speed None).
+    Returns new (pos, vel, obst, obst_vel)."""
+    pos = np.asarray(pos, np.float64); vel = np.asarray(vel, np.float64); act = np.asarray(act, np.float64)
+    obst = np.asarray(obst, np.float64); obst_vel = np.asarray(obst_vel, np.float64)
+    E, N, _ = pos.shape
+    O = obst.shape[1]
+    mass, size, accel, vmax = prm.per_agent(N)
+    sens = np.full(N, prm.sensitivity) if accel is None else accel
+    gain = mass if accel is None else mass * accel
+    F = np.array(gain[None, :, None] * (act * sens[None, :, None]) + (0.0 if noise is None else noise), np.float64)
+    P = np.concatenate([pos, obst], 1)
+    Fall = np.concatenate([F, np.zeros((E, O, 2))], 1)            # p_force[b] = 0.0 before the first add (:252-253)
+    esize = np.concatenate([size, np.full(O, obstacle_size)])
+    emass = np.concatenate([mass, np.full(O, obstacle_mass)])
+    agents_collide = [prm.collide] * N + [True] * O
+    k = prm.contact_margin
+    with np.errstate(all='ignore'):
+        for a in range(N + O):
+            for b in range(a + 1, N + O):
+                if not (agents_collide[a] and agents_collide[b]):
+                    continue
+                delta = P[:, a] - P[:, b]
+                dist = norm2(delta[:, 0], delta[:, 1])
+                dist_min = esize[a] + esize[b]
+                pen = np.logaddexp(0, -(dist - dist_min) / k) * k
+                force = prm.contact_force * delta / dist[:, None] * pen[:, None]
+                ratio = emass[b] / emass[a]
+                Fall[:, a] = ratio * force + Fall[:, a]
+                Fall[:, b] = -(1 / ratio) * force + Fall[:, b]
+    for w in prm.walls:                                            # every movable entity (core.py:255-261)
+        for a in range(N + O):
+            Fall[:, a] = Fall[:, a] + wall_force(P[:, a], esize[a], w, prm)
+    V = np.concatenate([vel, obst_vel], 1) * (1 - prm.damping)
+    V = V + (Fall / emass[None, :, None]) * prm.dt
+    if vmax is not None:
+        va = V[:, :N]
+        sp = np.sqrt(np.square(va[..., 0]) + np.square(va[..., 1]))
+        with np.errstate(all='ignore'):
+            clamped = va / sp[..., None] * vmax[None, :, None]
+        V[:, :N] = np.where((sp > vmax[None, :])[..., None], clamped, va)
+    P = P + V * prm.dt
+    return P[:, :N], V[:, :N], P[:, N:], V[:, N:]
+
+
+def obstacle_observation(pos, vel, goals, obst):
+    """formation_hd_obs_env.py:53-68: [v_i, goal landmark positions (absolute), obstacle positions - p_i,
+    p_j - p_i (j != i), comm of the others (zeros)]."""
+    E, N, _ = pos.shape
+    L, O = goals.shape[1], obst.shape[1]
+    D = 2 + 2 * L + 2 * O + 4 * (N - 1)
+    obs = np.zeros((E, N, D), np.float64)
+    for i in range(N):
+        obs[:, i, 0:2] = vel[:, i]
+        obs[:, i, 2:2 + 2 * L] = goals.reshape(E, 2 * L)
+        obs[:, i, 2 + 2 * L:2 + 2 * L + 2 * O] = (obst - pos[:, i:i + 1]).reshape(E, 2 * O)
+        others = [j for j in range(N) if j != i]
+        b = 2 + 2 * L + 2 * O
+        obs[:, i, b:b + 2 * (N - 1)] = (pos[:, others] - pos[:, i:i + 1]).reshape(E, 2 * (N - 1))
+    return obs
+
+
+def obstacle_reward(pos, goals, obst, prm=OBSTACLE_PARAMS, obstacle_size=OBSTACLE_SIZE):
+    """formation_hd_obs_env.py:70-99,147-149: -max(dH(u, v), dH(v, u)) with u = agents - mean, v = goal
+    landmarks - mean; -2 per other agent closer than s_a + s_i; -2 per obstacle closer than s_o + s_i."""
+    E, N, _ = pos.shape
+    _, size, _, _ = prm.per_agent(N)
+    u = pos - np.mean(pos, 1)[:, None, :]
+    v = goals - np.mean(goals, 1)[:, None, :]
+    base = -np.sqrt(np.maximum(directed_hausdorff_sq(u, v), directed_hausdorff_sq(v, u)))
+    rew = np.repeat(base[:, None], N, 1)
+    if prm.collide:
+        for i in range(N):
+            r = rew[:, i].copy()
+            for j in range(N):
+                if j == i:
+                    continue
+                d = pos[:, j] - pos[:, i]
+                r = np.where(norm2(d[:, 0], d[:, 1]) < (size[i] + size[j]), r - 2, r)
+            for kk in range(obst.shape[1]):
+                d = obst[:, kk] - pos[:, i]
+                r = np.where(norm2(d[:, 0], d[:, 1]) < (obstacle_size + size[i]), r - 2, r)
+            rew[:, i] = r
+    return rew
+
+
+def obstacle_velocity_rule(obst):
+    """Side effect of every ``reward`` call (formation_hd_obs_env.py:85-88): an obstacle above the floor falls at
+    (0, -1), below it stops."""
+    v = np.zeros_like(obst)
+    v[..., 1] = np.where(obst[..., 1] > OBSTACLE_FLOOR, -1.0, 0.0)
+    return v
+
+
+def obstacle_env_step(pos, vel, act, goals, obst, obst_vel, step, prm=OBSTACLE_PARAMS,
+                      obstacle_size=OBSTACLE_SIZE, noise=None):
+    """env.step for formation_hd_obs_env (environment.py:113-142 over the hooks above)."""
+    p, v, o, ov = obstacle_world_step(pos, vel, act, obst, obst_vel, prm, obstacle_size, 1.0, noise)
+    obs = obstacle_observation(p, v, np.asarray(goals, np.float64), o)
+    indiv = obstacle_reward(p, np.asarray(goals, np.float64), o, prm, obstacle_size)
+    new_step = np.asarray(step) + 1
+    return dict(pos=p, vel=v, obst=o, obst_vel=obstacle_velocity_rule(o), obst_vel_integrated=ov, obs=obs,
+                indiv=indiv, reward=shared_reward(indiv), done=new_step >= prm.world_length, step=new_step)
+
+
+def obstacle_reset_from_uniform(u_pos, u_goals, u_obst):
+    """formation_hd_obs_env.py:101-120 from U(0,1) draws ``u_obst`` [E,O,2] and U(-1,1) draws for agents and
+    goal landmarks: obstacle k starts at x ~ U(step[k], step[k+1]), step = linspace(-1.8, 1.8, O+1),
+    y ~ U(2.0, 2.5), velocity (0, -1)."""
+    u_obst = np.asarray(u_obst, np.float64)
+    O = u_obst.shape[1]
+    st = np.linspace(-1.8, 1.8, O + 1)
+    obst = np.empty_like(u_obst)
+    obst[..., 0] = st[:-1][None, :] + (st[1:] - st[:-1])[None, :] * u_obst[..., 0]
+    obst[..., 1] = 2.0 + 0.5 * u_obst[..., 1]
+    ov = np.zeros_like(obst)
+    ov[..., 1] = -1.0
+    pos = np.array(u_pos, np.float64)
+    return pos, np.zeros_like(pos), np.array(u_goals, np.float64), obst, ov
 
 
 # ------------------------------------------------------------------------------------------

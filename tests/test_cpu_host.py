@@ -38,7 +38,7 @@ def test_library_exports_every_declared_symbol():
     for s in syms:
         assert hasattr(lib, s), "missing export %s" % s
     assert sorted(_native.EXPORTS) == syms          # the binding covers exactly the header
-    assert _native.load().fg_abi_version() == _native.FG_ABI_VERSION == 4
+    assert _native.load().fg_abi_version() == _native.FG_ABI_VERSION == 5
 
 
 def test_ctypes_structs_match_c_layout():
@@ -121,7 +121,10 @@ def test_api_contract_static(scenario, n):
 def test_make_env_rejects_unknown_scenarios_and_small_hd():
     import formation_gym
     with pytest.raises(ValueError):
-        formation_gym.make_env("formation_hd_obs_env", False, 9)
+        formation_gym.make_env("simple_spread", False, 9)
+    env = formation_gym.make_env("formation_hd_obs_env", False, 4)      # host construction needs no device
+    assert len(env.world.landmarks) == 7 and env.observation_space[0].shape == (2 + 2 * 7 + 4 * 3,)
+    assert [l.movable and l.collide for l in env.world.landmarks] == [False] * 4 + [True] * 3
     with pytest.raises(Exception):
         formation_gym.make_env("formation_hd_env", False, 2)      # formation_hd_env.py:58 needs N >= 3
 

@@ -1,0 +1,157 @@
+"""formation_hd_obs_env (movable colliding obstacle landmarks) on the CUDA path, against
+fixtures frozen from the unmodified reference (tests/golden/obstacle_*.npz) and the numpy oracle."""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+import formation_gym  # noqa: E402
+from formation_gym.batched import BatchedFormationEnv  # noqa: E402
+from oracle import mpe_oracle as mo  # noqa: E402
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+FILES = sorted(glob.glob(os.path.join(GOLD, "obstacle_n*.npz")))
+SCN = "formation_hd_obs_env"
+
+
+def _dev(dtype):
+    return lambda x: torch.as_tensor(np.ascontiguousarray(x), dtype=dtype, device="cuda")
+
+
+def _err(a, b):
+    return float(np.abs(a.double().cpu().numpy() - b).max())
+
+
+def _load(env, dev, pos, vel, goals, obst, obst_vel, step0):
+    G = env.num_goals
+    env.pos.copy_(dev(pos)); env.vel.copy_(dev(vel))
+    env.landmarks[:, :G].copy_(dev(goals)); env.landmarks[:, G:].copy_(dev(obst))
+    env.landmark_vel.zero_(); env.landmark_vel[:, G:].copy_(dev(obst_vel))
+    env.step_count.copy_(torch.as_tensor(step0, dtype=torch.int32, device="cuda"))
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64], ids=["f32", "f64"])
+@pytest.mark.parametrize("path", FILES, ids=[os.path.basename(f) for f in FILES])
+def test_obstacle_single_step_golden(path, dtype):
+    g = np.load(path)
+    E, N = g["pos0"].shape[:2]
+    G, O = g["goals"].shape[1], g["obst0"].shape[1]
+    env = BatchedFormationEnv(SCN, E, N, episode_length=50, num_landmarks=G, num_obstacles=O, dtype=dtype,
+                              auto_reset=False)
+    dev = _dev(dtype)
+    _load(env, dev, g["pos0"], g["vel0"], g["goals"], g["obst0"], g["obst_vel0"], g["step0"])
+    obs, rew, done, info = env.step(dev(g["act"]))
+    tol = 1e-5 if dtype == torch.float32 else 1e-12
+    assert obs.shape[2] == g["obs"].shape[2]
+    assert _err(env.pos, g["pos"]) <= tol and _err(env.vel, g["vel"]) <= tol
+    assert _err(env.landmarks[:, G:], g["obst"]) <= tol and _err(env.landmarks[:, :G], g["goals"]) == 0.0
+    assert _err(env.landmark_vel[:, G:], g["obst_vel"]) == 0.0          # the reward hook's rule: exact values
+    assert _err(obs, g["obs"]) <= tol
+    assert _err(info["individual_reward"], g["indiv"]) <= tol * (1 if dtype == torch.float32 else 10)
+    assert _err(rew[:, :, 0], g["reward"]) <= tol * (8 if dtype == torch.float32 else 100)
+    assert np.array_equal(done.cpu().numpy(), g["done"])
+    # observation + reward alone (fg_obs_reward) from the stepped state gives the same rows
+    obs2 = env.observe().clone()
+    assert torch.equal(obs2, obs)
+
+
+def test_obstacle_trajectory_fp64():
+    """50 steps from the reference's seeded reset; the obstacles fall through the agents (contacts)."""
+    g = np.load(os.path.join(GOLD, "obstacle_traj50.npz"))
+    T, N = g["act"].shape[:2]
+    G, O = g["goals"].shape[0], g["obst0"].shape[0]
+    for dtype, tol in ((torch.float64, 1e-9), (torch.float32, 2e-4)):
+        env = BatchedFormationEnv(SCN, 1, N, episode_length=50, num_landmarks=G, num_obstacles=O, dtype=dtype,
+                                  auto_reset=False)
+        dev = _dev(dtype)
+        _load(env, dev, g["pos0"][None], np.zeros((1, N, 2)), g["goals"][None], g["obst0"][None],
+              g["obst_vel0"][None], np.zeros(1))
+        assert _err(env.observe()[0], g["obs0"]) <= (1e-12 if dtype == torch.float64 else 1e-6)
+        worst = 0.0
+        for t in range(T):
+            obs, rew, done, info = env.step(dev(g["act"][t][None]))
+            worst = max(worst, _err(env.pos[0], g["pos"][t]), _err(env.landmarks[0, G:], g["obst"][t]),
+                        _err(obs[0], g["obs"][t]))
+            if dtype == torch.float64:
+                assert _err(info["individual_reward"][0], g["indiv"][t]) <= 1e-9
+            assert _err(env.landmark_vel[0, G:], g["obst_vel"][t]) == 0.0
+        assert worst <= tol, worst
+        assert bool(done.all())
+
+
+@pytest.mark.parametrize("E,N,G,O", [(300, 4, 4, 3), (33, 40, 7, 5), (5, 243, 9, 4), (64, 9, 1, 1), (7, 256, 256 - 8, 8)])
+def test_obstacle_vs_oracle_random(E, N, G, O):
+    rng = np.random.default_rng(N * 17 + O)
+    f32 = lambda x: x.astype(np.float32).astype(np.float64)  # noqa: E731
+    pos = f32(rng.uniform(-0.7, 0.7, (E, N, 2))); vel = f32(rng.uniform(-0.5, 0.5, (E, N, 2)))
+    act = f32(rng.uniform(-1, 1, (E, N, 2))); goals = f32(rng.uniform(-1, 1, (E, G, 2)))
+    obst = f32(rng.uniform(-0.9, 0.9, (E, O, 2))); ov = f32(rng.uniform(-1, 1, (E, O, 2)))
+    obst[::3, :, 1] -= 2.6
+    step0 = rng.integers(0, 50, E)
+    ref = mo.obstacle_env_step(pos, vel, act, goals, obst, ov, step0)
+    for dtype, tol in ((torch.float32, 2e-5), (torch.float64, 1e-11)):
+        env = BatchedFormationEnv(SCN, E, N, episode_length=50, num_landmarks=G, num_obstacles=O, dtype=dtype,
+                                  auto_reset=False)
+        dev = _dev(dtype)
+        _load(env, dev, pos, vel, goals, obst, ov, step0)
+        obs, rew, done, info = env.step(dev(act))
+        assert _err(env.pos, ref["pos"]) <= tol and _err(env.vel, ref["vel"]) <= tol * 10
+        assert _err(env.landmarks[:, G:], ref["obst"]) <= tol
+        assert _err(env.landmark_vel[:, G:], ref["obst_vel"]) == 0.0
+        assert _err(obs, ref["obs"]) <= tol * 10
+        assert _err(info["individual_reward"], ref["indiv"]) <= tol * (1 if dtype == torch.float32 else 10)
+        R = ref["reward"]
+        assert np.all(np.abs(rew[:, 0, 0].double().cpu().numpy() - R) <= tol + 1e-6 * np.abs(R))
+        assert np.array_equal(done[:, 0].cpu().numpy(), ref["done"])
+
+
+def test_obstacle_reset_rollout_and_facade():
+    """Device reset distribution (formation_hd_obs_env.py:101-120), in-kernel rollout == stepwise, auto-reset,
+    and the single-env facade through the reference API against the frozen reference trajectory."""
+    env = BatchedFormationEnv(SCN, 4096, 4, episode_length=5, seed=3)
+    env.reset()
+    G, O = env.num_goals, env.num_obstacles
+    ob = env.landmarks[:, G:].cpu().numpy()
+    edges = np.linspace(-1.8, 1.8, O + 1)
+    for k in range(O):
+        assert ob[:, k, 0].min() >= edges[k] and ob[:, k, 0].max() <= edges[k + 1]
+        assert abs(ob[:, k, 0].mean() - 0.5 * (edges[k] + edges[k + 1])) < 0.03
+    assert ob[..., 1].min() >= 2.0 and ob[..., 1].max() <= 2.5
+    ov = env.landmark_vel[:, G:].cpu().numpy()
+    assert np.all(ov[..., 0] == 0.0) and np.all(ov[..., 1] == -1.0)
+    assert float(env.landmarks[:, :G].abs().max()) <= 1.0 and float(env.pos.abs().max()) <= 1.0
+    # stepwise random policy == one in-kernel rollout (same Philox stream), across an auto-reset
+    sd = env.state_dict()
+    for _ in range(7):
+        obs_a, rew_a, done_a, _ = env.step_random()
+    fin = {k: getattr(env, k).clone() for k in ("pos", "vel", "landmarks", "landmark_vel", "step_count")}
+    obs_a = obs_a.clone()
+    env.load_state_dict(sd)
+    obs_b, rew_b, done_b, _ = env.rollout_random(7)
+    for k, v in fin.items():
+        assert torch.equal(getattr(env, k), v), k
+    assert torch.equal(obs_a, obs_b)
+    assert int(env.step_count[0]) == 2                                  # 7 steps, episodes of 5
+    # facade: reference API, trajectory frozen from the unmodified reference
+    g = np.load(os.path.join(GOLD, "obstacle_traj50.npz"))
+    fenv = formation_gym.make_env(SCN, False, 4)
+    assert fenv.world_length == 50 and len(fenv.world.landmarks) == 7
+    np.random.seed(7)
+    obs_n = fenv.reset()
+    assert np.abs(np.stack(obs_n) - g["obs0"]).max() <= 1e-12
+    for t in range(6):
+        obs_n, reward_n, done_n, info_n = fenv.step([a.copy() for a in g["act"][t]])
+        assert np.abs(np.stack(obs_n) - g["obs"][t]).max() <= 1e-9
+        assert abs(reward_n[0][0] - g["reward"][t][0]) <= 1e-9 and reward_n[0] is reward_n[1]
+        lm = np.stack([l.state.p_pos for l in fenv.world.landmarks])
+        assert np.abs(lm[4:] - g["obst"][t]).max() <= 1e-9
+        lv = np.stack([l.state.p_vel for l in fenv.world.landmarks[4:]])
+        assert np.array_equal(lv, g["obst_vel"][t])
+    # the hooks alone (observation / reward from the host state), like user code calling them
+    sc = fenv.reward_callback.__self__
+    r0 = sc.reward(fenv.world.agents[0], fenv.world)
+    assert abs(r0 - g["indiv"][5][0]) <= 1e-9
