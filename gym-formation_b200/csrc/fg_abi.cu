@@ -122,6 +122,19 @@ int fill_args(fg::KArgs<T>& a, const fg_params* p, const fg_buffers* b, int scen
         const char* force = getenv("FG_FORCE_FAST_PAIRS");
         a.fast_pairs = N >= 32 && (!b->obs || N >= 128 || (force && force[0] == '1')) && !(slow && slow[0] == '1');
     }
+    {
+        // hashed cell lists of the packed pair loops (fg_pairs.cuh): buckets per env = largest power of two
+        // <= 4 * roundup(N, 32); cell edge = 2 * search radius * (1 + 2^-9)
+        const char* off = getenv("FG_NO_CELLS");                       // A/B switch for tests and profiling
+        const int NP = (N + 31) & ~31;
+        int logb = 0;
+        while ((2 << logb) <= 4 * NP) ++logb;
+        a.cell_shift = 32 - logb;
+        a.cells = a.fast_pairs && p->collide && !(off && off[0] == '1');
+        a.cell_inv_old = (float)(1.0 / (2.0 * std::sqrt((double)a.cut2) * (1.0 + 1.0 / 512.0)));
+        a.cell_inv_new = (float)(1.0 / (2.0 * std::sqrt((double)a.rthr2_hi) * (1.0 + 1.0 / 512.0)));
+        a.cell_off = 0;
+    }
     a.row_tma = scenario == FG_SCENARIO_HD && p->silent && a.IPR >= 144 && b->obs &&
                 ((uintptr_t)b->obs % sizeof(R2)) == 0;
     {
@@ -163,13 +176,25 @@ size_t fast_pairs_bytes(const fg::KArgs<T>& a) {
 template <typename T, int SCN, bool PHYS, bool OBSREW, bool HET, int OM, bool FP>
 int launch_one(const fg::KArgs<T>& a, size_t smem, cudaStream_t st) {
     const int grid = (a.E + a.EPC - 1) / a.EPC;
-    if (FP) smem += fast_pairs_bytes(a);
+    fg::KArgs<T> b = a;
+    if (FP) {
+        smem += fast_pairs_bytes(a);
+        if (a.cells) {                      // chain nodes [2][EPC][NP] x 16 B, bucket heads [2][EPC][CB], flags [2][EPC]
+            smem = (smem + 15) & ~(size_t)15;
+            b.cell_off = (unsigned)smem;
+            const size_t NP = ((size_t)a.N + 31) & ~(size_t)31, CB = (size_t)1 << (32 - a.cell_shift);
+            smem += 2 * (size_t)a.EPC * CB * sizeof(int) + 2 * (size_t)a.EPC * NP * 16 + 2 * (size_t)a.EPC * sizeof(int);
+            smem = (smem + 15) & ~(size_t)15;
+        }
+    } else {
+        b.cells = 0;
+    }
     if (smem > 48 * 1024) {
         cudaError_t e1 = cudaFuncSetAttribute(fg::k_step<T, SCN, PHYS, OBSREW, HET, OM, FP>,
                                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e1 != cudaSuccess) return fail(FG_ERR_CUDA, "cudaFuncSetAttribute failed: %s", cudaGetErrorString(e1));
     }
-    fg::k_step<T, SCN, PHYS, OBSREW, HET, OM, FP><<<grid, fg::kBlock, smem, st>>>(a);
+    fg::k_step<T, SCN, PHYS, OBSREW, HET, OM, FP><<<grid, fg::kBlock, smem, st>>>(b);
     cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess) return fail(FG_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(err));
     return FG_OK;

@@ -58,6 +58,10 @@ template <typename T> struct KArgs {
     int row_early;                   // OM == 2, fp32, odd N, 16-byte aligned obs: rows leave as aligned bulk pieces, the
                                      // static 2/3 before the physics and the dynamic 1/3 before the reward pass
     int fast_pairs;                  // tile kernel: packed pair loops of fg_pairs.cuh (N >= 32; fp32 hd uniform only)
+    int cells;                       // fast pairs: near partners from hashed cell lists instead of the O(N^2) filters
+    int cell_shift;                  // 32 - log2(buckets per env)
+    unsigned cell_off;               // byte offset of the cell-list region in dynamic shared memory
+    float cell_inv_old, cell_inv_new;   // 1 / cell edge: contact cut-off (old positions), reward collision (new)
     R2* lmv;                         // obstacle scenario: landmark velocities [E,L,2] (obstacle entries used)
     int n_obst;                      // obstacle scenario: the last n_obst landmarks are movable colliding obstacles
     T osize, omass, ofloor, ofall;   // obstacle size / mass, floor y and fall velocity of the reward hook's rule
@@ -186,10 +190,15 @@ __global__ void __launch_bounds__(kBlock, (OM == 2 || FP) ? 4 : 3) k_step(const 
     const int NP = (N + 31) & ~31;
     const int NB = a.row_nbuf;
     float* f_base = reinterpret_cast<float*>(s_rt_dyn + (OM == 2 ? NB * rt_dyn * (kBlock / 32) : 0));
-    float* f_xo = f_base;              float* f_yo = f_xo + EPC * NP;   float* f_no = f_yo + EPC * NP;
-    float* f_cx = f_no + EPC * NP;     float* f_cy = f_cx + EPC * NP;   float* f_nc = f_cy + EPC * NP;
-    float* f_sx = f_nc + EPC * NP;     float* f_sy = f_sx + EPC * NP;
-    float* f_part = f_sy + EPC * NP;                  // [EPC][8 warps][4]: partial sums of pos.xy, vel.xy
+    // Partner data as RECORDS of four partners (one address register + immediate offsets in the pair loops):
+    // f_ro [EPC][NP/4] x {x[4], y[4], |p|^2[4]} of the old positions (contact filter),
+    // f_rn [EPC][NP/4] x {cx[4], cy[4], |c|^2[4], sx[4], sy[4]} centred new positions and centred ideal shape.
+    float* f_ro = f_base;
+    float* f_rn = f_ro + 3 * EPC * NP;
+    float* f_part = f_rn + 5 * EPC * NP;              // [EPC][8 warps][4]: partial sums of pos.xy, vel.xy
+    const int NG = NP >> 2;                           // records per env
+    auto RO = [&](int e_, int i_, int c_) -> float& { return f_ro[((e_ * NG + (i_ >> 2)) * 3 + c_) * 4 + (i_ & 3)]; };
+    auto RN = [&](int e_, int i_, int c_) -> float& { return f_rn[((e_ * NG + (i_ >> 2)) * 5 + c_) * 4 + (i_ & 3)]; };
     R2* s_old = reinterpret_cast<R2*>(f_base + (FP ? 8 * EPC * NP + EPC * 32 : 0));   // positions the contact force reads
     R2* s_new = s_old + nA;                           // positions after integration
     R2* s_v = s_new + nA;                             // velocities after integration
@@ -205,6 +214,12 @@ __global__ void __launch_bounds__(kBlock, (OM == 2 || FP) ? 4 : 3) k_step(const 
     int* s_dn = s_col + EPC;                                  // episode-end flag per local env
     int* s_bad = s_dn + EPC;                                  // env has a non-finite position (NaN quirk, Q9)
     unsigned* s_nmax = reinterpret_cast<unsigned*>(s_bad + EPC);   // FP: [2][EPC] max |p|^2 bits (old, centred new)
+    // FP + cells: two hashed cell lists per env (old positions: contact cut-off; new positions: reward collision):
+    // bucket heads [2][EPC][CB], chain links [2][EPC][NP], "env has a far / non-finite agent" flags [2][EPC]
+    const int CB = 1 << (32 - a.cell_shift);
+    float4* c_node = reinterpret_cast<float4*>(smem_raw + a.cell_off);       // [2][EPC][NP] chain nodes {x, y, next}
+    int* c_head = reinterpret_cast<int*>(c_node + 2 * EPC * NP);             // [2][EPC][CB] bucket heads
+    int* c_far = c_head + 2 * EPC * CB;                                      // [2][EPC]
     __shared__ double s_stat[4];                              // episode statistics of this CTA's envs
     if (threadIdx.x < 4) s_stat[threadIdx.x] = 0.0;
 
@@ -236,10 +251,11 @@ __global__ void __launch_bounds__(kBlock, (OM == 2 || FP) ? 4 : 3) k_step(const 
     if (FP) {
         // neutral pad entries (never a candidate, never a minimum); the live entries are written below
         for (int q = t; q < EPC * NP; q += kBlock) {
-            if (q - (q / NP) * NP >= N) {
-                f_xo[q] = 0.f; f_yo[q] = 0.f; f_no[q] = INFINITY;
-                f_cx[q] = 1e18f; f_cy[q] = 1e18f; f_nc[q] = INFINITY;
-                f_sx[q] = 1e18f; f_sy[q] = 1e18f;
+            const int qe = q / NP, qi = q - qe * NP;
+            if (qi >= N) {
+                RO(qe, qi, 0) = 0.f; RO(qe, qi, 1) = 0.f; RO(qe, qi, 2) = INFINITY;
+                RN(qe, qi, 0) = 1e18f; RN(qe, qi, 1) = 1e18f; RN(qe, qi, 2) = INFINITY;
+                RN(qe, qi, 3) = 1e18f; RN(qe, qi, 4) = 1e18f;
             }
         }
         if (t < 2 * EPC) s_nmax[t] = 0u;
@@ -261,7 +277,7 @@ __global__ void __launch_bounds__(kBlock, (OM == 2 || FP) ? 4 : 3) k_step(const 
             if (SCN == kScnHD) {
                 const R2 S0 = a.shape[g];
                 s_s[t] = S0;
-                if constexpr (FP) { f_sx[le * NP + i] = (float)S0.x; f_sy[le * NP + i] = (float)S0.y; }
+                if constexpr (FP) { RN(le, i, 3) = (float)S0.x; RN(le, i, 4) = (float)S0.y; }
                 if constexpr (OM == 2) {
                     if (a.row_early) {        // static row images [comm zeros (N-1) | ideal_shape (N) | ideal_vel], both phases
                         R2* im0 = s_rt_img + (size_t)le * 2 * rt_img;
@@ -311,9 +327,12 @@ __global__ void __launch_bounds__(kBlock, (OM == 2 || FP) ? 4 : 3) k_step(const 
         if (OBSREW && t < EPC) { s_rowmax[t] = 0; s_col[t] = 0; s_bad[t] = 0; if (FP) s_nmax[EPC + t] = 0u; }
         float n_old = 0.f;
         if constexpr (FP) {
-            if (PHYS) {                                         // partner arrays of the contact filter
+            if (a.cells) {
+                for (int q = t; q < 2 * EPC * CB; q += kBlock) c_head[q] = -1;
+                if (t < 2 * EPC) c_far[t] = 0;
+            } else if (PHYS) {                                  // partner arrays of the contact filter
                 n_old = (float)p.x * (float)p.x + (float)p.y * (float)p.y;
-                if (active) { f_xo[le * NP + i] = (float)p.x; f_yo[le * NP + i] = (float)p.y; f_no[le * NP + i] = n_old; }
+                if (active) { RO(le, i, 0) = (float)p.x; RO(le, i, 1) = (float)p.y; RO(le, i, 2) = n_old; }
                 env_atomic_max(s_nmax, __float_as_uint(n_old));
             }
             if (t < EPC * 32) f_part[t] = 0.f;
@@ -336,6 +355,14 @@ __global__ void __launch_bounds__(kBlock, (OM == 2 || FP) ? 4 : 3) k_step(const 
             __syncthreads();
         }
 
+        CellPos cpos = {0, 0, 1, 1};                                        // FP + cells: my cell (old positions)
+        if constexpr (FP && PHYS) {
+            if (a.cells && a.collide) {
+                if (active) cpos = cell_insert((float)p.x, (float)p.y, a.cell_inv_old, a.cell_shift, c_head + le * CB,
+                                               c_node + le * NP, i, &c_far[le]);
+                __syncthreads();
+            }
+        }
         // =============================== World.step (core.py:206-225) ===========================
         if (PHYS) {
             if (active) {
@@ -365,9 +392,18 @@ __global__ void __launch_bounds__(kBlock, (OM == 2 || FP) ? 4 : 3) k_step(const 
                         // candidate groups of four partners from the packed filter, then the reference's exact
                         // test and force for the members of flagged groups, in ascending j
                         const T dmin = O::add(a.size, a.size);                  // core.py:307
-                        const float thr = ((float)a.cut2 - n_old) + filter_margin(n_old, __uint_as_float(s_nmax[le]));
-                        u64 near = filter_groups(f_xo + le * NP, f_yo + le * NP, f_no + le * NP, NP >> 2,
+                        u64 near;
+                        if (a.cells) {
+                            // true near partners (exact cut-off test on the spot) from the 3 x 3 cells around me;
+                            // an env with a far or non-finite agent falls back to testing every group
+                            if (c_far[le]) near = (NP == 256) ? ~0ull : ((1ull << (NP >> 2)) - 1ull);
+                            else near = cell_near_groups(c_head + le * CB, c_node + le * NP, a.cell_shift, cpos,
+                                                         (float)p.x, (float)p.y, (float)a.cut2, i);
+                        } else {
+                            const float thr = ((float)a.cut2 - n_old) + filter_margin(n_old, __uint_as_float(s_nmax[le]));
+                            near = filter_groups(reinterpret_cast<const ulonglong2*>(f_ro) + le * NG * 3, NG,
                                                  (float)p.x, (float)p.y, thr);
+                        }
                         // Two phases keep the warp converged on the expensive part: (1) cheap exact cut-off test
                         // of the members of flagged groups, true near partners appended (ascending j) to a
                         // register list of up to 8 byte-sized indices; (2) the softplus force for the listed
@@ -593,6 +629,9 @@ __global__ void __launch_bounds__(kBlock, (OM == 2 || FP) ? 4 : 3) k_step(const 
             // a non-finite position makes the centroid, hence the whole shape term, NaN (Q9)
             if (active && (!(fabs(p.x) < (T)INFINITY) || !(fabs(p.y) < (T)INFINITY))) s_bad[le] = 1;
             if constexpr (FP) {
+                if (a.cells && a.collide && active)                          // cell list of the NEW positions
+                    cpos = cell_insert((float)p.x, (float)p.y, a.cell_inv_new, a.cell_shift, c_head + (EPC + le) * CB,
+                                       c_node + (EPC + le) * NP, i, &c_far[EPC + le]);
                 // centroid and mean velocity (formation_hd_env.py:65,68): butterfly sums over the lanes of
                 // each env in the warp, one partial per (env, warp), combined in warp order after the barrier
                 if (PHYS && t < EPC) s_nmax[t] = 0u;                         // re-arm for the next rollout step
@@ -637,7 +676,7 @@ __global__ void __launch_bounds__(kBlock, (OM == 2 || FP) ? 4 : 3) k_step(const 
                 mvx = svx / (float)N; mvy = svy / (float)N;
                 fcx = (float)p.x - sx / (float)N; fcy = (float)p.y - sy / (float)N;   // centred agent shape
                 fnc = fcx * fcx + fcy * fcy;
-                if (active) { f_cx[le * NP + i] = fcx; f_cy[le * NP + i] = fcy; f_nc[le * NP + i] = fnc; }
+                if (active) { RN(le, i, 0) = fcx; RN(le, i, 1) = fcy; RN(le, i, 2) = fnc; }
                 env_atomic_max(s_nmax + EPC, __float_as_uint(fnc));
             } else if (active) {
                 const R2 mp = s_mean[2 * le], mv = s_mean[2 * le + 1];
@@ -655,8 +694,25 @@ __global__ void __launch_bounds__(kBlock, (OM == 2 || FP) ? 4 : 3) k_step(const 
                 const R2 Si = s_s[t];
                 const float thr = ((float)a.rthr2_hi - fnc) + filter_margin(fnc, __uint_as_float(s_nmax[EPC + le]));
                 float rowmin, colmin;
-                u64 hit = reward_pass(f_cx + le * NP, f_cy + le * NP, f_nc + le * NP, f_sx + le * NP, f_sy + le * NP,
-                                      NP >> 2, fcx, fcy, (float)Si.x, (float)Si.y, thr, a.collide != 0, &rowmin, &colmin);
+                const ulonglong2* rn = reinterpret_cast<const ulonglong2*>(f_rn) + le * NG * 5;
+                u64 hit = (a.collide && !a.cells)
+                    ? reward_pass<true>(rn, NG, fcx, fcy, (float)Si.x, (float)Si.y, thr, &rowmin, &colmin)
+                    : reward_pass<false>(rn, NG, fcx, fcy, (float)Si.x, (float)Si.y, thr, &rowmin, &colmin);
+                if (a.cells && a.collide) {
+                    // reward collisions (formation_hd_env.py:71-74,119-121; Q18) straight from the cell list of the
+                    // new positions: a count, so the visiting order does not matter
+                    if (c_far[EPC + le]) {
+                        for (int j = 0; j < N; ++j) {
+                            R2 q = envp[j];
+                            const T dx = O::sub(q.x, p.x), dy = O::sub(q.y, p.y);
+                            if (j != i && dx * dx + dy * dy < a.rthr2_hi) { if (O::norm2(dx, dy) < a.rthr) ++col; }
+                        }
+                    } else {
+                        col = cell_count_collisions(c_head + (EPC + le) * CB, c_node + (EPC + le) * NP,
+                                                    a.cell_shift, a.cell_inv_new, cpos, (float)p.x, (float)p.y,
+                                                    (float)a.rthr2_hi, (float)a.rthr, i);
+                    }
+                }
                 while (hit) {
                     const int j4 = (__ffsll((long long)hit) - 1) << 2;
                     hit &= hit - 1;
@@ -858,7 +914,7 @@ __global__ void __launch_bounds__(kBlock, (OM == 2 || FP) ? 4 : 3) k_step(const 
                     for (int j = 0; j < N; ++j) { sx = O::add(sx, raw[j].x); sy = O::add(sy, raw[j].y); }
                     R2 S = O::make(O::sub(lraw.x, O::div(sx, (T)N)), O::sub(lraw.y, O::div(sy, (T)N)));  // :93
                     s_s[t] = S; a.shape[g] = S;
-                    if constexpr (FP) { f_sx[le * NP + i] = (float)S.x; f_sy[le * NP + i] = (float)S.y; }
+                    if constexpr (FP) { RN(le, i, 3) = (float)S.x; RN(le, i, 4) = (float)S.y; }
                 }
                 if (dn && ts == a.n_steps - 1) { a.pos[g] = p; a.vel[g] = v; if (a.comm) a.comm[g] = v; }
                 __syncthreads();
