@@ -358,6 +358,34 @@ class BatchedFormationEnv:
             body()
         return graph
 
+    def render(self, env_index=0, mode='rgb_array', cam_range=None):
+        """Render bridge: copy ONE env's state to the host and draw it like the reference's
+        viewer (environment.py:243-393): agents half transparent, landmarks / obstacles solid, camera on the
+        agents' centroid.  Returns the 700 x 700 x 3 uint8 frame (``mode='human'`` also shows it via pyglet)."""
+        from . import render_bridge as rb
+        e = int(env_index)
+        P = self.pos[e].double().cpu().numpy()
+        size = float(self.params.agent_size)
+        circles = [(p[0], p[1], size, (0.35, 0.35, 0.85), 0.5) for p in P]
+        if self.scn == nat.FG_SCENARIO_HD:
+            # landmarks = ideal shape around the agents' centroid (formation_hd_env.py:40-44)
+            lm = self.landmarks[e].double().cpu().numpy() if self.landmarks is not None \
+                else self.ideal_shape[e].double().cpu().numpy() + P.mean(0)
+            circles += [(l[0], l[1], 0.01, (0.25, 0.25, 0.25), 1.0) for l in lm]
+        else:
+            lm = self.landmarks[e].double().cpu().numpy()
+            G = self.num_goals
+            circles += [(l[0], l[1], 0.02, (0.0, 0.6, 0.0) if self.num_obstacles else (0.25, 0.25, 0.25), 1.0)
+                        for l in lm[:G]]
+            circles += [(l[0], l[1], float(self.params.obstacle_size), (0.25, 0.25, 0.25), 1.0) for l in lm[G:]]
+        walls = [(rb.wall_rect(w.orient, w.axis_pos, w.end0, w.end1, w.width), (0.0, 0.0, 0.0), 1.0 if w.hard else 0.5)
+                 for w in list(self.params.walls)[:self.params.n_walls]]
+        center = P.mean(0) if bool((P == P).all()) else (0.0, 0.0)
+        frame = rb.rasterize(circles, walls, center, rb.CAM_RANGE if cam_range is None else cam_range)
+        if mode != 'rgb_array':
+            self._viewer = rb.show(frame, getattr(self, "_viewer", None))
+        return frame
+
     # ------------------------------------------------------------------ bookkeeping
     @property
     def share_obs(self):

@@ -230,6 +230,24 @@ class MultiAgentEnv(object):
         return [self._get_obs(agent) for agent in self.agents]
 
     def render(self, mode='human', close=False):
-        raise NotImplementedError(
-            "rendering (pyglet viewer, formation_gym/rendering.py) is host-side visualisation and "
-            "is not part of the B200 step path; read env.world.agents[i].state.p_pos to draw")
+        """Reference signature (environment.py:243-393).  Host-side visualisation of the facade's records through
+        ``formation_gym.render_bridge`` (numpy rasteriser; the reference's pyglet viewer is not needed):
+        ``mode='rgb_array'`` returns one 700 x 700 x 3 uint8 frame per viewer, ``mode='human'`` shows it in a pyglet
+        window when pyglet is importable."""
+        from . import render_bridge as rb
+        if close:
+            for i, viewer in enumerate(self.viewers):
+                if viewer is not None and hasattr(viewer, "close"):
+                    viewer.close()
+                self.viewers[i] = None
+            return []
+        results = []
+        for i in range(len(self.viewers)):
+            center = None if self.shared_viewer else self.agents[i].state.p_pos        # :363-367
+            frame = rb.world_frame(self.world, self.agents, center)
+            if mode == 'rgb_array':
+                results.append(frame)
+            else:
+                self.viewers[i] = rb.show(frame, self.viewers[i])
+                results.append(True)
+        return results

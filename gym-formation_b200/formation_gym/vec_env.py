@@ -162,7 +162,8 @@ class CudaVecEnv(object):
         self.closed = True
 
     def render(self, mode='human'):
-        raise NotImplementedError("rendering (pyglet) is not part of the accelerated step path")
+        """First env of the batch through the render bridge (``BatchedFormationEnv.render``)."""
+        return self.env.render(0, mode)
 
     def seed(self, seed=None):
         self.env.seed(seed)

@@ -244,3 +244,29 @@ def test_gloo_world_size_2_stats_allreduce():
     assert abs(res["stats"][1] - R.sum()) < 1e-6 and abs(res["stats"][2] - (R * R).sum()) < 1e-3
     assert abs(res["summary"]["return_mean"] - R.mean()) < 1e-9
     assert abs(res["summary"]["return_std"] - R.std()) < 1e-6
+
+
+def test_render_bridge_rgb_array_on_host():
+    """env.render(mode='rgb_array') (environment.py:243-393) through the numpy rasteriser: no display, no device."""
+    import formation_gym
+    from formation_gym import render_bridge as rb
+    from formation_gym.core import Wall
+    np.random.seed(3)
+    env = formation_gym.make_env("formation_hd_obs_env", False, 4)
+    env.world.walls.append(Wall(orient='V', axis_pos=1.5, endpoints=(-1, 1), width=0.2))
+    for k, a in enumerate(env.world.agents):
+        a.state.p_pos = np.array([0.5 * k - 0.75, 0.0])
+    frames = env.render(mode='rgb_array')
+    assert len(frames) == 1 and frames[0].shape == (700, 700, 3) and frames[0].dtype == np.uint8
+    f = frames[0].astype(int)
+    assert (f[0, 0] == 255).all()                                   # background
+    # camera centred on the agents' centroid (0, 0): agent 1 at (-0.25, 0) -> pixel (350 - 0.25 * 175, 350)
+    px = f[350, int(350 - 0.25 * 175)]
+    want = 0.5 * 255 + 0.5 * 255 * np.array([0.65, 0.65, 0.85])     # half-transparent agent colour on white
+    assert np.abs(px - want).max() <= 2
+    assert (f[350, int(350 + 1.5 * 175)] == 0).all()                # the wall, black
+    # circle radius in pixels = size * 700 / 4
+    img = rb.rasterize([(0.0, 0.0, 0.4, (1.0, 0.0, 0.0), 1.0)])
+    red = (img[..., 0] == 255) & (img[..., 1] == 0)
+    assert abs(red.sum() - np.pi * (0.4 * 175) ** 2) < 0.02 * np.pi * (0.4 * 175) ** 2
+    assert env.render(close=True) == []

@@ -91,3 +91,19 @@ def test_vec_env_pinned_action_buffer_and_basic_scenario():
     obs, rews, dones, infos = venv.step(buf)
     assert obs.shape == (4, 3, 18) and rews.shape == (4, 3, 1)
     assert np.isfinite(obs).all() and np.isfinite(rews).all()
+
+
+def test_render_bridge_batched():
+    """BatchedFormationEnv.render / CudaVecEnv.render: one env's state copied to the host and rasterised."""
+    import formation_gym
+    env = formation_gym.make_batched_env("formation_hd_obs_env", 8, 4, 50, seed=2)
+    env.reset()
+    env.pos[3] = torch.tensor([[-0.5, 0.0], [0.5, 0.0], [0.0, 0.5], [0.0, -0.5]], device="cuda")
+    frame = env.render(3)
+    assert frame.shape == (700, 700, 3) and frame.dtype == np.uint8
+    px = frame[350, int(350 + 0.5 * 175)].astype(int)                 # agent 1: half-transparent blue on white
+    assert np.abs(px - (0.5 * 255 + 0.5 * 255 * np.array([0.35, 0.35, 0.85]))).max() <= 2
+    venv = formation_gym.make_vec_env("formation_hd_env", 4, 9, 25)
+    venv.reset()
+    assert venv.render('rgb_array').shape == (700, 700, 3)
+    venv.close()
