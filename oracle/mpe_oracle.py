@@ -15,8 +15,8 @@ Third-party arithmetic restated here (the reference pins no versio
 ``setup.py:4-17`` has no install_requires; this container has numpy 2.3.5 / scipy 1.18.1):
   * ``scipy.spatial.distance.directed_hausdorff(u, v)[0]`` == sqrt(max_i min_j |u_i - v_j|^2)
     (call site formation_hd_env.py:66) -- restated as a brute-force max-min.
-  * ``np.logaddexp(0, t)`` (core.py:310) == stable softplus; numpy's own ufunc is called here,
-    the C twin (oracle/mpe_oracle.c) spells it out.
+  * ``np.logaddexp(0, t)`` (core.py:310) == stable softplus ``t > 0 ? t + log1p(exp(-t)) : log1p(exp(t))``;
+    numpy's own ufunc is called here (the CUDA kernels spell it out, fg_kernels.cuh contact_force).
 
 PINNING: the reference ships no tests, golden vectors or fixtures for this path,
 so this oracle is pinned against OUTPUTS OF THE UNMODIFIED REFERENCE RUN IN THE BUILD CONTAINER:
