@@ -316,6 +316,43 @@ def run_b200(a):
                "note": "H2D actions + fused step + D2H obs/reward/done/individual reward per step, pinned host "
                        "buffers, host sync every step (PCIe-bound: obs is 24N^2 B per env)"}
         del venv
+        # Informational second figure (NOT the `e2e` key): the same VecEnv API with to_numpy=False -- the
+        # observations stay in HBM for a policy network on the same GPU; per step the host uploads the actions
+        # from pinned memory and reads rewards + dones back.
+        try:
+            venv = formation_gym.make_vec_env(a.scenario, hi - lo, N, a.episode_length, device=device, dtype=dtype,
+                                              seed=0, env_offset=lo, to_numpy=False)
+            venv.reset()
+            act_p = torch.empty(hi - lo, N, 2, dtype=dtype).uniform_(-1, 1).pin_memory()
+            act_d = torch.empty(hi - lo, N, 2, dtype=dtype, device=device)
+            rew_p = torch.empty(hi - lo, N, 1, dtype=dtype).pin_memory()
+            done_p = torch.empty(hi - lo, N, dtype=torch.bool).pin_memory()
+
+            def dev_step():
+                act_d.copy_(act_p, non_blocking=True)
+                o, r, d, _ = venv.step(act_d)
+                rew_p.copy_(r, non_blocking=True); done_p.copy_(d, non_blocking=True)
+                torch.cuda.current_stream(device).synchronize()
+            for _ in range(3):
+                dev_step()
+            Kd = max(10, 5 * Ke)
+            barrier(); torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(Kd):
+                dev_step()
+            dt_d = time.perf_counter() - t0
+            barrier()
+            td = torch.tensor([dt_d], dtype=torch.float64, device=device)
+            if world > 1:
+                dist.all_reduce(td, op=dist.ReduceOp.MAX)
+            e2e["obs_on_device"] = {
+                "value": total_agents * Kd / float(td.item()), "unit": UNIT, "steps": Kd,
+                "h2d_bytes_per_step": int(act_p.numel() * act_p.element_size()) * world,
+                "d2h_bytes_per_step": int(rew_p.numel() * rew_p.element_size() + done_p.numel()) * world,
+                "api": "make_vec_env(..., to_numpy=False).step(cuda actions) -> CUDA obs; rewards/dones read to host"}
+            del venv
+        except Exception as ex:                                   # informational only
+            e2e["obs_on_device"] = {"error": repr(ex)[:200]}
 
     if rank != 0:
         if world > 1:

@@ -25,6 +25,16 @@ def _uniform(values, what, allow_mixed=False):
 
 
 class FacadeBackend(object):
+    """One contiguous device ARENA (all buffers of the C ABI, E = 1) with a pinned host mirror: a step costs one
+    H2D copy of the inputs, one launch, one D2H copy of the outputs and one stream synchronisation (the first
+    version issued ~15 small copies per step: 312 us per basic_formation_env step; the copies dominated)."""
+
+    # (name, elements per unit, unit) in arena order: [in-only | in/out | out-only]; unit 'N' / 'L' / '1' / obs
+    _SEGMENTS = (("act", 4, "N"), ("shape", 2, "N"), ("ivel", 2, "1"),
+                 ("pos", 2, "N"), ("vel", 2, "N"), ("comm", 2, "N"), ("lm", 2, "L"), ("lmv", 2, "L"), ("step", 0, "i32"),
+                 ("reward", 1, "N"), ("indiv", 1, "N"), ("done", 0, "u8"), ("obs", 0, "obs"))
+    _INOUT_FIRST, _OUT_FIRST = "pos", "reward"
+
     def __init__(self, world):
         self.lib = nat.load()
         if not torch.cuda.is_available():
@@ -35,37 +45,88 @@ class FacadeBackend(object):
         self.np_dtype = np.dtype(world.dtype)
         self.dtype = torch.float64 if self.np_dtype == np.float64 else torch.float32
         self.sfx = "_f64" if self.dtype == torch.float64 else ""
-        N, L = self.N, self.L
-        kw = dict(device=self.device, dtype=self.dtype)
-        self.pos = torch.zeros(1, N, 2, **kw)
-        self.vel = torch.zeros(1, N, 2, **kw)
-        self.act = torch.zeros(1, N, 4, **kw)
-        self.comm = torch.zeros(1, N, 2, **kw)
-        self.shape = torch.zeros(1, N, 2, **kw)
-        self.ivel = torch.zeros(1, 2, **kw)
-        self.lm = torch.zeros(1, max(L, 1), 2, **kw)
-        self.lmv = torch.zeros(1, max(L, 1), 2, **kw)          # landmark.state.p_vel (obstacle scenario)
         self._n_obst = 0
-        self.step = torch.zeros(1, dtype=torch.int32, device=self.device)
-        self.obs = None
-        self.reward = torch.zeros(1, N, 1, **kw)
-        self.indiv = torch.zeros(1, N, **kw)
-        self.done = torch.zeros(1, N, dtype=torch.uint8, device=self.device)
+        self._obs_cap = 0
+        self._alloc(6 * self.N)
         self._keep = []
+        self._pkey = None
+        self._pval = None
         self._cache_key = None
         self._cache_val = None
         self.launches = 0
+
+    def _alloc(self, obs_dim):
+        """(Re)build the arena for observation rows of up to ``obs_dim`` scalars."""
+        es, N, L = self.np_dtype.itemsize, self.N, max(self.L, 1)
+        off, self._off = 0, {}
+        for name, per, unit in self._SEGMENTS:
+            nbytes = {"N": per * N * es, "L": per * L * es, "1": per * es, "i32": 4, "u8": N,
+                      "obs": N * obs_dim * es}[unit]
+            self._off[name] = (off, nbytes)
+            off = (off + nbytes + 15) & ~15
+        self._obs_cap = obs_dim
+        self.d = torch.zeros(off, dtype=torch.uint8, device=self.device)
+        self.h = torch.zeros(off, dtype=torch.uint8).pin_memory()
+        hn = self.h.numpy()
+
+        def views(name, dtype_t, dtype_n, shape):
+            o, nb = self._off[name]
+            return (self.d[o:o + nb].view(dtype_t).view(shape), hn[o:o + nb].view(dtype_n).reshape(shape))
+        T, Tn = self.dtype, self.np_dtype
+        self.act, self.h_act = views("act", T, Tn, (1, N, 4))
+        self.shape, self.h_shape = views("shape", T, Tn, (1, N, 2))
+        self.ivel, self.h_ivel = views("ivel", T, Tn, (1, 2))
+        self.pos, self.h_pos = views("pos", T, Tn, (1, N, 2))
+        self.vel, self.h_vel = views("vel", T, Tn, (1, N, 2))
+        self.comm, self.h_comm = views("comm", T, Tn, (1, N, 2))
+        self.lm, self.h_lm = views("lm", T, Tn, (1, L, 2))
+        self.lmv, self.h_lmv = views("lmv", T, Tn, (1, L, 2))
+        self.step, self.h_step = views("step", torch.int32, np.int32, (1,))
+        self.reward, self.h_reward = views("reward", T, Tn, (1, N, 1))
+        self.indiv, self.h_indiv = views("indiv", T, Tn, (1, N))
+        self.done, self.h_done = views("done", torch.uint8, np.uint8, (1, N))
+        self.obs, self.h_obs_flat = views("obs", T, Tn, (N * obs_dim,))
 
     def matches(self, world):
         return (self.N == len(world.agents) and self.L == len(world.landmarks)
                 and self.np_dtype == np.dtype(world.dtype))
 
     # ------------------------------------------------------------------ host <-> device
-    def _up(self, dst, arr):
-        a = np.ascontiguousarray(arr, dtype=self.np_dtype).reshape(tuple(dst.shape))
-        dst.copy_(torch.from_numpy(a))
+    def _h2d(self):
+        """Everything the kernels read: [act .. step]."""
+        end = self._off["step"][0] + 16
+        self.d[:end].copy_(self.h[:end], non_blocking=True)
+
+    def _d2h(self, last):
+        """Everything the kernels wrote, from ``pos`` up to and including segment ``last`` (+ used obs rows)."""
+        start = self._off[self._INOUT_FIRST][0]
+        o, nb = self._off[last]
+        if last == "obs":
+            nb = self.N * self._D * self.np_dtype.itemsize
+        end = (o + nb + 15) & ~15
+        self.h[start:end].copy_(self.d[start:end], non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+
+    def _h_obs(self):
+        return self.h_obs_flat[: self.N * self._D].reshape(self.N, self._D)
 
     def _params(self, world, scenario_kind, prescaled, scenario=None):
+        """fg_params of the world's constants; rebuilt only when one of them changed."""
+        agents = world.agents
+        key = (scenario_kind, bool(prescaled), world.dt, world.damping, world.contact_force, world.contact_margin,
+               world.world_length, world.dim_c, getattr(scenario, "num_obs", None), getattr(scenario, "obs_range", None),
+               tuple((a.movable, a.collide, a.silent, a.u_noise, a.c_noise, a.mass, a.size, a.accel, a.max_speed,
+                      getattr(a, "ghost", False)) for a in agents),
+               tuple((l.movable, l.collide, l.size, l.mass, l.max_speed) for l in world.landmarks),
+               tuple((w.orient, float(w.axis_pos), float(w.endpoints[0]), float(w.endpoints[1]), float(w.width),
+                      bool(w.hard)) for w in world.walls))
+        if key == self._pkey:
+            return self._pval
+        self._pval = self._build_params(world, scenario_kind, prescaled, scenario)
+        self._pkey = key
+        return self._pval
+
+    def _build_params(self, world, scenario_kind, prescaled, scenario=None):
         agents = world.agents
         if not all(a.movable for a in agents):
             raise NotImplementedError("immovable agents are not supported by the accelerated path")
@@ -126,17 +187,24 @@ class FacadeBackend(object):
         V = np.stack([np.asarray(a.state.p_vel, np.float64) for a in world.agents])
         return P, V
 
+    def _stage_state(self, world):
+        """Agent positions / velocities into the pinned mirror; returns them (float64) for cache keys."""
+        P, V = self._gather_state(world)
+        self.h_pos[0] = P
+        self.h_vel[0] = V
+        return P, V
+
     def _scatter_state(self, world, with_comm=True):
-        P = self.pos[0].cpu().numpy().astype(np.float64)
-        V = self.vel[0].cpu().numpy().astype(np.float64)
-        Cm = self.comm[0].cpu().numpy().astype(np.float64)
+        P = self.h_pos[0].astype(np.float64)
+        V = self.h_vel[0].astype(np.float64)
+        Cm = self.h_comm[0].astype(np.float64)
         for i, a in enumerate(world.agents):
             a.state.p_pos = P[i].copy()
             a.state.p_vel = V[i].copy()
             if with_comm:
                 a.state.c = Cm[i, :world.dim_c].copy() if world.dim_c <= 2 else np.zeros(world.dim_c)
 
-    def _buffers(self, scenario_kind, with_obs):
+    def _buffers(self, scenario_kind, with_obs, scenario=None):
         b = nat.fg_buffers()
         b.pos, b.vel, b.act, b.comm = nat.ptr(self.pos), nat.ptr(self.vel), nat.ptr(self.act), nat.ptr(self.comm)
         b.ideal_shape, b.ideal_vel = nat.ptr(self.shape), nat.ptr(self.ivel)
@@ -146,9 +214,16 @@ class FacadeBackend(object):
         if with_obs:
             from .batched import obs_dim, SCENARIOS
             name = [k for k, v in SCENARIOS.items() if v == scenario_kind][0]
-            D = obs_dim(name, self.N, self.L, getattr(self, "_num_obs", 3))
-            if self.obs is None or self.obs.shape[2] != D:
-                self.obs = torch.zeros(1, self.N, D, device=self.device, dtype=self.dtype)
+            self._D = obs_dim(name, self.N, self.L, int(getattr(scenario, "num_obs", 3) or 0))
+            if self._D > self._obs_cap:
+                keep = self.h.clone()
+                old = dict(self._off)
+                self._alloc(self._D)
+                for nm, (o, nb) in old.items():                    # staged inputs survive the re-allocation
+                    if nm != "obs":
+                        o2, _ = self._off[nm]
+                        self.h[o2:o2 + nb] = keep[o:o + nb]
+                return self._buffers(scenario_kind, with_obs, scenario)
             b.obs = nat.ptr(self.obs)
         b.reward, b.indiv, b.done = nat.ptr(self.reward), nat.ptr(self.indiv), nat.ptr(self.done)
         return b
@@ -156,42 +231,41 @@ class FacadeBackend(object):
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
-    def _upload_actions(self, U, silent, Cact=None):
+    def _stage_actions(self, U, silent, Cact=None):
         if silent:
-            act = self.act.view(-1)[: self.N * 2].view(1, self.N, 2)
-            self._up(act, U)
+            self.h_act.reshape(-1)[: self.N * 2] = np.asarray(U, self.np_dtype).reshape(-1)
         else:
-            self._up(self.act, np.concatenate([U, Cact], axis=1))
+            self.h_act[0] = np.concatenate([U, Cact], axis=1)
 
     # ------------------------------------------------------------------ World.step
     def world_step(self, world):
         """core.py:206-225 on the GPU; ``agent.action.u`` is already scaled (action_prescaled)."""
         p, silent = self._params(world, nat.FG_SCENARIO_BASIC, True)
-        P, V = self._gather_state(world)
+        self._stage_state(world)
         U = np.stack([np.asarray(a.action.u, np.float64) for a in world.agents])
         Cact = None if silent else np.stack([np.asarray(a.action.c, np.float64) for a in world.agents])
-        self._up(self.pos, P)
-        self._up(self.vel, V)
-        self._upload_actions(U, silent, Cact)
+        self._stage_actions(U, silent, Cact)
         b = self._buffers(nat.FG_SCENARIO_BASIC, False)
         fn = getattr(self.lib, "fg_world_step" + self.sfx)
         with torch.cuda.device(self.device):
+            self._h2d()
             nat.check(fn(C.byref(p), C.byref(b), 1, self.N, int(world.seed) & (2 ** 64 - 1),
                          int(world.world_step) & 0xFFFFFFFF, 0, self._stream()), "fg_world_step")
+            self._d2h("comm")
         self.launches += 1
         self._scatter_state(world)
         self._cache_key = None
 
     # ------------------------------------------------------------------ scenario hooks
-    def _upload_scenario(self, world, scenario, kind):
+    def _stage_scenario(self, world, scenario, kind):
         if kind == nat.FG_SCENARIO_HD:
-            self._up(self.shape, np.asarray(scenario.ideal_shape, np.float64))
-            self._up(self.ivel, np.asarray(scenario.ideal_vel, np.float64))
+            self.h_shape[0] = np.asarray(scenario.ideal_shape, np.float64)
+            self.h_ivel[0] = np.asarray(scenario.ideal_vel, np.float64)
         if self.L > 0:
-            self._up(self.lm, np.stack([np.asarray(l.state.p_pos, np.float64) for l in world.landmarks]))
+            self.h_lm[0] = np.stack([np.asarray(l.state.p_pos, np.float64) for l in world.landmarks])
         if kind == nat.FG_SCENARIO_HD_OBSTACLE:
-            self._up(self.lmv, np.stack([np.zeros(2) if l.state.p_vel is None else np.asarray(l.state.p_vel, np.float64)
-                                         for l in world.landmarks]))
+            self.h_lmv[0] = np.stack([np.zeros(2) if l.state.p_vel is None else np.asarray(l.state.p_vel, np.float64)
+                                      for l in world.landmarks])
 
     def _scatter_obstacles(self, world, with_pos):
         """Obstacle state back to the host records: positions after a fused step, velocities as the reward
@@ -199,8 +273,8 @@ class FacadeBackend(object):
         n = self._n_obst
         if not n:
             return
-        lm = self.lm[0].cpu().numpy().astype(np.float64)
-        lv = self.lmv[0].cpu().numpy().astype(np.float64)
+        lm = self.h_lm[0].astype(np.float64)
+        lv = self.h_lmv[0].astype(np.float64)
         for k in range(self.L - n, self.L):
             if with_pos:
                 world.landmarks[k].state.p_pos = lm[k].copy()
@@ -221,26 +295,23 @@ class FacadeBackend(object):
                 self._scatter_obstacles(world, with_pos=False)
             return self._cache_val
         p, _ = self._params(world, kind, False, scenario)
-        self._num_obs = int(getattr(scenario, "num_obs", 3) or 0)
-        self._up(self.pos, P)
-        self._up(self.vel, V)
-        self._up(self.comm, Cm)
-        self._upload_scenario(world, scenario, kind)
-        b = self._buffers(kind, True)
+        b = self._buffers(kind, True, scenario)
+        self.h_pos[0], self.h_vel[0], self.h_comm[0] = P, V, Cm
+        self._stage_scenario(world, scenario, kind)
         fn = getattr(self.lib, "fg_obs_reward" + self.sfx)
         with torch.cuda.device(self.device):
+            self._h2d()
             nat.check(fn(C.byref(p), C.byref(b), kind, 1, self.N, self.L, self._stream()), "fg_obs_reward")
+            self._d2h("obs")
         self.launches += 1
-        val = dict(obs=self.obs[0].cpu().numpy().astype(np.float64),
-                   indiv=self.indiv[0].cpu().numpy().astype(np.float64),
-                   reward=float(self.reward[0, 0, 0].item()))
+        val = dict(obs=self._h_obs().astype(np.float64), indiv=self.h_indiv[0].astype(np.float64),
+                   reward=float(self.h_reward[0, 0, 0]))
         if kind == nat.FG_SCENARIO_HD and self.L > 0:
             # observation's side effect (formation_hd_env.py:40-44): landmarks re-centred
-            lm = self.lm[0].cpu().numpy().astype(np.float64)
+            lm = self.h_lm[0].astype(np.float64)
             for k, l in enumerate(world.landmarks):
                 l.state.p_pos = lm[k].copy()
-            lmh = lm
-            key = key[:3] + (lmh.tobytes(),) + key[4:]
+            key = key[:3] + (lm.tobytes(),) + key[4:]
         if kind == nat.FG_SCENARIO_HD_OBSTACLE:
             self._scatter_obstacles(world, with_pos=False)       # the reward hook's velocity rule
         self._cache_key, self._cache_val = key, val
@@ -250,29 +321,26 @@ class FacadeBackend(object):
     def step_fused(self, world, scenario, kind, acts, current_step, acts_c=None):
         """environment.py:113-142 in one launch.  ``current_step`` is the value BEFORE the step."""
         p, silent = self._params(world, kind, False, scenario)
-        self._num_obs = int(getattr(scenario, "num_obs", 3) or 0)
-        P, V = self._gather_state(world)
-        self._up(self.pos, P)
-        self._up(self.vel, V)
-        self._upload_actions(np.asarray(acts, np.float64), silent, acts_c)
-        self._upload_scenario(world, scenario, kind)
-        self.step.fill_(int(current_step))
-        b = self._buffers(kind, True)
+        b = self._buffers(kind, True, scenario)
+        self._stage_state(world)
+        self._stage_actions(np.asarray(acts, np.float64), silent, acts_c)
+        self._stage_scenario(world, scenario, kind)
+        self.h_step[0] = int(current_step)
         fn = getattr(self.lib, "fg_step_fused" + self.sfx)
         with torch.cuda.device(self.device):
+            self._h2d()
             nat.check(fn(C.byref(p), C.byref(b), kind, 1, self.N, self.L, 1, 0, 0,
                          int(world.seed) & (2 ** 64 - 1), int(world.world_step) & 0xFFFFFFFF, 0,
                          self._stream()), "fg_step_fused")
+            self._d2h("obs")
         self.launches += 1
         self._scatter_state(world)
         if kind == nat.FG_SCENARIO_HD and self.L > 0:
-            lm = self.lm[0].cpu().numpy().astype(np.float64)
+            lm = self.h_lm[0].astype(np.float64)
             for k, l in enumerate(world.landmarks):
                 l.state.p_pos = lm[k].copy()
         if kind == nat.FG_SCENARIO_HD_OBSTACLE:
             self._scatter_obstacles(world, with_pos=True)
         self._cache_key = None
-        return dict(obs=self.obs[0].cpu().numpy().astype(np.float64),
-                    indiv=self.indiv[0].cpu().numpy().astype(np.float64),
-                    reward=float(self.reward[0, 0, 0].item()),
-                    done=bool(self.done[0, 0].item()))
+        return dict(obs=self._h_obs().astype(np.float64), indiv=self.h_indiv[0].astype(np.float64),
+                    reward=float(self.h_reward[0, 0, 0]), done=bool(self.h_done[0, 0]))

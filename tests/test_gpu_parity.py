@@ -431,3 +431,35 @@ def test_fast_pairs_nan_env_matches_reference_pattern():
     assert bool(torch.isnan(a["pos"][1]).all()) and not bool(torch.isnan(a["pos"][0]).any())
     for k in a:
         assert torch.equal(torch.isnan(a[k]), torch.isnan(b[k])), k
+
+
+def test_fast_pairs_far_agents_take_the_exhaustive_fallback():
+    """Cell lists (fg_pairs.cuh) cover |x| < 100; an env with a farther agent is flagged and scanned exhaustively:
+    same contacts, same collision counts as the scalar kernel (the far agent has a partner in contact range)."""
+    outs = []
+    for fast in (True, False):
+        os.environ["FG_NO_FAST_PAIRS"] = "0" if fast else "1"
+        os.environ["FG_FORCE_FAST_PAIRS"] = "1" if fast else "0"
+        try:
+            env = BatchedFormationEnv("formation_hd_env", 4, 243, episode_length=25, seed=5, auto_reset=False,
+                                      write_obs=False)
+            env.reset()
+            env.pos[2] *= 0.25                                           # env 2: dense, many contacts
+            env.pos[2, 11] = torch.tensor([150.0, -3.0], device="cuda")  # ... with two agents far out,
+            env.pos[2, 200] = torch.tensor([150.02, -3.01], device="cuda")   # in contact AND in reward collision
+            env.pos[3, 5] = torch.tensor([-1e6, 2e6], device="cuda")     # env 3: one agent very far, alone
+            act = env.sample_actions().clone()
+            for _ in range(2):
+                env.step(act)
+            torch.cuda.synchronize()
+            outs.append({k: getattr(env, k).clone() for k in ("pos", "vel", "reward", "indiv", "ep_collisions")})
+        finally:
+            os.environ.pop("FG_NO_FAST_PAIRS", None)
+            os.environ.pop("FG_FORCE_FAST_PAIRS", None)
+    a, b = outs
+    assert torch.equal(a["ep_collisions"], b["ep_collisions"]) and int(a["ep_collisions"][2]) >= 2
+    assert float((a["vel"][2, 11] - a["vel"][2, 200]).abs().max()) > 1.0        # the far pair pushed each other apart
+    for k in ("pos", "vel", "indiv", "reward"):
+        ref = b[k].double().cpu().numpy()
+        err = np.abs(a[k].double().cpu().numpy() - ref).max()
+        assert err <= 2e-5 * max(1.0, float(np.abs(ref).max())), (k, err)
