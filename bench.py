@@ -434,8 +434,8 @@ def also_configs(formation_gym, torch, device, dtype, peak):
             ("configs[2] hd N=27 E=65536", "formation_hd_env", 27, 65536, 50, "step"),
             ("configs[3] hd N=243 E=1024 (one GPU's share of 8192)", "formation_hd_env", 243, 1024, 30, "step"),
             ("configs[3] hd N=243 E=8192 (all 8192 envs on one GPU: steady state, no wave tail)", "formation_hd_env", 243, 8192, 8, "step"),
-            ("hd N=243 E=1024 state+reward only (no obs; random policy drawn in the step kernel)", "formation_hd_env", 243, 1024, 30, "noobs"),
-            ("hd N=243 E=8192 state+reward only (no obs; steady state)", "formation_hd_env", 243, 8192, 8, "noobs"),
+            ("hd N=243 E=1024 state+reward only (no obs; fused step kernel alone, CUDA graph)", "formation_hd_env", 243, 1024, 8, "noobs"),
+            ("hd N=243 E=8192 state+reward only (no obs; steady state)", "formation_hd_env", 243, 8192, 3, "noobs"),
             ("hd N=3 E=1048576", "formation_hd_env", 3, 1048576, 50, "step"),
             ("basic N=3 L=3 E=1048576", "basic_formation_env", 3, 1048576, 50, "step")):
         try:
@@ -444,6 +444,10 @@ def also_configs(formation_gym, torch, device, dtype, peak):
             env.reset()
 
             graph = env.capture_steps(25) if mode == "graph" else None
+            if mode == "noobs":
+                # the step kernel alone: actions sampled once, 5 fused steps per CUDA graph (no launch gaps)
+                env.sample_actions()
+                graph = env.capture_steps(5, policy=lambda env_: None)
 
             def run(n):
                 for _ in range(n):
@@ -454,7 +458,7 @@ def also_configs(formation_gym, torch, device, dtype, peak):
                     elif mode == "bfs":
                         env.step(env.bfs_actions(3))
                     elif mode == "noobs":
-                        env.step_random()                     # one launch per step: Philox actions in-kernel
+                        graph.replay()
                     else:
                         env.sample_actions(); env.step(env.actions)
             run(5)
@@ -462,7 +466,7 @@ def also_configs(formation_gym, torch, device, dtype, peak):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(); run(steps); e1.record(); torch.cuda.synchronize()
             ms = e0.elapsed_time(e1)
-            env_steps = steps * (25 if mode in ("rollout", "graph") else 1)
+            env_steps = steps * (25 if mode in ("rollout", "graph") else 5 if mode == "noobs" else 1)
             gbs = env.bytes_per_env_step() * E * env_steps / (ms * 1e-3) / 1e9
             row = {"config": name, "agent_steps_per_s": E * N * env_steps / (ms * 1e-3),
                    "ms_per_env_step": ms / env_steps, "algorithmic_GBps": gbs, "hbm_frac": gbs / peak}
@@ -472,7 +476,7 @@ def also_configs(formation_gym, torch, device, dtype, peak):
                 row.update({"bound": "fp32", "algorithmic_TFLOPs": tf, "fp32_peak_TFLOPs": fp32_peak,
                             "fp32_frac": (tf / fp32_peak) if fp32_peak else None,
                             "flops_per_env_step": flops_per_env_step(N),
-                            "note": "one fused launch per step (actions from Philox inside the kernel); "
+                            "note": "fused step kernel alone (actions pre-sampled, CUDA graph of 5 steps); "
                                     "fraction of the MEASURED scalar-FFMA peak"})
             res.append(row)
             del env
