@@ -193,8 +193,11 @@ def run_b200(a):
     device = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        # NCCL writes its version banner / debug lines to stdout: send them to a file so that stdout carries
+        # exactly ONE JSON line whatever NCCL_DEBUG level the launcher chose
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/fg_bench_nccl.%h.%p.log")
         if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"          # NCCL's version banner goes to stdout; keep it to ONE JSON line
+            os.environ["NCCL_DEBUG"] = "WARN"          # NCCL honours the debug file only above the VERSION level
         dist.init_process_group("nccl", device_id=device)
     dtype = torch.float32 if a.dtype == "f32" else torch.float64
     E, N, K, W = a.envs_per_gpu, a.agents, a.steps, max(a.warmup, 3)
