@@ -65,6 +65,15 @@ int fill_args(fg::KArgs<T>& a, const fg_params* p, const fg_buffers* b, int scen
     }
     if ((uint64_t)E * (uint64_t)N >= (1ull << 31)) return fail(FG_ERR_ARG, "E*N must be < 2^31%s");
     if (p->n_walls < 0 || p->n_walls > FG_MAX_WALLS) return fail(FG_ERR_ARG, "n_walls out of range%s");
+    {
+        // every 2-vector buffer is accessed as float2 / double2 items
+        const void* vec[] = {b->pos, b->vel, b->act, b->comm, b->ideal_shape, b->ideal_vel, b->landmarks,
+                             b->landmark_vel, b->obs};
+        for (const void* q : vec)
+            if (q && ((uintptr_t)q % sizeof(R2)) != 0)
+                return fail(FG_ERR_ARG, "2-vector buffers (pos, vel, act, comm, ideal_*, landmarks, obs) must be "
+                                        "8-byte (fp32) / 16-byte (fp64) aligned%s");
+    }
     memset(&a, 0, sizeof(a));
     a.pos = (R2*)b->pos; a.vel = (R2*)b->vel; a.act = (const R2*)b->act; a.comm = (R2*)b->comm;
     a.shape = (R2*)b->ideal_shape; a.ivel = (R2*)b->ideal_vel; a.lm = (R2*)b->landmarks;
@@ -165,6 +174,20 @@ size_t smem_bytes(const fg::KArgs<T>& a, int scenario, bool het) {
     return (s + 15) & ~(size_t)15;
 }
 
+// OM == 3 (short rows staged per thread, one bulk store per tile): image of EPC*N rows (+ phase items)
+template <typename T>
+size_t tile_image_bytes(const fg::KArgs<T>& a) {
+    typedef typename fg::Ops<T>::R2 R2;
+    return (size_t)(((size_t)a.EPC * a.N * a.IPR + 3) & ~(size_t)1) * sizeof(R2);
+}
+template <typename T>
+bool tile_image_ok(const fg::KArgs<T>& a) {
+    typedef typename fg::Ops<T>::R2 R2;
+    const char* off = getenv("FG_NO_TILE_IMAGE");                      // A/B switch for tests and profiling
+    return a.obs && ((uintptr_t)a.obs % sizeof(R2)) == 0 && tile_image_bytes(a) <= 96 * 1024 &&
+           !(off && off[0] == '1');
+}
+
 // extra shared memory of the fast pair loops: 8 arrays of EPC*roundup(N,32) floats, the per-(env,warp)
 // partial sums and the two max-norm words per env
 template <typename T>
@@ -211,9 +234,10 @@ int launch_fp(const fg::KArgs<T>& a, size_t smem, cudaStream_t st) {
 // observation-writer mode of the tile kernel (fg_kernels.cuh k_step<..., OM>)
 template <typename T, int SCN, bool PHYS, bool OBSREW, bool HET>
 int launch_om(const fg::KArgs<T>& a, size_t smem, cudaStream_t st) {
-    if (!OBSREW || SCN >= fg::kScnPartial) return launch_fp<T, SCN, PHYS, OBSREW, HET, 0>(a, smem, st);
+    if (!OBSREW) return launch_fp<T, SCN, PHYS, OBSREW, HET, 0>(a, smem, st);
     if (SCN == fg::kScnHD && a.row_tma) return launch_fp<T, SCN, PHYS, OBSREW, HET, (SCN == fg::kScnHD ? 2 : 0)>(a, smem, st);
-    if (a.IPR >= 48) return launch_fp<T, SCN, PHYS, OBSREW, HET, 1>(a, smem, st);
+    if (SCN < fg::kScnPartial && a.IPR >= 48) return launch_fp<T, SCN, PHYS, OBSREW, HET, 1>(a, smem, st);
+    if (tile_image_ok<T>(a)) return launch_fp<T, SCN, PHYS, OBSREW, HET, (OBSREW ? 3 : 0)>(a, smem + tile_image_bytes<T>(a), st);
     return launch_fp<T, SCN, PHYS, OBSREW, HET, 0>(a, smem, st);
 }
 

@@ -164,8 +164,9 @@ __device__ __forceinline__ void wall_force(const WallT<T>& w, T px, T py, T size
 // The fused kernel.  PHYS: run World.step.  OBSREW: run observation/reward/done.  HET: per-agent
 // mass/size/accel/max_speed arrays (otherwise the scalar fast path).
 // OM selects the observation writer (one per instantiation keeps registers low): 0 = flat item loop
-// (short rows), 1 = one warp per row with plain streaming stores, 2 = one warp per row, static row part
-// bulk-stored from a shared image (hd, silent agents, long rows).
+// (fallback), 1 = one warp per row with plain streaming stores, 2 = one warp per row, static row part
+// bulk-stored from a shared image (hd, silent agents, long rows), 3 = short rows: own row per thread staged in
+// shared memory, the whole tile leaves as one bulk store.
 // FP: fast pair loops of fg_pairs.cuh (fp32, hd, uniform agents, N >= 32): structure-of-arrays partner
 // data, packed FFMA2/FADD2/FMUL2 arithmetic, group filters, warp-shuffle centroid and reductions.
 template <typename T, int SCN, bool PHYS, bool OBSREW, bool HET, int OM, bool FP>
@@ -185,6 +186,9 @@ __global__ void __launch_bounds__(kBlock, (OM == 2 || FP) ? 4 : 3) k_step(const 
     const int rt_dyn = (N + 3) & ~1;                  // items per staging buffer (16-byte multiple)
     R2* s_rt_img = reinterpret_cast<R2*>(smem_raw);
     R2* s_rt_dyn = s_rt_img + (OM == 2 ? 2 * rt_img * EPC : 0);
+    // OM == 3: image of the whole tile's observation rows (own row per thread), + 2 items for the 16-byte phase
+    const int img3_items = (OM == 3) ? ((EPC * N * a.IPR + 3) & ~1) : 0;
+    if (OM == 3) s_rt_dyn = s_rt_img + img3_items;
     // FP: per local env, arrays of NP = roundup(N, 32) floats (16-byte aligned): old positions and
     // their squared norms, centred new positions and norms, centred ideal shape.
     const int NP = (N + 31) & ~31;
@@ -1006,6 +1010,67 @@ __global__ void __launch_bounds__(kBlock, (OM == 2 || FP) ? 4 : 3) k_step(const 
                 }
                 // the images must outlive the bulk copies' reads (kernel exit or the next rollout step)
                 if (pending && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                __syncthreads();
+            } else if (OM == 3) {
+                // Short rows: every thread stages ITS OWN row in shared memory with simple loops (no per-item
+                // (row, item) decode); the tile's rows are ONE contiguous span of HBM, which leaves as one TMA
+                // bulk store (16-byte aligned middle) plus at most one 8-byte head / tail item.
+                R2* out = a.obs + (size_t)tile0 * N * IPR;
+                R2* img = s_rt_img + (((uint32_t)(uintptr_t)out & 15u) ? 1 : 0);      // same 16-byte phase as `out`
+                if (active) {
+                    R2* row = img + (size_t)t * IPR;
+                    const R2* P = s_new + le * N;
+                    const R2* Cm = s_c + le * N;
+                    row[0] = v;                                                        // p_vel
+                    int base = 1;
+                    if (SCN == kScnBasic) {
+                        row[1] = p;                                                    // p_pos
+                        const R2* Lm = s_s + le * L;
+                        for (int k = 0; k < L; ++k) { R2 l = Lm[k]; row[2 + k] = O::make(O::sub(l.x, p.x), O::sub(l.y, p.y)); }
+                        base = 2 + L;
+                    } else if (SCN >= kScnPartial) {
+                        const R2* Lm = s_s + le * L;
+                        for (int k = 0; k < L; ++k) row[1 + k] = Lm[k];                // landmarks, absolute
+                        base = 1 + L;
+                    }
+                    int nrel = N - 1;
+                    if (SCN == kScnPartial) {                                          // agents i+1 .. i+num_obs, cyclic
+                        nrel = a.num_obs;
+                        int j = i;
+                        for (int m = 0; m < nrel; ++m) {
+                            j = (j + 1 == N) ? 0 : j + 1;
+                            R2 pj = P[j];
+                            row[base + m] = O::make(O::sub(pj.x, p.x), O::sub(pj.y, p.y));
+                        }
+                    } else {
+                        for (int m = 0; m < N - 1; ++m) {                              // other_pos, j != i ascending
+                            R2 pj = P[m + (m >= i)];
+                            T dx = O::sub(pj.x, p.x), dy = O::sub(pj.y, p.y);
+                            if (SCN == kScnRange) {                                    // np.clip keeps NaN
+                                const T lo = -a.obs_range, hi = a.obs_range;
+                                dx = (dx < lo) ? lo : ((dx > hi) ? hi : dx);
+                                dy = (dy < lo) ? lo : ((dy > hi) ? hi : dy);
+                            }
+                            row[base + m] = O::make(dx, dy);
+                        }
+                    }
+                    for (int m = 0; m < N - 1; ++m) row[base + nrel + m] = Cm[m + (m >= i)];   // comm of the others
+                    if (SCN == kScnHD) {
+                        const R2* Sh = s_s + le * N;
+                        for (int k = 0; k < N; ++k) row[2 * N - 1 + k] = Sh[k];        // ideal_shape.flatten()
+                        row[3 * N - 1] = s_iv[le];                                     // ideal_vel
+                    }
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncthreads();
+                if (t < 32) {
+                    row_piece_store<R2>(out, img, (uint32_t)((size_t)nvalid * N * IPR * sizeof(R2)), t);
+                    if (t == 0) {
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                        // the image must outlive the bulk copy's reads (kernel exit or the next rollout step)
+                        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                    }
+                }
                 __syncthreads();
             } else if (OM == 1) {
                 // Long rows (N >= 16): one warp per row, one simple loop per row segment -- no per-item

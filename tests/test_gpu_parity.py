@@ -463,3 +463,47 @@ def test_fast_pairs_far_agents_take_the_exhaustive_fallback():
         ref = b[k].double().cpu().numpy()
         err = np.abs(a[k].double().cpu().numpy() - ref).max()
         assert err <= 2e-5 * max(1.0, float(np.abs(ref).max())), (k, err)
+
+
+@pytest.mark.parametrize("scen,E,N,kw", [("formation_hd_env", 1000, 5, {}), ("formation_hd_env", 77, 10, {}),
+                                         ("formation_hd_env", 300, 15, {}), ("basic_formation_env", 1000, 3, {}),
+                                         ("basic_formation_env", 90, 6, dict(num_landmarks=4)),
+                                         ("formation_hd_partial_env", 500, 5, dict(num_obs=3)),
+                                         ("formation_hd_partial_range_env", 500, 4, dict(obs_range=0.7))])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64], ids=["f32", "f64"])
+def test_tile_image_writer_equals_flat_writer(scen, E, N, kw, dtype):
+    """Observation writer OM == 3 (own row per thread staged in shared memory, one bulk store per tile) against the
+    flat item loop (FG_NO_TILE_IMAGE=1): bit-identical rows, stepwise and in a rollout with auto-resets, also for an
+    observation buffer that starts on an odd 8-byte slot."""
+    outs = []
+    for off in ("0", "1"):
+        os.environ["FG_NO_TILE_IMAGE"] = off
+        try:
+            env = BatchedFormationEnv(scen, E, N, episode_length=3, seed=11, dtype=dtype, **kw)
+            big = torch.zeros(E * N * env.D + 4, dtype=dtype, device="cuda")
+            env.obs = big[2:2 + E * N * env.D].view(E, N, env.D)            # fp32: odd 8-byte slot of a 16-byte line
+            env._bufs = env._make_buffers()
+            env.reset()
+            res = []
+            for _ in range(4):
+                env.step_random()
+                res.append(env.obs.clone())
+            env.rollout_random(3)
+            res.append(env.obs.clone())
+            assert float(big[:2].abs().sum()) == 0.0 and float(big[-2:].abs().sum()) == 0.0   # nothing outside the buffer
+            outs.append(res)
+        finally:
+            os.environ.pop("FG_NO_TILE_IMAGE", None)
+    for x, y in zip(*outs):
+        assert torch.equal(torch.nan_to_num(x), torch.nan_to_num(y))
+
+
+def test_misaligned_vector_buffers_are_rejected():
+    """float2 / double2 access: a 4-byte-aligned obs pointer is an argument error, not a device fault."""
+    from formation_gym import _native as nat
+    env = BatchedFormationEnv("formation_hd_env", 8, 5, episode_length=3)
+    big = torch.zeros(8 * 5 * env.D + 2, device="cuda")
+    env.obs = big[1:1 + 8 * 5 * env.D].view(8, 5, env.D)
+    env._bufs = env._make_buffers()
+    with pytest.raises(nat.NativeError, match="aligned"):
+        env.step_random()
