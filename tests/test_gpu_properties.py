@@ -1,0 +1,176 @@
+"""Size-independent properties of the step path, checked at small sizes and at the FULL sizes
+of BASELINE.json's configs, where the numpy oracle would take minutes: momentum symmetry of the contact force
+(core.py:314-318), far pairs contributing exactly nothing, permutation equivariance over agents, independence of the
+results from how envs are sharded over GPUs (Philox keyed by the global env id), noise and reset statistics
+(core.py:232-233, formation_hd_env.py:77-95), and the observation layout (formation_hd_env.py:52-59) recomputed with
+plain torch ops from the state tensors."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from formation_gym.batched import BatchedFormationEnv  # noqa: E402
+
+
+def _hd(E, N, dtype=torch.float64, **kw):
+    kw.setdefault("auto_reset", False)
+    env = BatchedFormationEnv("formation_hd_env", E, N, episode_length=25, dtype=dtype, seed=4, **kw)
+    env.reset()
+    return env
+
+
+def test_contact_forces_conserve_momentum():
+    """f_a = +f, f_b = -f for equal masses (core.py:314-318): with zero actions and zero velocities the velocities
+    after one step sum to zero in every env, however many agents are in contact."""
+    env = _hd(64, 27)
+    env.pos.mul_(0.1)                                    # dense: many contacts
+    env.vel.zero_()
+    env.step(torch.zeros_like(env.actions))
+    assert float(env.vel.abs().max()) > 1.0               # contacts did push
+    tot = env.vel.sum(1)
+    assert float(tot.abs().max()) <= 1e-11 * float(env.vel.abs().max()) * 27
+
+
+def test_far_pairs_contribute_exactly_nothing():
+    """Agents farther apart than the contact range: v' = v (1 - damping) + 5 a dt, p' = p + v' dt, bit for bit
+    (core.py:268-277; the softplus underflows to an exact 0 in the reference, the kernel skips the pair)."""
+    env = _hd(32, 9)
+    grid = torch.stack(torch.meshgrid(torch.arange(3.), torch.arange(3.), indexing="ij"), -1).reshape(9, 2)
+    env.pos.copy_((grid * 0.9 - 0.9).to(env.pos).expand(32, 9, 2) + 0.01 * env.pos)
+    v0 = torch.rand_like(env.vel) - 0.5
+    env.vel.copy_(v0)
+    p0 = env.pos.clone()
+    act = env.sample_actions().clone()
+    env.step(act)
+    v1 = v0 * 0.75 + (act * 5.0) * 0.1
+    assert torch.equal(env.vel, v1) and torch.equal(env.pos, p0 + v1 * 0.1)
+
+
+@pytest.mark.parametrize("N", [9, 40])
+def test_permutation_equivariance(N):
+    """Relabelling the agents (and the rows of the ideal shape with them) permutes positions, velocities and
+    individual rewards; the formation and velocity terms and the collision total do not change."""
+    a = _hd(16, N)
+    a.pos.mul_(0.3)
+    b = _hd(16, N)
+    perm = torch.randperm(N, device="cuda")
+    for k in ("pos", "vel", "ideal_shape"):
+        getattr(b, k).copy_(getattr(a, k)[:, perm])
+    b.ideal_vel.copy_(a.ideal_vel)
+    act = a.sample_actions().clone()
+    _, ra, _, ia = a.step(act)
+    _, rb, _, ib = b.step(act[:, perm].contiguous())
+    assert float((b.pos - a.pos[:, perm]).abs().max()) <= 1e-12          # force sums in a different order
+    assert float((b.vel - a.vel[:, perm]).abs().max()) <= 1e-11
+    assert float((ib["individual_reward"] - ia["individual_reward"][:, perm]).abs().max()) <= 1e-12
+    assert float((rb - ra).abs().max()) <= 1e-10
+
+
+@pytest.mark.parametrize("scen,N", [("formation_hd_env", 9), ("formation_hd_env", 27), ("formation_hd_env", 81),
+                                    ("basic_formation_env", 3), ("formation_hd_obs_env", 4)])
+def test_sharding_invariance(scen, N):
+    """One batch of E envs == two shards with env_offset (the multi-GPU layout): identical states, observations and
+    statistics after a random-policy rollout with auto-resets and motor noise."""
+    E, T = 1000, 12
+    kw = dict(episode_length=5, seed=9, u_noise=0.05, dtype=torch.float32)
+    full = BatchedFormationEnv(scen, E, N, **kw)
+    lo = BatchedFormationEnv(scen, 400, N, env_offset=0, **kw)
+    hi = BatchedFormationEnv(scen, 600, N, env_offset=400, **kw)
+    for env in (full, lo, hi):
+        env.reset()
+        for _ in range(T):
+            env.step_random()
+    for k in ("pos", "vel", "obs", "reward", "indiv", "step_count", "ep_return"):
+        both = torch.cat([getattr(lo, k), getattr(hi, k)], 0)
+        assert torch.equal(getattr(full, k), both), k
+    assert torch.allclose(full.stats, lo.stats + hi.stats, rtol=1e-12, atol=0)
+
+
+def test_motor_noise_statistics():
+    """core.py:232-233: F += randn(2) * u_noise.  Far-apart agents at rest with zero actions: v' = noise * dt."""
+    env = _hd(4096, 9, dtype=torch.float32, u_noise=0.1)
+    grid = torch.stack(torch.meshgrid(torch.arange(3.), torch.arange(3.), indexing="ij"), -1).reshape(9, 2)
+    env.pos.copy_(grid.to(env.pos).expand(4096, 9, 2))
+    env.vel.zero_()
+    env.step(torch.zeros_like(env.actions))
+    n = env.vel.double().flatten() / 0.1
+    assert abs(float(n.mean())) < 4 * 0.1 / np.sqrt(n.numel())
+    assert abs(float(n.std()) - 0.1) < 0.002
+    assert abs(float((n ** 4).mean() / n.var() ** 2) - 3.0) < 0.1         # Gaussian kurtosis
+    # the two components and different agents are uncorrelated
+    v = env.vel.double() / 0.1
+    assert abs(float((v[..., 0] * v[..., 1]).mean())) < 5e-4
+    assert abs(float((v[:, 0, 0] * v[:, 1, 0]).mean())) < 2e-3
+
+
+def test_reset_statistics():
+    """formation_hd_env.py:77-95: agents and landmarks ~ U(-1,1)^2, ideal_shape = landmarks - mean, ideal_vel ~
+    U(-1,1)^2, velocities 0; different envs / agents / purposes draw independent numbers."""
+    env = _hd(65536, 9, dtype=torch.float32)
+    p = env.pos.double()
+    assert float(p.abs().max()) <= 1.0 and float(env.vel.abs().max()) == 0.0
+    assert abs(float(p.mean())) < 3e-3 and abs(float(p.var()) - 1 / 3) < 3e-3
+    assert float(env.ideal_shape.double().mean(1).abs().max()) < 1e-6    # centred
+    # variance of a centred uniform sample: (1 - 1/N) / 3
+    assert abs(float(env.ideal_shape.double().var(unbiased=False)) - (8 / 9) / 3) < 3e-3
+    iv = env.ideal_vel.double()
+    assert abs(float(iv.mean())) < 6e-3 and abs(float(iv.var()) - 1 / 3) < 6e-3
+    assert abs(float((p[:, 0, 0] * p[:, 1, 0]).mean())) < 6e-3 and abs(float((p[:, 0, 0] * iv[:, 0]).mean())) < 6e-3
+    assert abs(float((p[:-1, 0, 0] * p[1:, 0, 0]).mean())) < 6e-3
+
+
+def _check_hd_outputs(env, act, p0, v0):
+    """Everything an env.step returns, recomputed with plain torch ops from the state tensors (exact where the
+    arithmetic is a single rounded operation)."""
+    E, N = env.E, env.N
+    obs, rew, done, info = env.obs, env.reward, env.done, {"individual_reward": env.indiv}
+    pos, vel = env.pos, env.vel
+    assert torch.equal(obs[:, :, 0:2], vel)                                          # p_vel
+    idx = torch.arange(N, device="cuda")
+    others = torch.stack([torch.cat([idx[:i], idx[i + 1:]]) for i in range(N)])      # [N, N-1]
+    for i in range(0, N, max(1, N // 9)):                                            # sampled rows (memory)
+        rel = pos[:, others[i]] - pos[:, i:i + 1]
+        assert torch.equal(obs[:, i, 2:2 * N].reshape(E, N - 1, 2), rel)             # other_pos
+        assert float(obs[:, i, 2 * N:4 * N - 2].abs().max()) == 0.0                  # comm of silent agents
+        assert torch.equal(obs[:, i, 4 * N - 2:6 * N - 2].reshape(E, N, 2), env.ideal_shape)
+        assert torch.equal(obs[:, i, 6 * N - 2:], env.ideal_vel)
+    # physics of agents that had nobody within the contact range: exact
+    d = torch.cdist(p0, p0) + 10.0 * torch.eye(N, device="cuda")
+    free = d.min(2).values > 0.09
+    v1 = v0 * 0.75 + (act * 5.0) * 0.1
+    # (fp32 build: the kernel may contract v * keep + F * dt into an FMA, hence one ulp)
+    assert float((vel[free] - v1[free]).abs().max()) <= 2e-7 and float((pos[free] - (p0 + v1 * 0.1)[free]).abs().max()) <= 5e-7
+    assert float(free.float().mean()) > 0.1
+    # reward: shared sum broadcast, individual rewards = base - collisions
+    assert torch.equal(rew[:, :, 0], rew[:, :1, 0].expand(E, N))
+    dn = torch.cdist(pos.double(), pos.double()) + 10.0 * torch.eye(N, device="cuda", dtype=torch.float64)
+    margin = (dn - 0.03).abs().min(2).values > 1e-6                                  # away from the threshold
+    col = (dn < 0.03).sum(2)
+    indiv = info["individual_reward"].double()
+    base = (indiv + col)                                                             # same for all agents of an env
+    ok = margin.all(1)
+    assert float((base[ok] - base[ok][:, :1]).abs().max()) <= 2e-5
+    C = pos.double() - pos.double().mean(1, keepdim=True)
+    S = env.ideal_shape.double()
+    d2 = torch.cdist(C, S)
+    form = torch.maximum(d2.min(2).values.max(1).values, d2.min(1).values.max(1).values)
+    velr = (env.ideal_vel.double() - vel.double().mean(1)).norm(dim=1)
+    assert float((base[ok][:, 0] - (-form - velr)[ok]).abs().max()) <= 2e-5
+    tot = (indiv.sum(1) - rew[:, 0, 0].double()).abs()
+    assert bool((tot <= 1e-5 + 1e-6 * rew[:, 0, 0].double().abs()).all())
+    assert torch.equal(done, (env.step_count >= 25)[:, None].expand(E, N)) or bool(env.auto_reset)
+
+
+@pytest.mark.parametrize("N,E", [(9, 131072), (27, 65536), (3, 1048576), (243, 1024), (9, 4096)])
+def test_full_size_step_properties(N, E):
+    """BASELINE.json's configs at FULL size (fp32): one step on given actions, outputs recomputed from the state
+    tensors with torch."""
+    env = _hd(E, N, dtype=torch.float32)
+    if N == 243:
+        env.pos.mul_(1.0)
+    p0, v0 = env.pos.clone(), (torch.rand_like(env.vel) - 0.5)
+    env.vel.copy_(v0)
+    act = env.sample_actions().clone()
+    env.step(act)
+    _check_hd_outputs(env, act, p0, v0)
