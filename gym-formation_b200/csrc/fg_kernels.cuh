@@ -665,7 +665,7 @@ __global__ void __launch_bounds__(kBlock, (OM == 2 || FP) ? 4 : 3) k_step(const 
                 T sx = 0, sy = 0;
 #pragma unroll 4
                 for (int j = 0; j < N; ++j) { R2 q = src[j]; sx = O::add(sx, q.x); sy = O::add(sy, q.y); }
-                s_mean[t] = O::make(O::div(sx, (T)N), O::div(sy, (T)N));
+                s_mean[t] = O::make(O::div_count(sx, N), O::div_count(sy, N));   // np.mean: fp64 divides, fp32 multiplies by 1/N
             }
             __syncthreads();
             if constexpr (FP) {
@@ -677,8 +677,9 @@ __global__ void __launch_bounds__(kBlock, (OM == 2 || FP) ? 4 : 3) k_step(const 
                         sx += q.x; sy += q.y; svx += q.z; svy += q.w;
                     }
                 }
-                mvx = svx / (float)N; mvy = svy / (float)N;
-                fcx = (float)p.x - sx / (float)N; fcy = (float)p.y - sy / (float)N;   // centred agent shape
+                const float invN = 1.0f / (float)N;
+                mvx = svx * invN; mvy = svy * invN;
+                fcx = (float)p.x - sx * invN; fcy = (float)p.y - sy * invN;           // centred agent shape
                 fnc = fcx * fcx + fcy * fcy;
                 if (active) { RN(le, i, 0) = fcx; RN(le, i, 1) = fcy; RN(le, i, 2) = fnc; }
                 env_atomic_max(s_nmax + EPC, __float_as_uint(fnc));

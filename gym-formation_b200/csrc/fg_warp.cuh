@@ -240,7 +240,7 @@ __global__ void __launch_bounds__(32 * WarpLayout<T, N, WOBS>::MAXW, WarpLayout<
             T sx = 0, sy = 0;
 #pragma unroll
             for (int j = 0; j < N; ++j) { R2 q = src[j]; sx = O::add(sx, q.x); sy = O::add(sy, q.y); }
-            s_mean[lane] = O::make(O::div(sx, (T)N), O::div(sy, (T)N));
+            s_mean[lane] = O::make(O::div_count(sx, N), O::div_count(sy, N));   // np.mean: fp64 divides, fp32 multiplies by 1/N
         }
         __syncwarp();
         const R2 mp = s_mean[2 * le], mv = s_mean[2 * le + 1];
