@@ -248,23 +248,43 @@ def run_b200(a):
     launches = 2 * K                                              # fg::k_random_actions + step kernel per step
     ms = ev0.elapsed_time(ev1)
 
-    # ---- timed region 2 (-> roofline): the same K steps as per-step launches with CUDA events around
-    # every fused-step launch, on the launching stream.  A device-side sleep is queued first so that
-    # the host runs ahead and the kernels execute back to back (otherwise event-to-event time would
-    # include the host's submission gap, not the kernel).
-    ka = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
-    kb = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
-    er0, er1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda._sleep(int(2.0e9 * min(0.4, 250e-6 * K + 0.01)))
-    er0.record()
-    for k in range(K):
+    # ---- timed region 2 (-> roofline): the fused step kernel ALONE.  G steps are captured into a CUDA graph, each
+    # on its own pre-sampled action buffer (fresh actions every step, as in region 1, but no random-policy kernel in
+    # between), and the graph is replayed until K steps have run; CUDA events on the launching stream bracket the
+    # replays.  kernel_ms = elapsed / steps is the kernel's average launch duration including the (sub-microsecond)
+    # kernel-to-kernel hand-over inside the graph.  (Events recorded around every single launch, the first version
+    # of this region, added ~5 us of launch latency to each 53 us kernel.)
+    G = max(1, min(K, 20))
+    acts = []
+    for _ in range(G):
         env.sample_actions()
-        ka[k].record()
-        env.step(env.actions)
-        kb[k].record()
+        acts.append(env.actions.clone())
+        env.step(env.actions)                                     # also advances the state / tick like region 1
+    env.use_device_tick(True)
+    torch.cuda.synchronize()
+    side = torch.cuda.Stream(device=device)
+    side.wait_stream(torch.cuda.current_stream(device))
+    with torch.cuda.stream(side):
+        for a_k in acts:                                          # warm-up outside capture (per-buffer fg_buffers)
+            env.step(a_k)
+    torch.cuda.current_stream(device).wait_stream(side)
+    torch.cuda.synchronize()
+    g2 = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g2):
+        for a_k in acts:
+            env.step(a_k)
+    g2.replay(); torch.cuda.synchronize()
+    reps2 = max(1, (K + G - 1) // G)
+    er0, er1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier(); torch.cuda.synchronize()
+    er0.record()
+    for _ in range(reps2):
+        g2.replay()
     er1.record()
     torch.cuda.synchronize(); barrier()
     region2_ms = er0.elapsed_time(er1)
+    kernel_ms = region2_ms / (reps2 * G)
+    del g2, acts
     # keep the sampler alive a little if the regions were short, so it has samples under load
     clocks = None
     if sampler:
@@ -277,7 +297,6 @@ def run_b200(a):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
-    kernel_ms = statistics.mean(x.elapsed_time(y) for x, y in zip(ka, kb))
     total_agents = (hi - lo) * world * N
     value = total_agents * K / (ms * 1e-3)
 
@@ -380,9 +399,10 @@ def run_b200(a):
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "peak_source": peak_src, "kernel_ms": kernel_ms,
                 "algorithmic_bytes_per_env_step": env.bytes_per_env_step(),
-                "share_of_step": kernel_ms * K / region2_ms,
-                "timing": "CUDA events around each fused-step launch over a second K-step region of per-step "
-                          "launches (region 1, which gives `value`, replays the same launches from a CUDA graph)"}
+                "share_of_step": kernel_ms / (ms / K),
+                "timing": "CUDA events around replays of a CUDA graph holding only fused-step launches, each on its "
+                          "own pre-sampled action buffer (region 1, which gives `value`, replays random-policy kernel "
+                          "+ fused step per step)"}
 
     cpu_baseline = None
     if world == 1 and not a.no_cpu_baseline:
@@ -473,6 +493,21 @@ def also_configs(formation_gym, torch, device, dtype, peak):
             gbs = env.bytes_per_env_step() * E * env_steps / (ms * 1e-3) / 1e9
             row = {"config": name, "agent_steps_per_s": E * N * env_steps / (ms * 1e-3),
                    "ms_per_env_step": ms / env_steps, "algorithmic_GBps": gbs, "hbm_frac": gbs / peak}
+            if mode == "step":
+                # the fused step kernel alone (actions pre-sampled, CUDA graph of 5 launches: no launch gaps, no
+                # random-policy kernel) -- the figure comparable with the headline's roofline.frac
+                env.sample_actions()
+                g5 = env.capture_steps(5, policy=lambda env_: None)
+                g5.replay(); torch.cuda.synchronize()
+                reps = max(2, steps // 5)
+                e0.record()
+                for _ in range(reps):
+                    g5.replay()
+                e1.record(); torch.cuda.synchronize()
+                kms = e0.elapsed_time(e1) / (5 * reps)
+                row.update({"step_kernel_ms": kms,
+                            "hbm_frac_step_kernel": env.bytes_per_env_step() * E / (kms * 1e-3) / 1e9 / peak})
+                del g5
             if mode == "noobs":
                 # the step+reward kernel without dense observations is pair-compute bound: FP32 roofline
                 tf = flops_per_env_step(N) * E * env_steps / (ms * 1e-3) / 1e12
