@@ -170,7 +170,7 @@ __device__ __forceinline__ void wall_force(const WallT<T>& w, T px, T py, T size
 // FP: fast pair loops of fg_pairs.cuh (fp32, hd, uniform agents, N >= 32): structure-of-arrays partner
 // data, packed FFMA2/FADD2/FMUL2 arithmetic, group filters, warp-shuffle centroid and reductions.
 template <typename T, int SCN, bool PHYS, bool OBSREW, bool HET, int OM, bool FP>
-__global__ void __launch_bounds__(kBlock, (OM == 2 || FP) ? 4 : 3) k_step(const __grid_constant__ KArgs<T> a) {
+__global__ void __launch_bounds__(kBlock, (OM == 3 && SCN == kScnBasic) ? 5 : (OM == 2 || OM == 3 || FP) ? 4 : 3) k_step(const __grid_constant__ KArgs<T> a) {
     typedef Ops<T> O;
     typedef typename O::R2 R2;
     typedef typename O::Bits Bits;
