@@ -67,25 +67,26 @@ __device__ __forceinline__ typename Ops<T>::R2 ezpolicy_dev(const typename Ops<T
 #pragma unroll
     for (int k = 0; k < CAP; ++k)
         if (k < n) d[k] = O::lenkey(O::sub(self.x, ideal[k].x), O::sub(self.y, ideal[k].y));
+    // rank of every landmark in the stable ascending order of d (computed once, not once per candidate)
+    int rank[CAP];
+#pragma unroll
+    for (int k = 0; k < CAP; ++k) {
+        int rk = 0;
+        if (k < n) {
+#pragma unroll
+            for (int j = 0; j < CAP; ++j)
+                if (j < n) rk += (d[j] < d[k] || (d[j] == d[k] && j < k)) ? 1 : 0;
+        }
+        rank[k] = rk;
+    }
     R2 act = O::make((T)0, (T)0);
     bool found = false;
 #pragma unroll
     for (int r = 0; r < CAP; ++r) {                                           // :36-40
         if (r < n && !found) {
-            int idx = 0;
-#pragma unroll
-            for (int k = 0; k < CAP; ++k) {
-                if (k < n) {
-                    int rank = 0;
-#pragma unroll
-                    for (int j = 0; j < CAP; ++j)
-                        if (j < n) rank += (d[j] < d[k] || (d[j] == d[k] && j < k)) ? 1 : 0;
-                    if (rank == r) idx = k;
-                }
-            }
             R2 tg = ideal[0];
 #pragma unroll
-            for (int k = 1; k < CAP; ++k) if (k < n && k == idx) tg = ideal[k];
+            for (int k = 1; k < CAP; ++k) if (k < n && rank[k] == r) tg = ideal[k];
             int closest = 0;
             T best = O::lenkey(O::sub(cur[0].x, tg.x), O::sub(cur[0].y, tg.y));
 #pragma unroll
@@ -140,12 +141,18 @@ __global__ void __launch_bounds__(256) k_policy_bfs(const __grid_constant__ PArg
         s_tv0[t] = a.ivel[e];                                                 // top layer: the env's ideal_vel (:74)
     }
     __syncthreads();
-    const R2* P = s_p + le * N;
-    const R2* S = s_s + le * N;
     int M = N;
+    const int nvalid = min(a.EPC, a.E - blockIdx.x * a.EPC);
     for (int l = 0; l < a.levels; ++l) {
         const int nxt = M / n;
-        if (active && (i % nxt) == 0) {                                       // leaders of this layer (:61)
+        const int nlead = N / nxt;                                            // leaders per env in this layer (:61)
+        // leaders are COMPACTED onto consecutive threads (upper layers have few of them: N / nxt per env), so
+        // a layer costs ceil(envs * leaders / 32) warps instead of every warp of the CTA at 1/nxt efficiency
+        for (int q = t; q < nvalid * nlead; q += kBlock) {
+            const int qe = q / nlead;
+            const int i = (q - qe * nlead) * nxt;
+            const R2* P = s_p + qe * N;
+            const R2* S = s_s + qe * N;
             const int gb = (i / M) * M;                                       // first agent of my group
             const int si = (i - gb) / nxt;                                    // my subgroup within the group
             const R2 pi = P[i];
@@ -158,9 +165,9 @@ __global__ void __launch_bounds__(256) k_policy_bfs(const __grid_constant__ PArg
                 T cx = 0, cy = 0, tx = 0, ty = 0;
                 const int b0 = gb + k * nxt;
                 for (int b = b0; b < b0 + nxt; ++b) {
-                    const R2 q = P[b];
-                    const T rx = (b == i) ? (T)0 : O::sub(q.x, pi.x);         // own slot is the inserted (0,0)
-                    const T ry = (b == i) ? (T)0 : O::sub(q.y, pi.y);
+                    const R2 q2 = P[b];
+                    const T rx = (b == i) ? (T)0 : O::sub(q2.x, pi.x);        // own slot is the inserted (0,0)
+                    const T ry = (b == i) ? (T)0 : O::sub(q2.y, pi.y);
                     cx = O::add(cx, rx); cy = O::add(cy, ry);
                     const R2 sb = S[b];
                     tx = O::add(tx, sb.x); ty = O::add(ty, sb.y);
@@ -178,10 +185,10 @@ __global__ void __launch_bounds__(256) k_policy_bfs(const __grid_constant__ PArg
                     others[k] = O::make(O::sub(c.x, own.x), O::sub(c.y, own.y));
                 }
             }
-            R2 out = ezpolicy_dev<T, NF>(others, tgt, s_tv0[t], n);           // :76-79
+            R2 out = ezpolicy_dev<T, NF>(others, tgt, s_tv0[qe * N + i], n);  // :76-79
             out = O::make(O::mul(out.x, a.mult[l]), O::mul(out.y, a.mult[l]));
-            if (nxt == 1) a.act[g] = out;                                     // :81-83
-            else for (int b = 0; b < nxt; ++b) s_tv1[t + b] = out;            // tar_vel of my subgroup (:84-97)
+            if (nxt == 1) a.act[((size_t)blockIdx.x * a.EPC + qe) * N + i] = out;          // :81-83
+            else for (int b = 0; b < nxt; ++b) s_tv1[qe * N + i + b] = out;   // tar_vel of my subgroup (:84-97)
         }
         __syncthreads();
         R2* tmp = s_tv0; s_tv0 = s_tv1; s_tv1 = tmp;
