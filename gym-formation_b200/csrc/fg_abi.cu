@@ -464,7 +464,12 @@ int policy_bfs_impl(const void* pos, const void* shape, const void* ivel, void* 
     a.pos = (const R2*)pos; a.shape = (const R2*)shape; a.ivel = (const R2*)ivel; a.act = (R2*)act;
     a.E = E; a.N = N; a.n = n; a.levels = levels; a.EPC = fg::kBlock / N; a.magic_n = magic_for(N);
     M = N;
-    for (int l = 0; l < levels; ++l) { a.mult[l] = (T)(std::log((double)M) / std::log((double)n)); M /= n; }   // :78
+    for (int l = 0; l < levels; ++l) {
+        a.mult[l] = (T)(std::log((double)M) / std::log((double)n));                             // :78
+        a.lev_M[l] = M; a.lev_nxt[l] = M / n; a.lev_nlead[l] = N / (M / n);
+        a.mg_M[l] = magic_for(M); a.mg_nxt[l] = magic_for(M / n); a.mg_nlead[l] = magic_for(N / (M / n));
+        M /= n;
+    }
     const size_t smem = (size_t)4 * a.EPC * N * sizeof(R2);
     const int grid = (E + a.EPC - 1) / a.EPC;
     cudaStream_t st = (cudaStream_t)stream;

@@ -26,6 +26,10 @@ template <typename T> struct PArgs {
     int E, N, n, levels, EPC;
     uint32_t magic_n;
     T mult[kPolicyMaxLevels];           // log(M)/log(n) per layer, top first (:78)
+    // per layer (top first): group size M, subgroup size nxt = M / n, leaders per env N / nxt, and the fastdiv
+    // magics of the three divisors (runtime integer divisions were 25 % of the kernel's instructions)
+    int lev_M[kPolicyMaxLevels], lev_nxt[kPolicyMaxLevels], lev_nlead[kPolicyMaxLevels];
+    uint32_t mg_M[kPolicyMaxLevels], mg_nxt[kPolicyMaxLevels], mg_nlead[kPolicyMaxLevels];
 };
 
 // formation_gym/__init__.py:19-47 on the sliced inputs: others [n-1] (other_pos), tgt [n] (ideal_shape
@@ -141,20 +145,19 @@ __global__ void __launch_bounds__(256) k_policy_bfs(const __grid_constant__ PArg
         s_tv0[t] = a.ivel[e];                                                 // top layer: the env's ideal_vel (:74)
     }
     __syncthreads();
-    int M = N;
     const int nvalid = min(a.EPC, a.E - blockIdx.x * a.EPC);
     for (int l = 0; l < a.levels; ++l) {
-        const int nxt = M / n;
-        const int nlead = N / nxt;                                            // leaders per env in this layer (:61)
+        const int M = a.lev_M[l], nxt = a.lev_nxt[l];
+        const int nlead = a.lev_nlead[l];                                     // leaders per env in this layer (:61)
         // leaders are COMPACTED onto consecutive threads (upper layers have few of them: N / nxt per env), so
         // a layer costs ceil(envs * leaders / 32) warps instead of every warp of the CTA at 1/nxt efficiency
         for (int q = t; q < nvalid * nlead; q += kBlock) {
-            const int qe = q / nlead;
+            const int qe = (int)fastdiv((uint32_t)q, a.mg_nlead[l]);
             const int i = (q - qe * nlead) * nxt;
             const R2* P = s_p + qe * N;
             const R2* S = s_s + qe * N;
-            const int gb = (i / M) * M;                                       // first agent of my group
-            const int si = (i - gb) / nxt;                                    // my subgroup within the group
+            const int gb = (int)fastdiv((uint32_t)i, a.mg_M[l]) * M;          // first agent of my group
+            const int si = (int)fastdiv((uint32_t)(i - gb), a.mg_nxt[l]);     // my subgroup within the group
             const R2 pi = P[i];
             R2 cur[CAP], tgt[CAP], others[CAP];
 #pragma unroll
@@ -192,7 +195,6 @@ __global__ void __launch_bounds__(256) k_policy_bfs(const __grid_constant__ PArg
         }
         __syncthreads();
         R2* tmp = s_tv0; s_tv0 = s_tv1; s_tv1 = tmp;
-        M = nxt;
     }
 }
 
