@@ -93,6 +93,7 @@ int fill_args(fg::KArgs<T>& a, const fg_params* p, const fg_buffers* b, int scen
     a.ofloor = (T)p->obstacle_floor; a.ofall = (T)p->obstacle_fall_vy;
     a.num_obs = p->num_obs; a.obs_range = (T)p->obs_range;
     a.magic_n = magic_for(N); a.magic_ipr = magic_for(a.IPR);
+    a.magic_l = magic_for(L); a.magic_np = magic_for((N + 31) & ~31);
     a.act_r2 = p->silent ? 1 : 2;
     a.dt = (T)p->dt; a.keep = (T)(1.0 - p->damping); a.cforce = (T)p->contact_force;
     a.margin = (T)p->contact_margin; a.size = (T)p->agent_size; a.mass = (T)p->mass;

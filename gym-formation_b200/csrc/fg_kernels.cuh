@@ -42,6 +42,7 @@ template <typename T> struct KArgs {
     // sizes
     int E, N, L, EPC, IPR;           // IPR = R2 items per observation row (hd 3N; basic 2+L+2(N-1))
     uint32_t magic_n, magic_ipr;     // fastdiv magics for N and IPR
+    uint32_t magic_l, magic_np;      // ... for L (landmark loops) and roundup(N, 32)
     int act_r2;                      // R2 elements per agent in act (1 silent, 2 with comm action)
     // params in T
     T dt, keep, cforce, margin, size, mass, vmax, u_noise, c_noise;
@@ -255,7 +256,7 @@ __global__ void __launch_bounds__(kBlock, (OM == 3 && SCN == kScnBasic) ? 5 : (O
     if (FP) {
         // neutral pad entries (never a candidate, never a minimum); the live entries are written below
         for (int q = t; q < EPC * NP; q += kBlock) {
-            const int qe = q / NP, qi = q - qe * NP;
+            const int qe = (int)fastdiv((uint32_t)q, a.magic_np), qi = q - qe * NP;
             if (qi >= N) {
                 RO(qe, qi, 0) = 0.f; RO(qe, qi, 1) = 0.f; RO(qe, qi, 2) = INFINITY;
                 RN(qe, qi, 0) = 1e18f; RN(qe, qi, 1) = 1e18f; RN(qe, qi, 2) = INFINITY;
@@ -807,7 +808,7 @@ __global__ void __launch_bounds__(kBlock, (OM == 3 && SCN == kScnBasic) ? 5 : (O
         if (SCN >= kScnPartial) {
             // columns: centred landmark k against all centred agents (one thread per (env, landmark))
             for (int q = t; q < nvalid * L; q += kBlock) {
-                const int qe = q / L;
+                const int qe = (int)fastdiv((uint32_t)q, a.magic_l);
                 const R2 ml = s_mean[2 * qe + 1];
                 const R2 l = s_s[q];
                 const R2 V = O::make(O::sub(l.x, ml.x), O::sub(l.y, ml.y));
@@ -823,7 +824,7 @@ __global__ void __launch_bounds__(kBlock, (OM == 3 && SCN == kScnBasic) ? 5 : (O
         if (SCN == kScnBasic) {
             // reward part 1 (basic_formation_env.py:45-47): min over agents of |p_a - l_k| per landmark
             for (int q = t; q < nvalid * L; q += kBlock) {
-                int qe = q / L;
+                int qe = (int)fastdiv((uint32_t)q, a.magic_l);
                 R2 l = s_s[q];
                 const R2* envp = s_new + qe * N;
                 T m = (T)INFINITY;
@@ -904,7 +905,7 @@ __global__ void __launch_bounds__(kBlock, (OM == 3 && SCN == kScnBasic) ? 5 : (O
                 }
                 if (SCN != kScnHD) {
                     for (int q = t; q < nvalid * L; q += kBlock) {
-                        int qe = q / L, k = q - qe * L;
+                        int qe = (int)fastdiv((uint32_t)q, a.magic_l), k = q - qe * L;
                         if (s_dn[qe]) {
                             U4 r = philox(a.seed, a.env_offset + (uint32_t)(tile0 + qe), (uint32_t)k, tk, kResetLandmark);
                             R2 l = O::make(uniform_pm1<T>(r.x), uniform_pm1<T>(r.y));
@@ -1140,7 +1141,7 @@ __global__ void __launch_bounds__(kBlock, (OM == 3 && SCN == kScnBasic) ? 5 : (O
                             const R2 pi = s_new[row];
                             if (SCN == kScnPartial) {                      // agents i+1 .. i+num_obs, cyclic (:53-55)
                                 int j = ri + 1 + m;
-                                j -= (j / N) * N;
+                                j -= (int)fastdiv((uint32_t)j, a.magic_n) * N;
                                 R2 pj = s_new[rle * N + j];
                                 val = O::make(O::sub(pj.x, pi.x), O::sub(pj.y, pi.y));
                             } else {                                       // all others, clipped to the range (:53)
