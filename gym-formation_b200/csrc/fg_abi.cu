@@ -284,7 +284,7 @@ int launch_obstacle(const fg::KArgs<T>& a, void* stream) {
 // observation-span image per warp).  Computed once per instantiation; all GPUs of a box are alike.
 struct WarpGeom { int ctas[4]; int best; int sms; };      // index: log2(w), w = 1, 2, 4, 8
 
-template <typename T, int N, bool WOBS>
+template <typename T, int N, bool WOBS, int SCN>
 const WarpGeom& warp_geom() {
     static const WarpGeom geom = [] {
         typedef fg::WarpLayout<T, N, WOBS> LY;
@@ -298,10 +298,10 @@ const WarpGeom& warp_geom() {
             const size_t smem = (size_t)w * LY::stride;
             g_.ctas[l] = 0;
             if (smem > 227 * 1024 || w > LY::MAXW) continue;
-            if (cudaFuncSetAttribute(fg::k_hd_warp<T, N, WOBS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+            if (cudaFuncSetAttribute(fg::k_hd_warp<T, N, WOBS, SCN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)smem) != cudaSuccess) { cudaGetLastError(); continue; }
             int ctas = 0;
-            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, fg::k_hd_warp<T, N, WOBS>, 32 * w, smem)
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, fg::k_hd_warp<T, N, WOBS, SCN>, 32 * w, smem)
                 != cudaSuccess) { cudaGetLastError(); continue; }
             g_.ctas[l] = ctas;
             if (ctas * w > best_res) { best_res = ctas * w; g_.best = l; }
@@ -311,17 +311,17 @@ const WarpGeom& warp_geom() {
     return geom;
 }
 
-template <typename T, int N, bool WOBS>
+template <typename T, int N, bool WOBS, int SCN>
 int launch_warp_n(const fg::KArgs<T>& a, cudaStream_t st) {
     typedef fg::WarpLayout<T, N, WOBS> LY;
-    const WarpGeom& gm = warp_geom<T, N, WOBS>();
+    const WarpGeom& gm = warp_geom<T, N, WOBS, SCN>();
     const int spans = (a.E + LY::EPW - 1) / LY::EPW;
     int l = gm.best;
     while (l > 0 && (spans >> l) < 2 * gm.sms) --l;                // small batches: spread over the SMs
     if (gm.ctas[l] < 1) return fail(FG_ERR_CUDA, "k_hd_warp does not fit on this device%s");
     const int w = 1 << l;
     const size_t smem = (size_t)w * LY::stride;
-    cudaError_t err = cudaFuncSetAttribute(fg::k_hd_warp<T, N, WOBS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t err = cudaFuncSetAttribute(fg::k_hd_warp<T, N, WOBS, SCN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            (int)smem);
     if (err != cudaSuccess) return fail(FG_ERR_CUDA, "cudaFuncSetAttribute failed: %s", cudaGetErrorString(err));
     // persistent warps: at most one resident wave; each warp walks spans gw, gw + nwarps, ...
@@ -330,24 +330,29 @@ int launch_warp_n(const fg::KArgs<T>& a, cudaStream_t st) {
     { const char* e_ = getenv("FG_WAVES"); if (e_) wave *= atoi(e_); }
     if (grid > wave) grid = wave;
     if ((grid * w) & 1) ++grid;                                    // even warp count (16-byte phase, fg_warp.cuh)
-    fg::k_hd_warp<T, N, WOBS><<<grid, 32 * w, smem, st>>>(a);
+    fg::k_hd_warp<T, N, WOBS, SCN><<<grid, 32 * w, smem, st>>>(a);
     err = cudaGetLastError();
     if (err != cudaSuccess) return fail(FG_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(err));
     return FG_OK;
 }
 
-template <typename T, int N>
+template <typename T, int N, int SCN = fg::kScnHD>
 int launch_warp(const fg::KArgs<T>& a, cudaStream_t st) {
-    return a.obs ? launch_warp_n<T, N, true>(a, st) : launch_warp_n<T, N, false>(a, st);
+    return a.obs ? launch_warp_n<T, N, true, SCN>(a, st) : launch_warp_n<T, N, false, SCN>(a, st);
 }
 
 // The fast path covers the configurations BASELINE.json names for formation_hd_env with N <= 27.
 template <typename T>
 bool warp_path_ok(const fg::KArgs<T>& a, int scenario, const fg_params* p, const fg_buffers* b) {
-    if (scenario != FG_SCENARIO_HD) return false;
-    if (a.N != 3 && a.N != 9 && a.N != 27) return false;
+    if (scenario == FG_SCENARIO_BASIC) {
+        if (a.N != 3 || a.L != a.N || !b->landmarks) return false;  // the default 3 agents / 3 landmarks
+    } else {
+        if (scenario != FG_SCENARIO_HD) return false;
+        if (a.N != 3 && a.N != 9 && a.N != 27) return false;
+        if (b->landmarks) return false;                             // landmark tracking: tile kernel
+    }
     if (p->agent_mass || p->agent_size_arr || p->agent_accel || p->agent_max_speed) return false;
-    if (p->n_walls != 0 || !p->silent || b->landmarks) return false;
+    if (p->n_walls != 0 || !p->silent) return false;
     if (((uintptr_t)b->obs) % sizeof(typename fg::Ops<T>::R2)) return false;
     const char* force = getenv("FG_FORCE_TILE_KERNEL");            // A/B switch for tests and profiling
     if (force && force[0] == '1') return false;
@@ -403,6 +408,7 @@ int step_fused_impl(const fg_params* p, const fg_buffers* b, int scenario, int E
     if (scenario == FG_SCENARIO_HD_OBSTACLE) return launch_obstacle<T, true>(a, stream);
     if (warp_path_ok<T>(a, scenario, p, b)) {
         cudaStream_t st = (cudaStream_t)stream;
+        if (scenario == FG_SCENARIO_BASIC) return launch_warp<T, 3, fg::kScnBasic>(a, st);
         switch (N) {
             case 3: return launch_warp<T, 3>(a, st);
             case 9: return launch_warp<T, 9>(a, st);

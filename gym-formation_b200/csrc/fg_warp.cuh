@@ -62,8 +62,13 @@ template <typename T, int N, bool WOBS> struct WarpLayout {
     static constexpr size_t stride = (raw + 15) & ~(size_t)15;
 };
 
-template <typename T, int N, bool WOBS>
+// SCN == kScnBasic (basic_formation_env with L == N landmarks, e.g. the default 3 agents / 3 landmarks): the same
+// kernel with lane i doubling as landmark i -- the landmark rides in the `S` slot of the ideal shape, the reward is
+// -sum_k min_a |p_a - l_k| - #{a incl. self : |p_a - p_i| < s_a + s_i} (basic_formation_env.py:43-52), the row is
+// [p_vel, p_pos, l_k - p, p_j - p, comm] (basic_formation_env.py:29-41; also 3N items when L == N).
+template <typename T, int N, bool WOBS, int SCN = kScnHD>
 __global__ void __launch_bounds__(32 * WarpLayout<T, N, WOBS>::MAXW, WarpLayout<T, N, WOBS>::MINB) k_hd_warp(const __grid_constant__ KArgs<T> a) {
+    static_assert(SCN == kScnHD || WarpLayout<T, N, WOBS>::LATE_FILL, "basic rows are written by the late fill");
     typedef Ops<T> O;
     typedef typename O::R2 R2;
     typedef typename O::Bits Bits;
@@ -121,9 +126,9 @@ __global__ void __launch_bounds__(32 * WarpLayout<T, N, WOBS>::MAXW, WarpLayout<
             const size_t fa = (size_t)fe0 * N + lane;
             p_n = a.pos[fa];
             v_n = a.vel[fa];
-            S_n = a.shape[fa];
+            if (SCN == kScnBasic) S_n = a.lm[fa];                          // landmark `lane` of the span (L == N)
+            else { S_n = a.shape[fa]; iv_n = a.ivel[fe0 + le]; }
             if (!a.random_actions) u_n = a.act[fa];
-            iv_n = a.ivel[fe0 + le];
             if (a.step) stp_n = a.step[fe0 + le];
             if (i == 0) {                                                   // running episode statistics of the env
                 if (a.ep_return) epr_n = a.ep_return[fe0 + le];
@@ -234,7 +239,7 @@ __global__ void __launch_bounds__(32 * WarpLayout<T, N, WOBS>::MAXW, WarpLayout<
         // ================= Scenario.reward on the NEW state (formation_hd_env.py:61-75; Q16) =====
         // centroid and mean velocity: one lane per (env, {pos, vel}), summed in agent order like
         // np.mean(axis=0)
-        if (lane < 2 * nval) {
+        if (SCN == kScnHD && lane < 2 * nval) {
             const int qe = lane >> 1, which = lane & 1;
             const R2* src = which ? (s_vel + qe * N) : (s_pnew + qe * 2 * N);
             T sx = 0, sy = 0;
@@ -243,9 +248,9 @@ __global__ void __launch_bounds__(32 * WarpLayout<T, N, WOBS>::MAXW, WarpLayout<
             s_mean[lane] = O::make(O::div_count(sx, N), O::div_count(sy, N));   // np.mean: fp64 divides, fp32 multiplies by 1/N
         }
         __syncwarp();
-        const R2 mp = s_mean[2 * le], mv = s_mean[2 * le + 1];
+        const R2 mp = (SCN == kScnHD) ? s_mean[2 * le] : zero, mv = (SCN == kScnHD) ? s_mean[2 * le + 1] : zero;
         const R2 C = O::make(O::sub(p.x, mp.x), O::sub(p.y, mp.y));         // centred agent shape
-        if (lane < NA) s_cen[lane] = C;
+        if (SCN == kScnHD && lane < NA) s_cen[lane] = C;
         if (WOBS && !LY::LATE_FILL && bulk_pending) {                       // previous image is still being read
             if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
             bulk_pending = false;
@@ -253,6 +258,34 @@ __global__ void __launch_bounds__(32 * WarpLayout<T, N, WOBS>::MAXW, WarpLayout<
         __syncwarp();
 
         int col = 0;
+        if (SCN == kScnBasic) {
+            T* s_lmin = reinterpret_cast<T*>(s_cen);                        // [NA] min_a |p_a - l_k| per landmark
+            if (active) {
+                const R2* eA = s_pnew + le * 2 * N;                         // eA[k] = agent k
+                // reward part 1 (basic_formation_env.py:45-47), lane i <-> landmark i = S
+                T m = (T)INFINITY;
+                bool nan_seen = false;
+                unsigned hit = 0;
+#pragma unroll
+                for (int k = 0; k < N; ++k) {
+                    R2 q = eA[k];
+                    T d = O::norm2(O::sub(q.x, S.x), O::sub(q.y, S.y));
+                    nan_seen |= (d != d);
+                    m = fmin(m, d);
+                    // is_collision candidates, self included (basic_formation_env.py:48-51,89-91)
+                    T dx = O::sub(q.x, p.x), dy = O::sub(q.y, p.y);
+                    hit |= (dx * dx + dy * dy < a.rthr2_hi) ? (1u << k) : 0u;
+                }
+                s_lmin[lane] = nan_seen ? O::from_bits(~(Bits)0 >> 1) : m;
+                while (a.collide && hit) {
+                    const int k = __ffs(hit) - 1;
+                    hit &= hit - 1;
+                    R2 q = eA[k];
+                    if (O::norm2(O::sub(q.x, p.x), O::sub(q.y, p.y)) < a.rthr) ++col;
+                }
+                if (col) atomicAdd(&s_col[le], col);
+            }
+        } else
         if (active) {
             const R2* eS = s_shp + le * N;
             const R2* eC = s_cen + le * N;
@@ -302,10 +335,18 @@ __global__ void __launch_bounds__(32 * WarpLayout<T, N, WOBS>::MAXW, WarpLayout<
         stp += 1;                                                           // environment.py:114
         const bool dn = active && a.step && (stp >= a.world_length);
         if (active) {
-            T form = -O::sqrt_(O::from_bits(s_max[le]));                    // -max(dH(C,S), dH(S,C))
-            if (env_bad) form = O::from_bits(~(Bits)0 >> 1);                // NaN, as the reference
-            T velr = O::norm2(O::sub(iv.x, mv.x), O::sub(iv.y, mv.y));      // formation_hd_env.py:68-69
-            T base = O::sub(form, velr);
+            T base;
+            if (SCN == kScnBasic) {
+                const T* s_lmin = reinterpret_cast<const T*>(s_cen) + le * N;
+                base = (T)0;
+#pragma unroll
+                for (int k = 0; k < N; ++k) base = O::sub(base, s_lmin[k]);  // rew -= min(dists), landmark order
+            } else {
+                T form = -O::sqrt_(O::from_bits(s_max[le]));                // -max(dH(C,S), dH(S,C))
+                if (env_bad) form = O::from_bits(~(Bits)0 >> 1);            // NaN, as the reference
+                T velr = O::norm2(O::sub(iv.x, mv.x), O::sub(iv.y, mv.y));  // formation_hd_env.py:68-69
+                base = O::sub(form, velr);
+            }
             T r = base;
             for (int c = 0; c < col; ++c) r = O::sub(r, (T)1);              // rew -= 1 per collision
             const int coltot = s_col[le];
@@ -340,16 +381,23 @@ __global__ void __launch_bounds__(32 * WarpLayout<T, N, WOBS>::MAXW, WarpLayout<
                 v = zero;
                 U4 q = philox(a.seed, ge, (uint32_t)i, tk, kResetLandmark);
                 lraw = O::make(uniform_pm1<T>(q.x), uniform_pm1<T>(q.y));
-                U4 w = philox(a.seed, ge, 0u, tk, kResetIdealVel);
-                iv = O::make(uniform_pm1<T>(w.x), uniform_pm1<T>(w.y));
-                s_pold[lane] = lraw;                                        // scratch: pold is dead until the next step
                 s_pnew[le * 2 * N + i] = p;
                 s_pnew[le * 2 * N + N + i] = p;
-                if (i == 0) a.ivel[e] = iv;
                 stp = 0;
+                if (SCN == kScnBasic) {                                     // basic_formation_env.py:54-65: no shape, no ideal_vel
+                    S = lraw;
+                    s_shp[lane] = S;
+                    a.lm[g] = S;
+                    if (ts == a.n_steps - 1) { a.pos[g] = p; a.vel[g] = v; }
+                } else {
+                    U4 w = philox(a.seed, ge, 0u, tk, kResetIdealVel);
+                    iv = O::make(uniform_pm1<T>(w.x), uniform_pm1<T>(w.y));
+                    s_pold[lane] = lraw;                                    // scratch: pold is dead until the next step
+                    if (i == 0) a.ivel[e] = iv;
+                }
             }
             __syncwarp();
-            if (dn) {
+            if (SCN == kScnHD && dn) {
                 const R2* raw = s_pold + le * N;
                 T sx = 0, sy = 0;
                 for (int j = 0; j < N; ++j) { sx = O::add(sx, raw[j].x); sy = O::add(sy, raw[j].y); }
@@ -381,17 +429,26 @@ __global__ void __launch_bounds__(32 * WarpLayout<T, N, WOBS>::MAXW, WarpLayout<
                 const R2* eP = s_pnew + le * 2 * N + i;                     // eP[k] = agent (i + k) mod N
                 const R2* eS = s_shp + le * N;
                 row[0] = v;
+                // basic: [p_vel, p_pos, l_k - p (L = N), other_pos, comm] (basic_formation_env.py:29-41)
+                constexpr int OFF = (SCN == kScnBasic) ? 1 + N : 0;         // other_pos starts at 1 + OFF
+                if (SCN == kScnBasic) {
+                    row[1] = p;
+#pragma unroll
+                    for (int k = 0; k < N; ++k) { R2 l = eS[k]; row[2 + k] = O::make(O::sub(l.x, p.x), O::sub(l.y, p.y)); }
+                }
 #pragma unroll
                 for (int k = 1; k < N; ++k) {
                     R2 q = eP[k];
                     const int slot = (i + k < N) ? (i + k) : (i + k - N + 1);
-                    row[slot] = O::make(O::sub(q.x, p.x), O::sub(q.y, p.y));   // other_pos (formation_hd_env.py:55)
+                    row[OFF + slot] = O::make(O::sub(q.x, p.x), O::sub(q.y, p.y));   // other_pos (formation_hd_env.py:55)
                 }
 #pragma unroll
-                for (int k = 0; k < N - 1; ++k) row[N + k] = zero;          // comm of the others (silent)
+                for (int k = 0; k < N - 1; ++k) row[OFF + N + k] = zero;    // comm of the others (silent)
+                if (SCN == kScnHD) {
 #pragma unroll
-                for (int k = 0; k < N; ++k) row[2 * N - 1 + k] = eS[k];
-                row[3 * N - 1] = iv;
+                    for (int k = 0; k < N; ++k) row[2 * N - 1 + k] = eS[k];
+                    row[3 * N - 1] = iv;
+                }
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // generic-proxy writes -> async proxy
             __syncwarp();

@@ -507,3 +507,59 @@ def test_misaligned_vector_buffers_are_rejected():
     env._bufs = env._make_buffers()
     with pytest.raises(nat.NativeError, match="aligned"):
         env.step_random()
+
+
+def _run_basic(E, dtype, steps, force_tile, rollout=False, u_noise=None):
+    os.environ["FG_FORCE_TILE_KERNEL"] = "1" if force_tile else "0"
+    try:
+        env = BatchedFormationEnv("basic_formation_env", E, 3, episode_length=7, dtype=dtype, seed=13,
+                                  auto_reset=True, u_noise=u_noise)
+        env.reset()
+        env.pos.mul_(0.3)                       # agents of size 0.1: contacts and collisions occur
+        hist = []
+        if rollout:
+            env.rollout_random(steps)
+        else:
+            for _ in range(steps):
+                obs, rew, done, info = env.step_random()
+                hist.append((rew[:, 0, 0].clone(), done[:, 0].clone(), info["individual_reward"].clone()))
+        torch.cuda.synchronize()
+        out = {k: getattr(env, k).clone() for k in ("pos", "vel", "obs", "reward", "indiv", "landmarks", "step_count",
+                                                    "ep_return", "ep_collisions", "stats")}
+        out["done"] = env.done.clone()
+        return out, hist
+    finally:
+        os.environ.pop("FG_FORCE_TILE_KERNEL", None)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64], ids=["f32", "f64"])
+@pytest.mark.parametrize("E", [1, 10, 1001])
+def test_basic_warp_kernel_matches_tile_kernel(E, dtype):
+    """basic_formation_env (3 agents / 3 landmarks) on the warp-autonomous kernel (fg_warp.cuh, SCN = basic) against
+    the tile kernel: bit-exact in fp64 over 16 steps with two auto-resets (landmarks redrawn), a few ulp in fp32;
+    the in-kernel rollout equals the stepwise one; motor noise uses the same Philox counters."""
+    a, ha = _run_basic(E, dtype, 16, force_tile=False)
+    b, hb = _run_basic(E, dtype, 16, force_tile=True)
+    for k in a:
+        if dtype == torch.float64 or not a[k].is_floating_point():
+            if k == "stats":
+                assert torch.allclose(a[k], b[k], rtol=1e-12), k
+            else:
+                assert torch.equal(a[k], b[k]), k
+        else:
+            ref = b[k].double().cpu().numpy()
+            assert maxerr(a[k], ref) <= 2e-5 * max(1.0, float(np.abs(ref).max())), k
+    assert float(a["stats"][0]) == 2 * E
+    assert int(a["ep_collisions"].sum()) > 0 or E < 10
+    for (ra, da, ia), (rb, db, ib) in zip(ha, hb):
+        assert torch.equal(da, db)
+        if dtype == torch.float64:
+            assert torch.equal(ra, rb) and torch.equal(ia, ib)
+    c, _ = _run_basic(E, dtype, 16, force_tile=False, rollout=True)
+    for k in a:
+        assert torch.allclose(a[k], c[k], rtol=1e-12) if k == "stats" else torch.equal(a[k], c[k]), k
+    if dtype == torch.float64:
+        n1, _ = _run_basic(E, dtype, 5, force_tile=False, u_noise=0.2)
+        n2, _ = _run_basic(E, dtype, 5, force_tile=True, u_noise=0.2)
+        for k in ("pos", "vel", "obs", "reward"):
+            assert torch.equal(n1[k], n2[k]), k
