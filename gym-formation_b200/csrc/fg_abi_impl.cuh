@@ -1,4 +1,7 @@
-// fg_abi.cu -- extern "C" entry points declared in include/formation_gym_b200.h.
+#pragma once
+// fg_abi_impl.cuh -- implementation of the extern "C" entry points declared in include/formation_gym_b200.h,
+// templated on the real type; fg_abi_f32.cu / fg_abi_f64.cu instantiate one precision each (two translation units,
+// compiled in parallel by formation_gym/_build.py).
 // Validates arguments, converts fg_params (double) into the kernels' typed argument block and
 // launches asynchronously on the caller's stream.  No allocation, no global state, no sync.
 #include <cstdio>
@@ -14,9 +17,11 @@
 #include "fg_obstacle.cuh"
 #include "fg_policy.cuh"
 
+namespace fgabi { extern thread_local char g_err[512]; }      // defined in fg_abi_f32.cu, shared by both precisions
+
 namespace {
 
-thread_local char g_err[512] = "";
+using fgabi::g_err;
 
 int fail(int code, const char* fmt, const char* detail = "") {
     snprintf(g_err, sizeof(g_err), fmt, detail);
@@ -348,7 +353,7 @@ bool warp_path_ok(const fg::KArgs<T>& a, int scenario, const fg_params* p, const
         if (a.N != 3 || a.L != a.N || !b->landmarks) return false;  // the default 3 agents / 3 landmarks
     } else {
         if (scenario != FG_SCENARIO_HD) return false;
-        if (a.N != 3 && a.N != 9 && a.N != 27) return false;
+        if (a.N != 3 && a.N != 4 && a.N != 5 && a.N != 8 && a.N != 9 && a.N != 16 && a.N != 27) return false;
         if (b->landmarks) return false;                             // landmark tracking: tile kernel
     }
     if (p->agent_mass || p->agent_size_arr || p->agent_accel || p->agent_max_speed) return false;
@@ -411,7 +416,11 @@ int step_fused_impl(const fg_params* p, const fg_buffers* b, int scenario, int E
         if (scenario == FG_SCENARIO_BASIC) return launch_warp<T, 3, fg::kScnBasic>(a, st);
         switch (N) {
             case 3: return launch_warp<T, 3>(a, st);
+            case 4: return launch_warp<T, 4>(a, st);
+            case 5: return launch_warp<T, 5>(a, st);
+            case 8: return launch_warp<T, 8>(a, st);
             case 9: return launch_warp<T, 9>(a, st);
+            case 16: return launch_warp<T, 16>(a, st);
             default: return launch_warp<T, 27>(a, st);
         }
     }
@@ -493,85 +502,3 @@ int policy_bfs_impl(const void* pos, const void* shape, const void* ivel, void* 
 
 }  // namespace
 
-extern "C" {
-
-int fg_policy_bfs(const void* pos, const void* ideal_shape, const void* ideal_vel, void* act, int E, int N,
-                  int num_agents_per_layer, void* stream) {
-    return policy_bfs_impl<float>(pos, ideal_shape, ideal_vel, act, E, N, num_agents_per_layer, stream);
-}
-int fg_policy_bfs_f64(const void* pos, const void* ideal_shape, const void* ideal_vel, void* act, int E, int N,
-                      int num_agents_per_layer, void* stream) {
-    return policy_bfs_impl<double>(pos, ideal_shape, ideal_vel, act, E, N, num_agents_per_layer, stream);
-}
-
-int fg_abi_version(void) { return FG_ABI_VERSION; }
-
-const char* fg_last_error(void) { return g_err; }
-
-int fg_device_info(int* sm_count, int* cc_major, int* cc_minor) {
-    int dev = 0;
-    cudaError_t err = cudaGetDevice(&dev);
-    cudaDeviceProp prop;
-    if (err == cudaSuccess) err = cudaGetDeviceProperties(&prop, dev);
-    if (err != cudaSuccess) return fail(FG_ERR_CUDA, "fg_device_info: %s", cudaGetErrorString(err));
-    if (sm_count) *sm_count = prop.multiProcessorCount;
-    if (cc_major) *cc_major = prop.major;
-    if (cc_minor) *cc_minor = prop.minor;
-    return FG_OK;
-}
-
-int fg_launch_geometry(int N, int* envs_per_cta, int* threads_per_cta) {
-    if (N < 1 || N > FG_MAX_AGENTS) return fail(FG_ERR_ARG, "N must be in [1, FG_MAX_AGENTS=256]%s");
-    if (envs_per_cta) *envs_per_cta = fg::kBlock / N;
-    if (threads_per_cta) *threads_per_cta = fg::kBlock;
-    return FG_OK;
-}
-
-int fg_world_step(const fg_params* p, const fg_buffers* b, int E, int N, uint64_t seed, uint32_t tick,
-                  uint32_t env_offset, void* stream) {
-    return world_step_impl<float>(p, b, E, N, seed, tick, env_offset, stream);
-}
-int fg_world_step_f64(const fg_params* p, const fg_buffers* b, int E, int N, uint64_t seed, uint32_t tick,
-                      uint32_t env_offset, void* stream) {
-    return world_step_impl<double>(p, b, E, N, seed, tick, env_offset, stream);
-}
-
-int fg_obs_reward(const fg_params* p, const fg_buffers* b, int scenario, int E, int N, int L, void* stream) {
-    return obs_reward_impl<float>(p, b, scenario, E, N, L, stream);
-}
-int fg_obs_reward_f64(const fg_params* p, const fg_buffers* b, int scenario, int E, int N, int L, void* stream) {
-    return obs_reward_impl<double>(p, b, scenario, E, N, L, stream);
-}
-
-int fg_step_fused(const fg_params* p, const fg_buffers* b, int scenario, int E, int N, int L, int n_steps,
-                  int random_actions, int auto_reset, uint64_t seed, uint32_t tick, uint32_t env_offset,
-                  void* stream) {
-    return step_fused_impl<float>(p, b, scenario, E, N, L, n_steps, random_actions, auto_reset, seed, tick,
-                                  env_offset, stream);
-}
-int fg_step_fused_f64(const fg_params* p, const fg_buffers* b, int scenario, int E, int N, int L, int n_steps,
-                      int random_actions, int auto_reset, uint64_t seed, uint32_t tick, uint32_t env_offset,
-                      void* stream) {
-    return step_fused_impl<double>(p, b, scenario, E, N, L, n_steps, random_actions, auto_reset, seed, tick,
-                                   env_offset, stream);
-}
-
-int fg_reset(const fg_params* p, const fg_buffers* b, int scenario, int E, int N, int L, const uint8_t* mask,
-             uint64_t seed, uint32_t tick, uint32_t env_offset, void* stream) {
-    return reset_impl<float>(p, b, scenario, E, N, L, mask, seed, tick, env_offset, stream);
-}
-int fg_reset_f64(const fg_params* p, const fg_buffers* b, int scenario, int E, int N, int L, const uint8_t* mask,
-                 uint64_t seed, uint32_t tick, uint32_t env_offset, void* stream) {
-    return reset_impl<double>(p, b, scenario, E, N, L, mask, seed, tick, env_offset, stream);
-}
-
-int fg_random_actions(void* act, int E, int N, uint64_t seed, uint32_t tick, uint32_t env_offset,
-                      const uint32_t* tick_dev, void* stream) {
-    return random_actions_impl<float>(act, E, N, seed, tick, env_offset, tick_dev, stream);
-}
-int fg_random_actions_f64(void* act, int E, int N, uint64_t seed, uint32_t tick, uint32_t env_offset,
-                          const uint32_t* tick_dev, void* stream) {
-    return random_actions_impl<double>(act, E, N, seed, tick, env_offset, tick_dev, stream);
-}
-
-}  // extern "C"
