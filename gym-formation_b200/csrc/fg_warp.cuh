@@ -37,8 +37,8 @@ template <typename T, int N, bool WOBS> struct WarpLayout {
     // shared memory caps the SM at 12 warps anyway: 4-warp CTAs let ptxas use up to 255 registers (with
     // 256-thread bounds it stopped at 128 and spilled two, and with ~2 KB of L1 left beside the shared
     // memory every spill reload went to L2 -- 34 % of all stall samples in profiles/r01c_warp27_before).
-    static constexpr int MAXW = (N >= 27) ? 4 : 8;
-    static constexpr int MINB = (N >= 27) ? 0 : 3;
+    static constexpr int MAXW = (N >= 16) ? 4 : 8;
+    static constexpr int MINB = (N >= 16) ? 0 : 3;
     // Where the observation image is filled.  LATE (after rewards / auto-reset, from the shared state):
     // the bulk copy of the previous span has the whole step to finish reading the image, at the price of
     // re-reading the partner positions (measured: N = 3 91.1 -> 86.9 us per 1 M envs, N = 27 246 -> 241 us
@@ -429,6 +429,27 @@ __global__ void __launch_bounds__(32 * WarpLayout<T, N, WOBS>::MAXW, WarpLayout<
                 const R2* eP = s_pnew + le * 2 * N + i;                     // eP[k] = agent (i + k) mod N
                 const R2* eS = s_shp + le * N;
                 row[0] = v;
+                if constexpr (SCN == kScnHD && (N & 1) == 0) {
+                    // EVEN N: the row stride 3N items is a multiple of 8 (N = 4), 16 (N = 8) or 32 (N = 16) banks,
+                    // so "every lane writes item k of its row" would hit 4 / 2 / 1 banks.  Each lane instead walks
+                    // every row segment in an order rotated by its lane index (runtime indices, 2-3 way conflicts
+                    // at worst): N = 16 173 -> see DESIGN.md.
+                    const R2* eA = s_pnew + le * 2 * N;                     // eA[j] = agent j
+                    const int r1 = lane % (N - 1), rN = lane % N;
+#pragma unroll
+                    for (int m = 0; m < N - 1; ++m) {
+                        int mm = m + r1; mm -= (mm >= N - 1) ? (N - 1) : 0;
+                        R2 q = eA[mm + (mm >= i ? 1 : 0)];                  // partner of slot mm: j != i ascending
+                        row[1 + mm] = O::make(O::sub(q.x, p.x), O::sub(q.y, p.y));
+                        row[N + mm] = zero;                                 // comm of the others (silent)
+                    }
+#pragma unroll
+                    for (int k = 0; k < N; ++k) {
+                        int kk = k + rN; kk -= (kk >= N) ? N : 0;
+                        row[2 * N - 1 + kk] = eS[kk];
+                    }
+                    row[3 * N - 1] = iv;
+                } else {
                 // basic: [p_vel, p_pos, l_k - p (L = N), other_pos, comm] (basic_formation_env.py:29-41)
                 constexpr int OFF = (SCN == kScnBasic) ? 1 + N : 0;         // other_pos starts at 1 + OFF
                 if (SCN == kScnBasic) {
@@ -448,6 +469,7 @@ __global__ void __launch_bounds__(32 * WarpLayout<T, N, WOBS>::MAXW, WarpLayout<
 #pragma unroll
                     for (int k = 0; k < N; ++k) row[2 * N - 1 + k] = eS[k];
                     row[3 * N - 1] = iv;
+                }
                 }
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // generic-proxy writes -> async proxy
