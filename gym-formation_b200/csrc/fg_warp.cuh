@@ -307,6 +307,9 @@ __global__ void __launch_bounds__(32 * WarpLayout<T, N, WOBS>::MAXW, WarpLayout<
                     R2 q = eP[k];
                     T dx = O::sub(q.x, p.x), dy = O::sub(q.y, p.y);         // other_pos (formation_hd_env.py:55)
                     if (FUSE) {
+                        // (a slot-ordered variant -- same store offset in every lane, partner index at run time --
+                        // removes the 4-way store conflicts of this order but was measured slower at N = 9:
+                        // 59.4 vs 53.6 us per 131072 envs)
                         const int slot = (i + k < N) ? (i + k) : (i + k - N + 1);
                         row[slot] = O::make(dx, dy);
                     }
@@ -457,11 +460,11 @@ __global__ void __launch_bounds__(32 * WarpLayout<T, N, WOBS>::MAXW, WarpLayout<
 #pragma unroll
                     for (int k = 0; k < N; ++k) { R2 l = eS[k]; row[2 + k] = O::make(O::sub(l.x, p.x), O::sub(l.y, p.y)); }
                 }
+                const R2* eA = s_pnew + le * 2 * N;                         // eA[j] = agent j
 #pragma unroll
-                for (int k = 1; k < N; ++k) {
-                    R2 q = eP[k];
-                    const int slot = (i + k < N) ? (i + k) : (i + k - N + 1);
-                    row[OFF + slot] = O::make(O::sub(q.x, p.x), O::sub(q.y, p.y));   // other_pos (formation_hd_env.py:55)
+                for (int m = 0; m < N - 1; ++m) {                           // slot order: same store offset in every lane
+                    R2 q = eA[m + (m >= i ? 1 : 0)];
+                    row[OFF + 1 + m] = O::make(O::sub(q.x, p.x), O::sub(q.y, p.y));   // other_pos (formation_hd_env.py:55)
                 }
 #pragma unroll
                 for (int k = 0; k < N - 1; ++k) row[OFF + N + k] = zero;    // comm of the others (silent)
