@@ -265,7 +265,7 @@ int launch(const fg::KArgs<T>& a, int scenario, const fg_params* p, void* stream
 
 
 // formation_hd_obs_env (fg_obstacle.cuh)
-template <typename T, bool PHYS>
+template <typename T, bool PHYS, bool OBSREW = true>
 int launch_obstacle(const fg::KArgs<T>& a, void* stream) {
     typedef typename fg::Ops<T>::R2 R2;
     typedef typename fg::Ops<T>::Bits Bits;
@@ -274,11 +274,11 @@ int launch_obstacle(const fg::KArgs<T>& a, void* stream) {
                   + a.EPC * sizeof(Bits) + 3 * a.EPC * sizeof(int);
     smem = (smem + 15) & ~(size_t)15;
     if (smem > 48 * 1024) {
-        cudaError_t e1 = cudaFuncSetAttribute(fg::k_step_obst<T, PHYS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e1 = cudaFuncSetAttribute(fg::k_step_obst<T, PHYS, OBSREW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e1 != cudaSuccess) return fail(FG_ERR_CUDA, "cudaFuncSetAttribute failed: %s", cudaGetErrorString(e1));
     }
     const int grid = (a.E + a.EPC - 1) / a.EPC;
-    fg::k_step_obst<T, PHYS><<<grid, fg::kBlock, smem, (cudaStream_t)stream>>>(a);
+    fg::k_step_obst<T, PHYS, OBSREW><<<grid, fg::kBlock, smem, (cudaStream_t)stream>>>(a);
     cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess) return fail(FG_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(err));
     return FG_OK;
@@ -368,6 +368,14 @@ template <typename T>
 int world_step_impl(const fg_params* p, const fg_buffers* b, int E, int N, uint64_t seed, uint32_t tick,
                     uint32_t env_offset, void* stream) {
     fg::KArgs<T> a;
+    if (p && p->num_obstacles > 0) {
+        // World.step on a world with movable colliding landmarks (formation_hd_obs_env's obstacles)
+        int rc = fill_args<T>(a, p, b, FG_SCENARIO_HD_OBSTACLE, E, N, p->num_landmarks, seed, tick, env_offset);
+        if (rc) return rc;
+        if (!b->pos || !b->vel || !b->act || !b->landmarks)
+            return fail(FG_ERR_ARG, "fg_world_step: pos/vel/act/landmarks must be non-null%s");
+        return launch_obstacle<T, true, false>(a, stream);
+    }
     // the physics does not depend on the scenario; hd's N>=3 rule must not apply here
     int rc = fill_args<T>(a, p, b, FG_SCENARIO_BASIC, E, N, 1, seed, tick, env_offset);
     if (rc) return rc;

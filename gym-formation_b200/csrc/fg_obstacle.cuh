@@ -33,8 +33,11 @@ __device__ __forceinline__ void obstacle_reset(uint64_t seed, uint32_t ge, int s
     *vel = Ops<T>::make((T)0, fall_vy);
 }
 
-template <typename T, bool PHYS>
+// OBSREW = false: World.step alone (core.py:206-225) on a world with obstacles -- no scenario hooks, so the
+// obstacles keep their INTEGRATED velocity (the (0, -1) rule is the reward hook's side effect).
+template <typename T, bool PHYS, bool OBSREW = true>
 __global__ void __launch_bounds__(kBlock, 2) k_step_obst(const __grid_constant__ KArgs<T> a) {
+    static_assert(PHYS || OBSREW, "nothing to do");
     typedef Ops<T> O_;
     typedef typename O_::R2 R2;
     typedef typename O_::Bits Bits;
@@ -196,7 +199,13 @@ __global__ void __launch_bounds__(kBlock, 2) k_step_obst(const __grid_constant__
                 ov.x = O_::add(ov.x, O_::mul(O_::div(Fx, a.omass), a.dt));
                 ov.y = O_::add(ov.y, O_::mul(O_::div(Fy, a.omass), a.dt));
                 s_on[q] = O_::make(O_::add(po.x, O_::mul(ov.x, a.dt)), O_::add(po.y, O_::mul(ov.y, a.dt)));
+                if (!OBSREW) {                                                   // World.step alone: write back and leave
+                    const size_t gi = (size_t)(tile0 + qe) * L + LG + k;
+                    a.lm[gi] = s_on[q];
+                    if (a.lmv) a.lmv[gi] = ov;
+                }
             }
+            if (!OBSREW) { tick_arrive(a.tick_dev, gridDim.x, a.n_steps, t == 0); return; }
             __syncthreads();
         }
 

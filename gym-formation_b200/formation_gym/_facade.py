@@ -141,8 +141,8 @@ class FacadeBackend(object):
                   and len({(float(l.size), float(l.mass)) for l in obstacles}) == 1)
             if not ok:
                 raise NotImplementedError(
-                    "movable / colliding landmarks are supported as the trailing, uniform obstacles of the "
-                    "formation_hd_obs_env scenario hooks only (fg_step_fused / fg_obs_reward)")
+                    "movable / colliding landmarks are supported as the trailing, uniform obstacles of a world "
+                    "(formation_hd_obs_env layout: goal landmarks first, obstacles last, one size and mass)")
         elif scenario_kind == nat.FG_SCENARIO_HD_OBSTACLE and len(world.landmarks) < 1:
             raise NotImplementedError("formation_hd_obs_env needs at least one goal landmark")
         collide, _ = _uniform([bool(a.collide) for a in agents], "collide")
@@ -170,7 +170,7 @@ class FacadeBackend(object):
             world_length=world.world_length, walls=walls, action_prescaled=prescaled,
             num_obs=getattr(scenario, "num_obs", 0) or 0, obs_range=getattr(scenario, "obs_range", 0.0) or 0.0,
             num_obstacles=n_obst, obstacle_size=float(obstacles[0].size) if n_obst else 0.15,
-            obstacle_mass=float(obstacles[0].mass) if n_obst else 1.0)
+            obstacle_mass=float(obstacles[0].mass) if n_obst else 1.0, num_landmarks=len(world.landmarks))
         self._n_obst = n_obst
         self._keep = []
         for field, arr in (("agent_mass", mass_arr), ("agent_size_arr", size_arr),
@@ -239,21 +239,27 @@ class FacadeBackend(object):
 
     # ------------------------------------------------------------------ World.step
     def world_step(self, world):
-        """core.py:206-225 on the GPU; ``agent.action.u`` is already scaled (action_prescaled)."""
-        p, silent = self._params(world, nat.FG_SCENARIO_BASIC, True)
+        """core.py:206-225 on the GPU; ``agent.action.u`` is already scaled (action_prescaled).  A world whose
+        trailing landmarks are movable colliders (formation_hd_obs_env's obstacles) steps them too."""
+        has_obst = any(l.movable or l.collide for l in world.landmarks)
+        p, silent = self._params(world, nat.FG_SCENARIO_HD_OBSTACLE if has_obst else nat.FG_SCENARIO_BASIC, True)
         self._stage_state(world)
+        if has_obst:
+            self._stage_scenario(world, None, nat.FG_SCENARIO_HD_OBSTACLE)
         U = np.stack([np.asarray(a.action.u, np.float64) for a in world.agents])
         Cact = None if silent else np.stack([np.asarray(a.action.c, np.float64) for a in world.agents])
         self._stage_actions(U, silent, Cact)
-        b = self._buffers(nat.FG_SCENARIO_BASIC, False)
+        b = self._buffers(nat.FG_SCENARIO_HD_OBSTACLE if has_obst else nat.FG_SCENARIO_BASIC, False)
         fn = getattr(self.lib, "fg_world_step" + self.sfx)
         with torch.cuda.device(self.device):
             self._h2d()
             nat.check(fn(C.byref(p), C.byref(b), 1, self.N, int(world.seed) & (2 ** 64 - 1),
                          int(world.world_step) & 0xFFFFFFFF, 0, self._stream()), "fg_world_step")
-            self._d2h("comm")
+            self._d2h("lmv" if has_obst else "comm")
         self.launches += 1
         self._scatter_state(world)
+        if has_obst:
+            self._scatter_obstacles(world, with_pos=True)        # integrated velocities: no reward hook ran
         self._cache_key = None
 
     # ------------------------------------------------------------------ scenario hooks

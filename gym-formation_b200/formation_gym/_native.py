@@ -8,7 +8,7 @@ import os
 
 from . import _build
 
-FG_ABI_VERSION = 5
+FG_ABI_VERSION = 6
 FG_MAX_AGENTS = 256
 FG_MAX_LANDMARKS = 256
 FG_MAX_WALLS = 8
@@ -46,6 +46,7 @@ class fg_params(C.Structure):
         ("has_accel", C.c_int32), ("has_max_speed", C.c_int32), ("collide", C.c_int32),
         ("silent", C.c_int32), ("world_length", C.c_int32), ("n_walls", C.c_int32),
         ("action_prescaled", C.c_int32), ("num_obs", C.c_int32), ("num_obstacles", C.c_int32),
+        ("num_landmarks", C.c_int32),
         ("agent_mass", C.c_void_p), ("agent_size_arr", C.c_void_p),
         ("agent_accel", C.c_void_p), ("agent_max_speed", C.c_void_p),
         ("walls", fg_wall * FG_MAX_WALLS),
@@ -117,7 +118,7 @@ def make_params(dt=0.1, damping=0.25, contact_force=1e2, contact_margin=1e-3, se
                 agent_size=0.03, mass=1.0, accel=None, max_speed=None, u_noise=None, c_noise=None,
                 collide=True, silent=True, world_length=100, walls=(), action_prescaled=False,
                 num_obs=0, obs_range=0.0, num_obstacles=0, obstacle_size=0.15, obstacle_mass=1.0,
-                obstacle_floor=-2.2, obstacle_fall_vy=-1.0):
+                obstacle_floor=-2.2, obstacle_fall_vy=-1.0, num_landmarks=0):
     """fg_params from World/Agent attributes (formation_gym/core.py:45-139 defaults)."""
     p = fg_params()
     p.dt, p.damping, p.contact_force, p.contact_margin = dt, damping, contact_force, contact_margin
@@ -133,6 +134,7 @@ def make_params(dt=0.1, damping=0.25, contact_force=1e2, contact_margin=1e-3, se
     p.num_obs, p.obs_range = int(num_obs), float(obs_range)
     p.num_obstacles, p.obstacle_size, p.obstacle_mass = int(num_obstacles), float(obstacle_size), float(obstacle_mass)
     p.obstacle_floor, p.obstacle_fall_vy = float(obstacle_floor), float(obstacle_fall_vy)
+    p.num_landmarks = int(num_landmarks)
     walls = list(walls)
     if len(walls) > FG_MAX_WALLS:
         raise NativeError("at most %d walls are supported" % FG_MAX_WALLS)

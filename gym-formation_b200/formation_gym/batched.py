@@ -114,7 +114,7 @@ class BatchedFormationEnv:
             collide=collide, silent=silent, world_length=self.world_length, walls=walls,
             num_obs=self.num_obs, obs_range=self.obs_range, num_obstacles=self.num_obstacles,
             obstacle_size=obstacle_size, obstacle_mass=obstacle_mass, obstacle_floor=obstacle_floor,
-            obstacle_fall_vy=obstacle_fall_vy)
+            obstacle_fall_vy=obstacle_fall_vy, num_landmarks=self.L)
         kw = dict(device=self.device, dtype=dtype)
         E, N, L = self.E, self.N, self.L
         # optional per-agent arrays (kept alive here; the params struct stores raw pointers)

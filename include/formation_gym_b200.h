@@ -42,7 +42,7 @@
 extern "C" {
 #endif
 
-#define FG_ABI_VERSION 5
+#define FG_ABI_VERSION 6
 #define FG_MAX_AGENTS 256      /* one CTA holds at least one whole env; 3^5 = 243 fits */
 #define FG_MAX_LANDMARKS 256
 #define FG_MAX_WALLS 8
@@ -104,6 +104,9 @@ typedef struct fg_params {
     int32_t num_obs;           /* FG_SCENARIO_HD_PARTIAL: Scenario.num_obs (formation_hd_partial_env.py:15) */
     int32_t num_obstacles;     /* FG_SCENARIO_HD_OBSTACLE: Scenario.num_obstacles (formation_hd_obs_env.py:14); the
                                   entry points' L counts goal landmarks + obstacles */
+    int32_t num_landmarks;     /* fg_world_step only (it has no L argument): entries per env of `landmarks` /
+                                  `landmark_vel` when num_obstacles > 0 -- World.step on a world whose trailing
+                                  num_obstacles landmarks are movable colliders (core.py:240-277) */
     /* optional per-agent DEVICE arrays [N] in the entry point's real type; NULL = scalar above.
        agent_accel / agent_max_speed entries < 0 mean "None" for that agent. */
     const void* agent_mass;
@@ -152,7 +155,9 @@ int fg_device_info(int* sm_count, int* cc_major, int* cc_minor);
  * (environment.py:187-236): apply_action_force (core.py:228-237, Philox u-noise),
  * apply_environment_force / get_entity_collision_force (core.py:240-262,289-322; walls
  * 325-362), integrate_state (core.py:264-277), update_agent_state (core.py:279-286).
- * Reads b->pos, vel, act; writes pos, vel, comm.  One fused kernel. */
+ * Reads b->pos, vel, act; writes pos, vel, comm.  One fused kernel.
+ * With p->num_obstacles > 0 the trailing obstacles of b->landmarks [E, p->num_landmarks, 2] take part in the contact
+ * forces and are integrated too (their velocities in b->landmark_vel, in/out). */
 int fg_world_step(const fg_params* p, const fg_buffers* b, int E, int N,
                   uint64_t seed, uint32_t tick, uint32_t env_offset, void* stream);
 int fg_world_step_f64(const fg_params* p, const fg_buffers* b, int E, int N,

@@ -155,3 +155,43 @@ def test_obstacle_reset_rollout_and_facade():
     sc = fenv.reward_callback.__self__
     r0 = sc.reward(fenv.world.agents[0], fenv.world)
     assert abs(r0 - g["indiv"][5][0]) <= 1e-9
+
+
+def test_world_step_alone_on_obstacle_world():
+    """World.step() without the scenario hooks (core.py:206-225) on a world with movable colliding landmarks:
+    fg_world_step integrates the obstacles too and leaves their INTEGRATED velocity (the (0, -1) rule belongs to the
+    reward hook).  Batched entry point and the facade's World.step() against the oracle."""
+    rng = np.random.default_rng(5)
+    E, N, G, O = 40, 6, 3, 4
+    f32 = lambda x: x.astype(np.float32).astype(np.float64)  # noqa: E731
+    pos = f32(rng.uniform(-0.5, 0.5, (E, N, 2))); vel = f32(rng.uniform(-0.5, 0.5, (E, N, 2)))
+    act = f32(rng.uniform(-1, 1, (E, N, 2))); goals = f32(rng.uniform(-1, 1, (E, G, 2)))
+    obst = f32(rng.uniform(-0.6, 0.6, (E, O, 2))); ov = f32(rng.uniform(-1, 1, (E, O, 2)))
+    p, v, o, ovi = mo.obstacle_world_step(pos, vel, act, obst, ov)
+    for dtype, tol in ((torch.float32, 2e-5), (torch.float64, 1e-11)):
+        env = BatchedFormationEnv(SCN, E, N, num_landmarks=G, num_obstacles=O, dtype=dtype, auto_reset=False)
+        dev = _dev(dtype)
+        _load(env, dev, pos, vel, goals, obst, ov, np.zeros(E))
+        env.world_step(dev(act))
+        assert _err(env.pos, p) <= tol and _err(env.vel, v) <= 10 * tol
+        assert _err(env.landmarks[:, G:], o) <= tol and _err(env.landmark_vel[:, G:], ovi) <= 10 * tol
+        assert _err(env.landmarks[:, :G], goals) == 0.0
+    # facade: World.step() as user code with its own callbacks would call it
+    fenv = formation_gym.make_env(SCN, False, 4)
+    w = fenv.world
+    P0 = np.stack([a.state.p_pos for a in w.agents]) * 0.3
+    for a, q in zip(w.agents, P0):
+        a.state.p_pos = q.copy()
+        a.action.u = np.array([0.5, -0.25]) * 5.0                   # already scaled by _set_action
+    lm = np.stack([l.state.p_pos for l in w.landmarks])
+    lm[4:] = np.array([[0.05, 0.1], [-0.2, 0.0], [0.3, -0.1]])      # obstacles among the agents
+    for l, q in zip(w.landmarks, lm):
+        l.state.p_pos = q.copy()
+    lv = np.stack([np.asarray(l.state.p_vel, float) for l in w.landmarks[4:]])
+    V0 = np.stack([a.state.p_vel for a in w.agents])
+    w.step()
+    rp, rv, ro, rov = mo.obstacle_world_step(P0[None], V0[None], np.tile([0.5, -0.25], (1, 4, 1)), lm[None, 4:], lv[None])
+    assert np.abs(np.stack([a.state.p_pos for a in w.agents]) - rp[0]).max() <= 1e-11
+    assert np.abs(np.stack([l.state.p_pos for l in w.landmarks[4:]]) - ro[0]).max() <= 1e-11
+    assert np.abs(np.stack([l.state.p_vel for l in w.landmarks[4:]]) - rov[0]).max() <= 1e-10
+    assert np.abs(rov[0] - np.array([0.0, -0.75])).max() > 1e-3      # contacts did change an obstacle's velocity
