@@ -135,7 +135,7 @@ int fill_args(fg::KArgs<T>& a, const fg_params* p, const fg_buffers* b, int scen
         // 93 -> 59 us per 1024 envs); with observations the kernel is bound by its obs writer and the extra
         // shared memory only pays for large N
         const char* force = getenv("FG_FORCE_FAST_PAIRS");
-        a.fast_pairs = N >= 32 && (!b->obs || N >= 128 || (force && force[0] == '1')) && !(slow && slow[0] == '1');
+        a.fast_pairs = N >= 32 && (!b->obs || N >= 64 || (force && force[0] == '1')) && !(slow && slow[0] == '1');
     }
     {
         // hashed cell lists of the packed pair loops (fg_pairs.cuh): buckets per env = largest power of two

@@ -640,6 +640,21 @@ __global__ void __launch_bounds__(kBlock, (OM == 3 && SCN == kScnBasic) ? 5 : (O
                 // centroid and mean velocity (formation_hd_env.py:65,68): butterfly sums over the lanes of
                 // each env in the warp, one partial per (env, warp), combined in warp order after the barrier
                 if (PHYS && t < EPC) s_nmax[t] = 0u;                         // re-arm for the next rollout step
+                if (EPC > 1) {
+                    // several envs per CTA: an env's lanes are cut by the warp boundaries at places that depend on
+                    // its position in the tile, so butterfly partials would make the rounding of the sums -- and
+                    // with it the results -- depend on how envs are sharded over launches / GPUs.  One thread per
+                    // (env, quantity) sums in agent order instead (as the scalar path does).
+                    if (t < 2 * nvalid) {
+                        const int qe = t >> 1;
+                        const R2* src = (t & 1) ? (s_v + qe * N) : (s_new + qe * N);
+                        float sx = 0.f, sy = 0.f;
+#pragma unroll 4
+                        for (int j = 0; j < N; ++j) { R2 q = src[j]; sx += (float)q.x; sy += (float)q.y; }
+                        f_part[(qe * 8) * 4 + 2 * (t & 1)] = sx;
+                        f_part[(qe * 8) * 4 + 2 * (t & 1) + 1] = sy;
+                    }
+                } else {
                 float a0 = inA ? (float)p.x : 0.f, a1 = inA ? (float)p.y : 0.f;
                 float a2 = inA ? (float)v.x : 0.f, a3 = inA ? (float)v.y : 0.f;
 #pragma unroll
@@ -659,6 +674,7 @@ __global__ void __launch_bounds__(kBlock, (OM == 3 && SCN == kScnBasic) ? 5 : (O
                     }
                     if (lane_ == 0)
                         *reinterpret_cast<float4*>(f_part + ((leA + 1) * 8 + wp_) * 4) = make_float4(a0, a1, a2, a3);
+                }
                 }
             } else if (t < 2 * nvalid) {
                 const int qe = t >> 1;

@@ -68,6 +68,7 @@ def test_permutation_equivariance(N):
 
 
 @pytest.mark.parametrize("scen,N", [("formation_hd_env", 9), ("formation_hd_env", 27), ("formation_hd_env", 81),
+                                    ("formation_hd_env", 16), ("formation_hd_env", 100),
                                     ("basic_formation_env", 3), ("formation_hd_obs_env", 4)])
 def test_sharding_invariance(scen, N):
     """One batch of E envs == two shards with env_offset (the multi-GPU layout): identical states, observations and
