@@ -175,3 +175,21 @@ def test_full_size_step_properties(N, E):
     act = env.sample_actions().clone()
     env.step(act)
     _check_hd_outputs(env, act, p0, v0)
+
+
+@pytest.mark.parametrize("N", [40, 81, 243])
+def test_sharding_invariance_without_observations(N):
+    """State + reward only (write_obs=False: the packed pair loops with cell lists from N = 32 up): sharding the batch
+    does not change a bit either."""
+    E, T = 300, 8
+    kw = dict(episode_length=5, seed=3, dtype=torch.float32, write_obs=False)
+    full = BatchedFormationEnv("formation_hd_env", E, N, **kw)
+    lo = BatchedFormationEnv("formation_hd_env", 100, N, env_offset=0, **kw)
+    hi = BatchedFormationEnv("formation_hd_env", 200, N, env_offset=100, **kw)
+    for env in (full, lo, hi):
+        env.reset()
+        env.pos.mul_(0.5)                       # denser: contacts and reward collisions
+        for _ in range(T):
+            env.step_random()
+    for k in ("pos", "vel", "reward", "indiv", "step_count", "ep_return", "ep_collisions"):
+        assert torch.equal(getattr(full, k), torch.cat([getattr(lo, k), getattr(hi, k)], 0)), k
