@@ -193,3 +193,60 @@ def test_sharding_invariance_without_observations(N):
             env.step_random()
     for k in ("pos", "vel", "reward", "indiv", "step_count", "ep_return", "ep_collisions"):
         assert torch.equal(getattr(full, k), torch.cat([getattr(lo, k), getattr(hi, k)], 0)), k
+
+
+@pytest.mark.parametrize("scen,N", [("formation_hd_env", 9), ("formation_hd_env", 40), ("basic_formation_env", 3),
+                                    ("formation_hd_partial_env", 5), ("formation_hd_obs_env", 4)])
+def test_masked_reset_touches_only_masked_envs(scen, N):
+    """fg_reset with a mask (env.reset of SOME envs): masked envs get a fresh reset_world state and step 0, the
+    others keep every bit; two different ticks draw different states."""
+    E = 257
+    env = BatchedFormationEnv(scen, E, N, episode_length=25, seed=6, auto_reset=False)
+    env.reset()
+    for _ in range(3):
+        env.step_random()
+    keys = [k for k in ("pos", "vel", "landmarks", "landmark_vel", "ideal_shape", "ideal_vel", "step_count")
+            if getattr(env, k, None) is not None]
+    before = {k: getattr(env, k).clone() for k in keys}
+    mask = (torch.arange(E, device="cuda") % 3 == 1)
+    env.reset(mask)
+    for k in keys:
+        a, b = getattr(env, k), before[k]
+        assert torch.equal(a[~mask], b[~mask]), k
+        if k in ("pos", "step_count"):
+            assert not torch.equal(a[mask], b[mask]), k
+    assert int(env.step_count[mask].abs().sum()) == 0 and int(env.step_count[~mask].min()) == 3
+    assert float(env.vel[mask].abs().max()) == 0.0 and float(env.pos[mask].abs().max()) <= 1.0
+    first = env.pos[mask].clone()
+    env.reset(mask)
+    assert not torch.equal(env.pos[mask], first)
+
+
+@pytest.mark.parametrize("N", [3, 9, 40])
+def test_non_silent_agents_communicate(N):
+    """agent.silent = False (core.py:279-286): actions carry [u, c], the comm state becomes action.c and every agent
+    observes the others' utterances in agent order (formation_hd_env.py:50-57).  Goes through the tile kernel."""
+    E = 50
+    env = BatchedFormationEnv("formation_hd_env", E, N, episode_length=25, seed=2, auto_reset=False, silent=False,
+                              dtype=torch.float64)
+    env.reset()
+    assert env.act_dim == 4
+    act = torch.rand(E, N, 4, device="cuda", dtype=torch.float64) * 2 - 1
+    sil = BatchedFormationEnv("formation_hd_env", E, N, episode_length=25, seed=2, auto_reset=False, dtype=torch.float64)
+    sil.reset()
+    obs, rew, done, info = env.step(act)
+    obs_s, rew_s, _, _ = sil.step(act[..., :2].contiguous())
+    assert torch.equal(env.comm, act[..., 2:])
+    assert torch.equal(env.pos, sil.pos) and torch.equal(rew, rew_s)          # comm does not touch the physics
+    for i in range(N):
+        others = [j for j in range(N) if j != i]
+        assert torch.equal(obs[:, i, 2 * N:4 * N - 2].reshape(E, N - 1, 2), act[:, others, 2:])
+        assert torch.equal(obs[:, i, :2 * N], obs_s[:, i, :2 * N]) and torch.equal(obs[:, i, 4 * N - 2:], obs_s[:, i, 4 * N - 2:])
+    # comm noise (core.py:284-285): c = action.c + N(0, c_noise)
+    noisy = BatchedFormationEnv("formation_hd_env", 4096, 3, episode_length=25, seed=2, auto_reset=False, silent=False,
+                                c_noise=0.05)
+    noisy.reset()
+    a4 = torch.zeros(4096, 3, 4, device="cuda")
+    noisy.step(a4)
+    c = noisy.comm.double().flatten()
+    assert abs(float(c.mean())) < 2e-3 and abs(float(c.std()) - 0.05) < 2e-3
