@@ -138,3 +138,42 @@ def test_custom_callbacks_use_gpu_world_step():
         assert np.abs(np.stack([a.state.p_vel for a in world.agents]) - v1).max() <= 1e-12
         assert np.abs(np.stack([a.state.p_pos for a in world.agents]) - (p0 + v1 * 0.1)).max() <= 1e-12
     assert abs(reward_n[0][0] - sum(i["individual_reward"] for i in info_n)) <= 1e-12
+
+
+@pytest.mark.parametrize("scenario", ["formation_hd_env", "basic_formation_env"])
+@pytest.mark.parametrize("mode", ["onehot", "input", "force", "box"])
+def test_discrete_action_modes_and_benchmark_data(scenario, mode):
+    """The less-travelled corners of MultiAgentEnv against the unmodified reference (tests/golden/misc_api.npz,
+    make_golden_misc.py): one-hot Discrete(5) action spaces (environment.py:203-206), discrete_action_input
+    (:194-202), world.discrete_action -> argmax one-hot (:207-211), and Scenario.benchmark_data."""
+    import formation_gym
+    from formation_gym.environment import MultiAgentEnv
+    g = np.load(os.path.join(GOLD, "misc_api.npz"))
+    key = lambda k: g["%s/%s/%s" % (scenario, mode, k)]  # noqa: E731
+    n = 3
+    env0 = formation_gym.make_env(scenario, False, n)
+    sc = env0.reset_callback.__self__
+    world = env0.world
+    kw = {}
+    if mode == "onehot":
+        kw = dict(discrete_action=True)
+    elif mode == "force":
+        world.discrete_action = True
+    env = MultiAgentEnv(world, sc.reset_world, sc.reward, sc.observation, **kw)
+    if mode == "input":
+        env.discrete_action_input = True
+    assert int(getattr(env.action_space[0], "n", -1)) == int(key("action_space_n"))
+    np.random.seed(77)
+    env.reset()
+    assert np.array_equal(np.stack([a.state.p_pos for a in world.agents]), key("pos0"))
+    for t in range(4):
+        a = key("act")[t]
+        act_n = [int(x) for x in a] if mode == "input" else [np.array(x, np.float64) for x in a]
+        obs_n, reward_n, done_n, info_n = env.step(act_n)
+        assert np.abs(np.stack(obs_n) - key("obs")[t]).max() <= 1e-9
+        assert abs(reward_n[0][0] - key("reward")[t]) <= 1e-9
+        assert np.abs(np.array([i["individual_reward"] for i in info_n]) - key("indiv")[t]).max() <= 1e-9
+        assert np.abs(np.stack([a_.state.p_pos for a_ in world.agents]) - key("pos")[t]).max() <= 1e-9
+    bench = [sc.benchmark_data(a_, world) for a_ in world.agents]
+    got = np.array([[b["reward"], b["collisions"], b["min_dists"], b["occupied_landmarks"]] for b in bench], np.float64)
+    assert np.abs(got - key("bench")).max() <= 1e-9
