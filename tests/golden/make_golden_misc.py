@@ -63,8 +63,47 @@ def run(scenario, n, mode, seed):
     return d
 
 
+def run_scripted(seed):
+    """formation_hd_env, 3 agents, agent 2 scripted (core.py:210-211: action_callback), callbacks that count calls:
+    done_callback, post_step_callback, info_callback with a 'fail' key (environment.py:131-133,140-141)."""
+    fg = rh.load_reference()
+    from formation_gym.environment import MultiAgentEnv
+    from formation_gym.core import Action
+    env0 = fg.make_env("formation_hd_env", False, 3)
+    sc = rh.scenario_of(env0)
+    world = env0.world
+
+    def script(agent, w):
+        act = Action()
+        act.u = np.array([0.3, -0.2]) * (1 + w.world_step)
+        act.c = np.zeros(w.dim_c)
+        return act
+    world.agents[2].action_callback = script
+    calls = {"post": 0}
+    env = MultiAgentEnv(world, sc.reset_world, sc.reward, sc.observation,
+                        info_callback=lambda agent, w: {"fail": agent.state.p_pos[0] > 0.0, "other": 1},
+                        done_callback=lambda agent, w: bool(agent.state.p_pos[1] > 0.0),
+                        post_step_callback=lambda w: calls.__setitem__("post", calls["post"] + 1))
+    np.random.seed(seed)
+    obs0 = np.stack(env.reset())
+    rng = np.random.default_rng(seed)
+    d = dict(obs0=obs0, n_policy=np.int64(env.num_agents), obs=[], reward=[], done=[], fail=[], pos=[], act=[])
+    for t in range(4):
+        a = rng.uniform(-1, 1, (2, 2))
+        obs_n, reward_n, done_n, info_n = env.step([np.array(x) for x in a])
+        d["act"].append(a); d["obs"].append(np.stack(obs_n)); d["reward"].append(reward_n[0][0])
+        d["done"].append(done_n); d["fail"].append([bool(i["fail"]) for i in info_n])
+        d["pos"].append(np.stack([ag.state.p_pos for ag in world.agents]))
+        assert all(set(i.keys()) == {"individual_reward", "fail"} for i in info_n)
+    d["post_calls"] = np.int64(calls["post"])
+    return {k: np.array(v) for k, v in d.items()}
+
+
 if __name__ == "__main__":
     out = {}
+    for k, v in run_scripted(31).items():
+        out["scripted/" + k] = v
+    print("scripted", out["scripted/obs"].shape, int(out["scripted/n_policy"]), int(out["scripted/post_calls"]))
     for scenario, n in (("formation_hd_env", 3), ("basic_formation_env", 3)):
         for mode in ("onehot", "input", "force", "box"):
             d = run(scenario, n, mode, 77)

@@ -177,3 +177,42 @@ def test_discrete_action_modes_and_benchmark_data(scenario, mode):
     bench = [sc.benchmark_data(a_, world) for a_ in world.agents]
     got = np.array([[b["reward"], b["collisions"], b["min_dists"], b["occupied_landmarks"]] for b in bench], np.float64)
     assert np.abs(got - key("bench")).max() <= 1e-9
+
+
+def test_scripted_agent_and_callbacks():
+    """A scripted agent (core.py:210-211), done_callback, info_callback's 'fail' key and post_step_callback
+    (environment.py:131-133,140-141,172-178) against the unmodified reference: only the policy agents are observed and
+    rewarded, the scripted one still pushes and is pushed (World.step on the GPU)."""
+    import formation_gym
+    from formation_gym.environment import MultiAgentEnv
+    from formation_gym.core import Action
+    g = np.load(os.path.join(GOLD, "misc_api.npz"))
+    key = lambda k: g["scripted/" + k]  # noqa: E731
+    env0 = formation_gym.make_env("formation_hd_env", False, 3)
+    sc = env0.reset_callback.__self__
+    world = env0.world
+
+    def script(agent, w):
+        act = Action()
+        act.u = np.array([0.3, -0.2]) * (1 + w.world_step)
+        act.c = np.zeros(w.dim_c)
+        return act
+    world.agents[2].action_callback = script
+    calls = {"post": 0}
+    env = MultiAgentEnv(world, sc.reset_world, sc.reward, sc.observation,
+                        info_callback=lambda agent, w: {"fail": agent.state.p_pos[0] > 0.0, "other": 1},
+                        done_callback=lambda agent, w: bool(agent.state.p_pos[1] > 0.0),
+                        post_step_callback=lambda w: calls.__setitem__("post", calls["post"] + 1))
+    assert env.num_agents == int(key("n_policy")) == 2
+    np.random.seed(31)
+    obs0 = np.stack(env.reset())
+    assert np.abs(obs0 - key("obs0")).max() <= 1e-12
+    for t in range(4):
+        obs_n, reward_n, done_n, info_n = env.step([np.array(x) for x in key("act")[t]])
+        assert len(obs_n) == 2 and np.abs(np.stack(obs_n) - key("obs")[t]).max() <= 1e-9
+        assert abs(reward_n[0][0] - key("reward")[t]) <= 1e-9
+        assert list(done_n) == [bool(x) for x in key("done")[t]]
+        assert [bool(i["fail"]) for i in info_n] == [bool(x) for x in key("fail")[t]]
+        assert all(set(i.keys()) == {"individual_reward", "fail"} for i in info_n)
+        assert np.abs(np.stack([a.state.p_pos for a in world.agents]) - key("pos")[t]).max() <= 1e-9
+    assert calls["post"] == int(key("post_calls")) == 4
