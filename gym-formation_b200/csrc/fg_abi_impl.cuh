@@ -353,7 +353,10 @@ bool warp_path_ok(const fg::KArgs<T>& a, int scenario, const fg_params* p, const
         if (a.N != 3 || a.L != a.N || !b->landmarks) return false;  // the default 3 agents / 3 landmarks
     } else {
         if (scenario != FG_SCENARIO_HD) return false;
-        if (a.N != 3 && a.N != 4 && a.N != 5 && a.N != 8 && a.N != 9 && a.N != 16 && a.N != 27) return false;
+        switch (a.N) {                                              // instantiated agent counts (n^k for n = 2 .. 8)
+            case 3: case 4: case 5: case 6: case 7: case 8: case 9: case 16: case 25: case 27: case 32: break;
+            default: return false;
+        }
         if (b->landmarks) return false;                             // landmark tracking: tile kernel
     }
     if (p->agent_mass || p->agent_size_arr || p->agent_accel || p->agent_max_speed) return false;
@@ -426,9 +429,13 @@ int step_fused_impl(const fg_params* p, const fg_buffers* b, int scenario, int E
             case 3: return launch_warp<T, 3>(a, st);
             case 4: return launch_warp<T, 4>(a, st);
             case 5: return launch_warp<T, 5>(a, st);
+            case 6: return launch_warp<T, 6>(a, st);
+            case 7: return launch_warp<T, 7>(a, st);
             case 8: return launch_warp<T, 8>(a, st);
             case 9: return launch_warp<T, 9>(a, st);
             case 16: return launch_warp<T, 16>(a, st);
+            case 25: return launch_warp<T, 25>(a, st);
+            case 32: return launch_warp<T, 32>(a, st);
             default: return launch_warp<T, 27>(a, st);
         }
     }

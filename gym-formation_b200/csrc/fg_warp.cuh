@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(32 * WarpLayout<T, N, WOBS>::MAXW, WarpLayout<
     const uint32_t tick0 = a.tick + (a.tick_dev ? a.tick_dev[0] : 0u);
     const int le = lane < NA ? lane / N : 0;
     const int i = lane < NA ? lane - le * N : 0;
-    const unsigned envmask = ((1u << N) - 1u) << (le * N);                  // lanes of this env
+    const unsigned envmask = (N == 32 ? 0xffffffffu : ((1u << (N & 31)) - 1u)) << (le * N);   // lanes of this env
 
     unsigned char* wr = smem_raw + (size_t)wib * LY::stride;
     R2* s_pold = reinterpret_cast<R2*>(wr + LY::off_pold);

@@ -268,7 +268,8 @@ def _run_steps(E, N, dtype, steps, force_tile, episode_length=7, u_noise=None, r
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.float64], ids=["f32", "f64"])
 @pytest.mark.parametrize("E,N", [(1001, 3), (10, 3), (1000, 9), (4, 9), (257, 9), (65, 27), (1, 27),
-                                 (333, 4), (7, 4), (333, 5), (100, 8), (3, 8), (65, 16), (2, 16)])
+                                 (333, 4), (7, 4), (333, 5), (100, 8), (3, 8), (65, 16), (2, 16),
+                                 (200, 6), (200, 7), (40, 25), (40, 32), (1, 32)])
 def test_warp_kernel_matches_tile_kernel(E, N, dtype):
     """Both kernels implement the same arithmetic in the same order: bit-exact in the fp64 build;
     fp32 may contract FMAs differently (a few ulp)."""
@@ -290,7 +291,7 @@ def test_warp_kernel_matches_tile_kernel(E, N, dtype):
             assert torch.equal(ra, rb) and torch.equal(ia, ib)
 
 
-@pytest.mark.parametrize("N", [3, 4, 5, 8, 9, 16, 27])
+@pytest.mark.parametrize("N", [3, 4, 5, 6, 7, 8, 9, 16, 25, 27, 32])
 def test_warp_kernel_rollout_equals_stepwise(N):
     """n_steps random-policy steps inside ONE launch == the same steps as separate launches
     (same Philox counters), bit for bit, including the auto-resets in between."""
