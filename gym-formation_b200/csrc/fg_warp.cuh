@@ -432,7 +432,7 @@ __global__ void __launch_bounds__(32 * WarpLayout<T, N, WOBS>::MAXW, WarpLayout<
                 const R2* eP = s_pnew + le * 2 * N + i;                     // eP[k] = agent (i + k) mod N
                 const R2* eS = s_shp + le * N;
                 row[0] = v;
-                if constexpr (SCN == kScnHD && (N & 1) == 0) {
+                if constexpr (SCN == kScnHD && ((N & 1) == 0 || N >= 25)) {
                     // EVEN N: the row stride 3N items is a multiple of 8 (N = 4), 16 (N = 8) or 32 (N = 16) banks,
                     // so "every lane writes item k of its row" would hit 4 / 2 / 1 banks.  Each lane instead walks
                     // every row segment in an order rotated by its lane index (runtime indices, 2-3 way conflicts
