@@ -559,13 +559,16 @@ __global__ void __launch_bounds__(kBlock, (OM == 3 && SCN == kScnBasic) ? 5 : (O
                 uint64_t pol;
                 asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
                 int pending = 0;
-                for (int row = wp_; row < nrows; row += kBlock / 32) {
+                // per-row bookkeeping hoisted out of the loop (it was ~200 of the ~250 warp instructions per row and
+                // makes mid-size N issue-bound): a warp's rows are 8 apart, so they all have the SAME 16-byte phase;
+                // (env, agent) of the row and its output pointer advance incrementally (N >= 48 > 8: one wrap at most)
+                const bool odd = ((((size_t)tile0 * N) + (size_t)wp_) & 1) != 0;
+                int rle = 0, ri = wp_;
+                R2* out = a.obs + ((size_t)tile0 * N + wp_) * a.IPR;
+                const size_t ostride = (size_t)(kBlock / 32) * a.IPR;
+                for (int row = wp_; row < nrows; row += kBlock / 32, out += ostride, ri += kBlock / 32) {
+                    if (ri >= N) { ri -= N; ++rle; }
                     R2* img = dyn2 + (NB == 2 ? (pending & 1) : 0) * rt_dyn;
-                    const int rle = (int)fastdiv((uint32_t)row, a.magic_n);
-                    const int ri = row - rle * N;
-                    const size_t grow = (size_t)tile0 * N + row;
-                    R2* out = a.obs + grow * a.IPR;
-                    const bool odd = (grow & 1) != 0;
                     if (lane_ == 0) {            // the buffer being refilled must have been read by its bulk copy
                         if (NB == 2) { if (pending >= 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
                         else if (pending >= 1) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
@@ -582,7 +585,7 @@ __global__ void __launch_bounds__(kBlock, (OM == 3 && SCN == kScnBasic) ? 5 : (O
                     }
                     if (lane_ == 0) {
                         if (!odd) { img[0] = s_v[row]; img[N] = O::make((T)0, (T)0); }
-                        else if (row > 0) { img[0] = s_iv[(int)fastdiv((uint32_t)(row - 1), a.magic_n)]; img[1] = s_v[row]; }
+                        else if (row > 0) { img[0] = s_iv[ri == 0 ? rle - 1 : rle]; img[1] = s_v[row]; }   // previous row's env
                         else O::stcs(out, s_v[row]);
                         if (!odd && row == nrows - 1) O::stcs(out + 3 * N - 1, s_iv[rle]);   // nobody follows
                     }
