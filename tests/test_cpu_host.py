@@ -270,3 +270,19 @@ def test_render_bridge_rgb_array_on_host():
     red = (img[..., 0] == 255) & (img[..., 1] == 0)
     assert abs(red.sum() - np.pi * (0.4 * 175) ** 2) < 0.02 * np.pi * (0.4 * 175) ** 2
     assert env.render(close=True) == []
+
+
+def test_bench_reference_arm_runs_on_cpu():
+    """`bench.py --impl reference` (the reference's per-env CPU loop on the host cores) needs no GPU and prints exactly
+    one JSON line with the contract's keys."""
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "3",
+                          "--warmup", "1"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-500:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "agent-steps/s" and d["higher_is_better"] is True
+    assert d["value"] > 0 and d["steps"] == 3 and d["gpu_launches"] == 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["value"] == d["value"] and d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+    assert d["config"]["scenario"] == "formation_hd_env" and d["config"]["agents"] == 9
