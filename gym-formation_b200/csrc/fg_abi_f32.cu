@@ -1,7 +1,42 @@
 // fg_abi_f32.cu -- fp32 entry points + the precision-independent ones (see fg_abi_impl.cuh).
 #include "fg_abi_impl.cuh"
+#include <cctype>
 
-namespace fgabi { thread_local char g_err[512] = ""; }
+namespace fgabi {
+thread_local char g_err[512] = "";
+
+namespace {
+struct OptionDesc { const char* name; std::atomic<int> Switches::* field; int lo, hi; };
+const OptionDesc kOptions[] = {
+    {"no_fast_pairs", &Switches::no_fast_pairs, 0, 1},       {"force_fast_pairs", &Switches::force_fast_pairs, 0, 1},
+    {"no_cells", &Switches::no_cells, 0, 1},                 {"row_nbuf", &Switches::row_nbuf, 1, 2},
+    {"no_early_rows", &Switches::no_early_rows, 0, 1},       {"no_tile_image", &Switches::no_tile_image, 0, 1},
+    {"force_tile_kernel", &Switches::force_tile_kernel, 0, 1}, {"waves", &Switches::waves, 1, 64},
+    {"no_persistent_tiles", &Switches::no_persistent_tiles, 0, 1}, {"nvtx", &Switches::nvtx, 0, 1},
+};
+}  // namespace
+
+// Initialised ONCE (thread-safe static) from FG_<NAME> environment variables; out-of-range values are ignored.
+Switches& switches() {
+    static Switches sw;
+    static const bool init = [] {
+        for (const OptionDesc& o : kOptions) {
+            char env[64] = "FG_";
+            size_t k = 3;
+            for (const char* c = o.name; *c && k + 1 < sizeof(env); ++c) env[k++] = (char)toupper((unsigned char)*c);
+            env[k] = 0;
+            const char* v = getenv(env);
+            if (!v || !*v) continue;
+            char* end = nullptr;
+            const long x = strtol(v, &end, 10);
+            if (end != v && x >= o.lo && x <= o.hi) (sw.*(o.field)).store((int)x);
+        }
+        return true;
+    }();
+    (void)init;
+    return sw;
+}
+}  // namespace fgabi
 
 extern "C" {
 
@@ -11,6 +46,24 @@ int fg_policy_bfs(const void* pos, const void* ideal_shape, const void* ideal_ve
 }
 
 int fg_abi_version(void) { return FG_ABI_VERSION; }
+
+int fg_set_option(const char* name, int value) {
+    if (!name) return fail(FG_ERR_ARG, "fg_set_option: null name%s");
+    for (const fgabi::OptionDesc& o : fgabi::kOptions)
+        if (!strcmp(name, o.name)) {
+            if (value < o.lo || value > o.hi) return fail(FG_ERR_ARG, "fg_set_option: value out of range for '%s'", name);
+            (fgabi::switches().*(o.field)).store(value);
+            return FG_OK;
+        }
+    return fail(FG_ERR_ARG, "fg_set_option: unknown option '%s'", name);
+}
+
+int fg_get_option(const char* name, int* value) {
+    if (!name || !value) return fail(FG_ERR_ARG, "fg_get_option: null argument%s");
+    for (const fgabi::OptionDesc& o : fgabi::kOptions)
+        if (!strcmp(name, o.name)) { *value = (fgabi::switches().*(o.field)).load(); return FG_OK; }
+    return fail(FG_ERR_ARG, "fg_get_option: unknown option '%s'", name);
+}
 
 const char* fg_last_error(void) { return g_err; }
 

@@ -17,7 +17,56 @@
 #include "fg_obstacle.cuh"
 #include "fg_policy.cuh"
 
-namespace fgabi { extern thread_local char g_err[512]; }      // defined in fg_abi_f32.cu, shared by both precisions
+#include <algorithm>
+#include <atomic>
+#include <nvtx3/nvToolsExt.h>
+
+namespace fgabi {
+extern thread_local char g_err[512];                          // defined in fg_abi_f32.cu, shared by both precisions
+
+// A/B switches for tests and profiling (fg_set_option / FG_<NAME> environment variables, read ONCE when the
+// library is first used -- never on the launch path).  Defaults select the product kernels.
+struct Switches {
+    std::atomic<int> no_fast_pairs{0};      // tile kernel: scalar pair loops instead of fg_pairs.cuh
+    std::atomic<int> force_fast_pairs{0};   // tile kernel: packed pair loops also for 32 <= N < 64 with observations
+    std::atomic<int> no_cells{0};           // packed pair loops: O(N^2) group filters instead of the cell lists
+    std::atomic<int> row_nbuf{2};           // OM == 2: staging buffers per warp (1 or 2)
+    std::atomic<int> no_early_rows{0};      // OM == 2: rows leave after the reward pass
+    std::atomic<int> no_tile_image{0};      // OM == 3 off: flat item loop
+    std::atomic<int> force_tile_kernel{0};  // fg_step_fused never takes the warp-autonomous kernel
+    std::atomic<int> waves{1};              // warp kernel: grid = waves x one resident wave (>= 1)
+    std::atomic<int> no_persistent_tiles{0};// tile kernel: one CTA per tile instead of a persistent grid
+    std::atomic<int> nvtx{1};               // NVTX ranges around the launches of every entry point
+};
+Switches& switches();                                         // defined in fg_abi_f32.cu
+}
+
+namespace {
+// NVTX range around the launches of one entry point (free when no tool is attached: one load + branch)
+struct NvtxRange {
+    bool on;
+    explicit NvtxRange(const char* name) : on(fgabi::switches().nvtx.load(std::memory_order_relaxed) != 0) {
+        if (on) nvtxRangePushA(name);
+    }
+    ~NvtxRange() { if (on) nvtxRangePop(); }
+};
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is sticky per (function, device): raise it only when a launch needs
+// more than what was set before (it used to be re-set on every launch: ~1 us of host time per step).
+constexpr int kMaxDev = 64;
+template <auto Kernel>
+cudaError_t ensure_dyn_smem(size_t smem) {
+    static std::atomic<size_t> have[kMaxDev];
+    if (smem <= 48 * 1024) return cudaSuccess;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDev)
+        return cudaFuncSetAttribute(Kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (smem <= have[dev].load(std::memory_order_acquire)) return cudaSuccess;
+    cudaError_t e = cudaFuncSetAttribute(Kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) have[dev].store(smem, std::memory_order_release);
+    return e;
+}
+}
 
 namespace {
 
@@ -84,7 +133,7 @@ int fill_args(fg::KArgs<T>& a, const fg_params* p, const fg_buffers* b, int scen
     a.shape = (R2*)b->ideal_shape; a.ivel = (R2*)b->ideal_vel; a.lm = (R2*)b->landmarks;
     a.step = b->step; a.obs = (R2*)b->obs; a.reward = (T*)b->reward; a.indiv = (T*)b->indiv;
     a.done = b->done; a.ep_return = (T*)b->ep_return; a.ep_coll = b->ep_collisions; a.stats = b->stats;
-    a.tick_dev = b->tick_dev;
+    a.tick_dev = b->tick_dev; a.nan_flag = b->nan_flag;
     a.a_mass = (const T*)p->agent_mass; a.a_size = (const T*)p->agent_size_arr;
     a.a_accel = (const T*)p->agent_accel; a.a_vmax = (const T*)p->agent_max_speed;
     a.E = E; a.N = N; a.L = L;
@@ -130,37 +179,30 @@ int fill_args(fg::KArgs<T>& a, const fg_params* p, const fg_buffers* b, int scen
     // long hd rows of silent agents: static 2/3 of each row bulk-stored from one shared image
     // (measured: N = 243 270 us vs 353 us with plain stores; break-even near N = 50)
     {
-        const char* slow = getenv("FG_NO_FAST_PAIRS");                 // A/B switch for tests and profiling
+        const fgabi::Switches& sw = fgabi::switches();                 // A/B switches for tests and profiling
         // measured (scripts/cfg_time.py): without observations the packed loops win from N = 32 up (N = 243:
         // 93 -> 59 us per 1024 envs); with observations the kernel is bound by its obs writer and the extra
         // shared memory only pays for large N
-        const char* force = getenv("FG_FORCE_FAST_PAIRS");
-        a.fast_pairs = N >= 32 && (!b->obs || N >= 64 || (force && force[0] == '1')) && !(slow && slow[0] == '1');
+        a.fast_pairs = N >= 32 && (!b->obs || N >= 64 || sw.force_fast_pairs.load(std::memory_order_relaxed)) &&
+                       !sw.no_fast_pairs.load(std::memory_order_relaxed);
     }
     {
         // hashed cell lists of the packed pair loops (fg_pairs.cuh): buckets per env = largest power of two
         // <= 4 * roundup(N, 32); cell edge = 2 * search radius * (1 + 2^-9)
-        const char* off = getenv("FG_NO_CELLS");                       // A/B switch for tests and profiling
         const int NP = (N + 31) & ~31;
         int logb = 0;
         while ((2 << logb) <= 4 * NP) ++logb;
         a.cell_shift = 32 - logb;
-        a.cells = a.fast_pairs && p->collide && !(off && off[0] == '1');
+        a.cells = a.fast_pairs && p->collide && !fgabi::switches().no_cells.load(std::memory_order_relaxed);
         a.cell_inv_old = (float)(1.0 / (2.0 * std::sqrt((double)a.cut2) * (1.0 + 1.0 / 512.0)));
         a.cell_inv_new = (float)(1.0 / (2.0 * std::sqrt((double)a.rthr2_hi) * (1.0 + 1.0 / 512.0)));
         a.cell_off = 0;
     }
     a.row_tma = scenario == FG_SCENARIO_HD && p->silent && a.IPR >= 144 && b->obs &&
                 ((uintptr_t)b->obs % sizeof(R2)) == 0;
-    {
-        const char* nb = getenv("FG_ROW_NBUF");
-        a.row_nbuf = (nb && nb[0] == '1') ? 1 : 2;
-    }
-    {
-        const char* late = getenv("FG_NO_EARLY_ROWS");                 // A/B switch for tests and profiling
-        a.row_early = a.row_tma && sizeof(R2) == 8 && (N & 1) && ((uintptr_t)b->obs % 16) == 0 &&
-                      !(late && late[0] == '1');
-    }
+    a.row_nbuf = fgabi::switches().row_nbuf.load(std::memory_order_relaxed) == 1 ? 1 : 2;
+    a.row_early = a.row_tma && sizeof(R2) == 8 && (N & 1) && ((uintptr_t)b->obs % 16) == 0 &&
+                  !fgabi::switches().no_early_rows.load(std::memory_order_relaxed);
     return FG_OK;
 }
 
@@ -189,9 +231,8 @@ size_t tile_image_bytes(const fg::KArgs<T>& a) {
 template <typename T>
 bool tile_image_ok(const fg::KArgs<T>& a) {
     typedef typename fg::Ops<T>::R2 R2;
-    const char* off = getenv("FG_NO_TILE_IMAGE");                      // A/B switch for tests and profiling
     return a.obs && ((uintptr_t)a.obs % sizeof(R2)) == 0 && tile_image_bytes(a) <= 96 * 1024 &&
-           !(off && off[0] == '1');
+           !fgabi::switches().no_tile_image.load(std::memory_order_relaxed);
 }
 
 // extra shared memory of the fast pair loops: 8 arrays of EPC*roundup(N,32) floats, the per-(env,warp)
@@ -218,9 +259,8 @@ int launch_one(const fg::KArgs<T>& a, size_t smem, cudaStream_t st) {
     } else {
         b.cells = 0;
     }
-    if (smem > 48 * 1024) {
-        cudaError_t e1 = cudaFuncSetAttribute(fg::k_step<T, SCN, PHYS, OBSREW, HET, OM, FP>,
-                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    {
+        cudaError_t e1 = ensure_dyn_smem<fg::k_step<T, SCN, PHYS, OBSREW, HET, OM, FP>>(smem);
         if (e1 != cudaSuccess) return fail(FG_ERR_CUDA, "cudaFuncSetAttribute failed: %s", cudaGetErrorString(e1));
     }
     fg::k_step<T, SCN, PHYS, OBSREW, HET, OM, FP><<<grid, fg::kBlock, smem, st>>>(b);
@@ -273,8 +313,8 @@ int launch_obstacle(const fg::KArgs<T>& a, void* stream) {
     size_t smem = (4 * nA + (size_t)a.EPC * a.L + 2 * (size_t)a.EPC * a.n_obst + 2 * a.EPC) * sizeof(R2)
                   + a.EPC * sizeof(Bits) + 3 * a.EPC * sizeof(int);
     smem = (smem + 15) & ~(size_t)15;
-    if (smem > 48 * 1024) {
-        cudaError_t e1 = cudaFuncSetAttribute(fg::k_step_obst<T, PHYS, OBSREW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    {
+        cudaError_t e1 = ensure_dyn_smem<fg::k_step_obst<T, PHYS, OBSREW>>(smem);
         if (e1 != cudaSuccess) return fail(FG_ERR_CUDA, "cudaFuncSetAttribute failed: %s", cudaGetErrorString(e1));
     }
     const int grid = (a.E + a.EPC - 1) / a.EPC;
@@ -326,13 +366,12 @@ int launch_warp_n(const fg::KArgs<T>& a, cudaStream_t st) {
     if (gm.ctas[l] < 1) return fail(FG_ERR_CUDA, "k_hd_warp does not fit on this device%s");
     const int w = 1 << l;
     const size_t smem = (size_t)w * LY::stride;
-    cudaError_t err = cudaFuncSetAttribute(fg::k_hd_warp<T, N, WOBS, SCN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           (int)smem);
+    cudaError_t err = ensure_dyn_smem<fg::k_hd_warp<T, N, WOBS, SCN>>(smem);
     if (err != cudaSuccess) return fail(FG_ERR_CUDA, "cudaFuncSetAttribute failed: %s", cudaGetErrorString(err));
     // persistent warps: at most one resident wave; each warp walks spans gw, gw + nwarps, ...
     int grid = (spans + w - 1) / w;
     int wave = gm.sms * gm.ctas[l];
-    { const char* e_ = getenv("FG_WAVES"); if (e_) wave *= atoi(e_); }
+    wave *= std::max(1, fgabi::switches().waves.load(std::memory_order_relaxed));
     if (grid > wave) grid = wave;
     if ((grid * w) & 1) ++grid;                                    // even warp count (16-byte phase, fg_warp.cuh)
     fg::k_hd_warp<T, N, WOBS, SCN><<<grid, 32 * w, smem, st>>>(a);
@@ -362,14 +401,13 @@ bool warp_path_ok(const fg::KArgs<T>& a, int scenario, const fg_params* p, const
     if (p->agent_mass || p->agent_size_arr || p->agent_accel || p->agent_max_speed) return false;
     if (p->n_walls != 0 || !p->silent) return false;
     if (((uintptr_t)b->obs) % sizeof(typename fg::Ops<T>::R2)) return false;
-    const char* force = getenv("FG_FORCE_TILE_KERNEL");            // A/B switch for tests and profiling
-    if (force && force[0] == '1') return false;
-    return true;
+    return !fgabi::switches().force_tile_kernel.load(std::memory_order_relaxed);   // A/B switch for tests and profiling
 }
 
 template <typename T>
 int world_step_impl(const fg_params* p, const fg_buffers* b, int E, int N, uint64_t seed, uint32_t tick,
                     uint32_t env_offset, void* stream) {
+    NvtxRange nvtx_("fg_world_step");
     fg::KArgs<T> a;
     if (p && p->num_obstacles > 0) {
         // World.step on a world with movable colliding landmarks (formation_hd_obs_env's obstacles)
@@ -388,6 +426,7 @@ int world_step_impl(const fg_params* p, const fg_buffers* b, int E, int N, uint6
 
 template <typename T>
 int obs_reward_impl(const fg_params* p, const fg_buffers* b, int scenario, int E, int N, int L, void* stream) {
+    NvtxRange nvtx_("fg_obs_reward");
     fg::KArgs<T> a;
     int rc = fill_args<T>(a, p, b, scenario, E, N, L, 0, 0, 0);
     if (rc) return rc;
@@ -405,6 +444,7 @@ template <typename T>
 int step_fused_impl(const fg_params* p, const fg_buffers* b, int scenario, int E, int N, int L, int n_steps,
                     int random_actions, int auto_reset, uint64_t seed, uint32_t tick, uint32_t env_offset,
                     void* stream) {
+    NvtxRange nvtx_("fg_step_fused");
     fg::KArgs<T> a;
     int rc = fill_args<T>(a, p, b, scenario, E, N, L, seed, tick, env_offset);
     if (rc) return rc;
@@ -414,8 +454,12 @@ int step_fused_impl(const fg_params* p, const fg_buffers* b, int scenario, int E
     if (n_steps < 1) return fail(FG_ERR_ARG, "fg_step_fused: n_steps must be >= 1%s");
     if (n_steps > 1 && !random_actions)
         return fail(FG_ERR_ARG, "fg_step_fused: n_steps > 1 needs random_actions (one action set per call)%s");
+    if (random_actions < 0 || random_actions > 2) return fail(FG_ERR_ARG, "fg_step_fused: random_actions must be 0, 1 or 2%s");
     if (random_actions && !p->silent)
         return fail(FG_ERR_ARG, "fg_step_fused: random_actions supports silent agents only%s");
+    if (random_actions == 2 && (!b->act || scenario == FG_SCENARIO_HD_OBSTACLE))
+        return fail(FG_ERR_ARG, "fg_step_fused: random_actions == 2 records the drawn actions in b->act (non-null; not "
+                                "available for formation_hd_obs_env)%s");
     if (scenario == FG_SCENARIO_HD && (!b->ideal_shape || !b->ideal_vel))
         return fail(FG_ERR_ARG, "fg_step_fused(hd): ideal_shape/ideal_vel must be non-null%s");
     if (scenario != FG_SCENARIO_HD && !b->landmarks)
@@ -445,6 +489,7 @@ int step_fused_impl(const fg_params* p, const fg_buffers* b, int scenario, int E
 template <typename T>
 int reset_impl(const fg_params* p, const fg_buffers* b, int scenario, int E, int N, int L, const uint8_t* mask,
                uint64_t seed, uint32_t tick, uint32_t env_offset, void* stream) {
+    NvtxRange nvtx_("fg_reset");
     fg::KArgs<T> a;
     int rc = fill_args<T>(a, p, b, scenario, E, N, L, seed, tick, env_offset);
     if (rc) return rc;
@@ -466,6 +511,7 @@ int reset_impl(const fg_params* p, const fg_buffers* b, int scenario, int E, int
 template <typename T>
 int random_actions_impl(void* act, int E, int N, uint64_t seed, uint32_t tick, uint32_t env_offset,
                         const uint32_t* tick_dev, void* stream) {
+    NvtxRange nvtx_("fg_random_actions");
     if (!act || E < 1 || N < 1) return fail(FG_ERR_ARG, "fg_random_actions: bad argument%s");
     if ((uint64_t)E * (uint64_t)N >= (1ull << 31)) return fail(FG_ERR_ARG, "E*N must be < 2^31%s");
     const uint32_t n = (uint32_t)E * (uint32_t)N;
@@ -481,6 +527,7 @@ int random_actions_impl(void* act, int E, int N, uint64_t seed, uint32_t tick, u
 template <typename T>
 int policy_bfs_impl(const void* pos, const void* shape, const void* ivel, void* act, int E, int N, int n,
                     void* stream) {
+    NvtxRange nvtx_("fg_policy_bfs");
     typedef typename fg::Ops<T>::R2 R2;
     if (!pos || !shape || !ivel || !act) return fail(FG_ERR_ARG, "fg_policy_bfs: null pointer%s");
     if (E < 1 || N < 1 || N > FG_MAX_AGENTS) return fail(FG_ERR_ARG, "fg_policy_bfs: bad E or N%s");

@@ -71,6 +71,7 @@ template <typename T> struct KArgs {
     int n_steps, random_actions, auto_reset;
     uint64_t seed; uint32_t tick; uint32_t env_offset;
     uint32_t* tick_dev;              // (opt) [2]: device tick added to `tick`, arrival counter (CUDA graphs)
+    uint8_t* nan_flag;               // (opt) [E]: set to 1 (never cleared) when the env holds a non-finite position (Q9)
     WallT<T> walls[kMaxWalls];
 };
 
@@ -374,6 +375,7 @@ __global__ void __launch_bounds__(kBlock, (OM == 3 && SCN == kScnBasic) ? 5 : (O
                 if (a.random_actions) {                                     // test.py:20
                     U4 r = philox(a.seed, ge, (uint32_t)i, tick0 + (uint32_t)ts, kAction);
                     u = O::make(uniform_pm1<T>(r.x), uniform_pm1<T>(r.y));
+                    if (a.random_actions == 2) const_cast<R2*>(a.act)[g] = u;   // recorded for the caller (replay buffer)
                 }
                 T m_i = HET ? s_het[i] : a.mass;
                 T size_i = HET ? s_het[N + i] : a.size;
@@ -841,6 +843,7 @@ __global__ void __launch_bounds__(kBlock, (OM == 3 && SCN == kScnBasic) ? 5 : (O
             }
         }
         if (SCN == kScnBasic) {
+            if (a.nan_flag && active && (!(fabs(p.x) < (T)INFINITY) || !(fabs(p.y) < (T)INFINITY))) s_bad[le] = 1;
             // reward part 1 (basic_formation_env.py:45-47): min over agents of |p_a - l_k| per landmark
             for (int q = t; q < nvalid * L; q += kBlock) {
                 int qe = (int)fastdiv((uint32_t)q, a.magic_l);
@@ -885,6 +888,7 @@ __global__ void __launch_bounds__(kBlock, (OM == 3 && SCN == kScnBasic) ? 5 : (O
             a.reward[g] = (T)R;
             if (a.indiv) a.indiv[g] = r;
             if (a.done) a.done[g] = (uint8_t)(a.step ? (stp >= a.world_length) : 0);
+            if (i == 0 && a.nan_flag && s_bad[le]) a.nan_flag[e] = 1;           // the reference's failure mode (Q9), sticky
             if (i == 0 && a.step) {
                 T ret = (T)R;
                 if (a.ep_return) { ret = a.ep_return[e] + (T)R; a.ep_return[e] = (dn && a.auto_reset) ? (T)0 : ret; }

@@ -278,6 +278,7 @@ __global__ void __launch_bounds__(kBlock, 2) k_step_obst(const __grid_constant__
             a.reward[g] = (T)R;
             if (a.indiv) a.indiv[g] = r;
             if (a.done) a.done[g] = (uint8_t)(a.step ? (stp >= a.world_length) : 0);
+            if (i == 0 && a.nan_flag && s_bad[le]) a.nan_flag[e] = 1;           // the reference's failure mode (Q9), sticky
             if (i == 0 && a.step) {
                 T ret = (T)R;
                 if (a.ep_return) { ret = a.ep_return[e] + (T)R; a.ep_return[e] = (dn && a.auto_reset) ? (T)0 : ret; }

@@ -168,6 +168,7 @@ __global__ void __launch_bounds__(32 * WarpLayout<T, N, WOBS>::MAXW, WarpLayout<
             if (a.random_actions) {                                         // test.py:20
                 U4 r = philox(a.seed, ge, (uint32_t)i, tick0 + (uint32_t)ts, kAction);
                 u = O::make(uniform_pm1<T>(r.x), uniform_pm1<T>(r.y));
+                if (a.random_actions == 2) const_cast<R2*>(a.act)[g] = u;   // recorded for the caller (replay buffer)
             }
             // _set_action: u *= sensitivity (environment.py:216-221); apply_action_force:
             // F = gain * u + noise (core.py:232-236)
@@ -358,6 +359,7 @@ __global__ void __launch_bounds__(32 * WarpLayout<T, N, WOBS>::MAXW, WarpLayout<
             a.reward[g] = (T)R;
             if (a.indiv) a.indiv[g] = r;
             if (a.done) a.done[g] = (uint8_t)(a.step ? (stp >= a.world_length) : 0);
+            if (i == 0 && env_bad && a.nan_flag) a.nan_flag[e] = 1;         // the reference's failure mode (Q9), sticky
             if (i == 0 && a.step) {
                 const T ret = epr + (T)R;                                   // epr == 0 when ep_return is not tracked
                 const int ec = epc + coltot;

@@ -100,20 +100,44 @@ def ezpolicy(obs):
     return _policy_device(pos, shape, obs[-2:], n)[n - 1]
 
 
+def _consistent_observations(obs, N):
+    """True when every obs[j] (formation_hd_env layout, length 6N) shows the state that obs[0] implies: the same
+    ideal shape and ideal velocity, and other_pos == pos[k] - pos[j] for k != j with agent 0 at the origin."""
+    import numpy as np
+    try:
+        O = np.stack([np.asarray(o, dtype=np.float64) for o in obs])
+    except ValueError:
+        return False
+    if O.shape != (N, 6 * N) or not np.all(np.isfinite(O[:, 2:])):
+        return False                                                         # malformed / NaN: read them like the reference
+    pos = np.concatenate([[0.0, 0.0], O[0, 2:2 * N]]).reshape(N, 2)
+    rel = pos[None, :, :] - pos[:, None, :]                                  # rel[j, k] = pos[k] - pos[j]
+    keep = ~np.eye(N, dtype=bool)
+    want = rel[keep].reshape(N, 2 * (N - 1))                                 # k != j, ascending
+    scale = max(1.0, float(np.abs(pos).max()))
+    return bool(np.allclose(O[:, 2:2 * N], want, rtol=0.0, atol=1e-9 * scale)
+                and np.array_equal(O[:, 4 * N - 2:], O[:1, 4 * N - 2:].repeat(N, 0)))
+
+
 def get_action_BFS(policy, obs, num_agents_per_layer):
     """Reference signature (formation_gym/__init__.py:49-98): expand ``policy`` hierarchically over the
     per-agent observation list ``obs`` and return the list of actions.
 
     With ``policy is formation_gym.ezpolicy`` (the reference's demo, test.py:23) the whole tree runs in ONE
     device launch (``fg_policy_bfs_f64``): agent 0's observation gives every position relative to agent 0,
-    the ideal shape and the ideal velocity (formation_hd_env.py:52-59).  Any other callable is user code:
-    the tree is walked on the host exactly like the reference does and only ``policy`` itself is called."""
+    the ideal shape and the ideal velocity (formation_hd_env.py:52-59).  PRECONDITION of that shortcut: the N
+    observations describe ONE consistent state (what ``env.step`` / ``env.reset`` return).  The reference reads
+    each layer leader's and each group member's OWN observation, so observations that a wrapper has made
+    inconsistent (noise, clipping, per-agent normalisation, stale entries) are detected here -- every
+    ``obs[j]``'s other_pos / ideal_shape / ideal_vel slices are compared with the state derived from
+    ``obs[0]`` -- and take the host tree walk below, which reads them exactly like the reference does.
+    Any other callable is user code: the tree is walked on the host and only ``policy`` itself is called."""
     import numpy as np
     n = int(num_agents_per_layer)
     N = len(obs)
     num_layer = np.log(N) / np.log(n)
     assert num_layer.is_integer(), 'Observation shape error!'
-    if policy is ezpolicy:
+    if policy is ezpolicy and _consistent_observations(obs, N):
         o0 = np.asarray(obs[0], dtype=np.float64)
         pos = np.concatenate([[0.0, 0.0], o0[2:2 * N]]).reshape(N, 2)         # agent 0 at the origin
         act = _policy_device(pos, o0[4 * N - 2:6 * N - 2].reshape(N, 2), o0[-2:], n)

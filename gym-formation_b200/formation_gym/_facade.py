@@ -293,14 +293,15 @@ class FacadeBackend(object):
         Cm = np.stack([np.asarray(a.state.c, np.float64) if a.state.c is not None
                        else np.zeros(2) for a in world.agents]) if world.dim_c == 2 else np.zeros((self.N, 2))
         lmh = np.stack([np.asarray(l.state.p_pos, np.float64) for l in world.landmarks]) if self.L else np.zeros((0, 2))
+        p, _ = self._params(world, kind, False, scenario)      # cached on every constant the kernels read
         key = (P.tobytes(), V.tobytes(), Cm.tobytes(), lmh.tobytes(),
                np.asarray(getattr(scenario, "ideal_shape", 0.0), np.float64).tobytes(),
-               np.asarray(getattr(scenario, "ideal_vel", 0.0), np.float64).tobytes())
+               np.asarray(getattr(scenario, "ideal_vel", 0.0), np.float64).tobytes(),
+               self._pkey)                                      # kind, sizes, collide, num_obs, obs_range, ...
         if key == self._cache_key:
             if kind == nat.FG_SCENARIO_HD_OBSTACLE:
                 self._scatter_obstacles(world, with_pos=False)
             return self._cache_val
-        p, _ = self._params(world, kind, False, scenario)
         b = self._buffers(kind, True, scenario)
         self.h_pos[0], self.h_vel[0], self.h_comm[0] = P, V, Cm
         self._stage_scenario(world, scenario, kind)

@@ -8,7 +8,7 @@ import os
 
 from . import _build
 
-FG_ABI_VERSION = 6
+FG_ABI_VERSION = 7
 FG_MAX_AGENTS = 256
 FG_MAX_LANDMARKS = 256
 FG_MAX_WALLS = 8
@@ -19,7 +19,7 @@ FG_SCENARIO_HD_PARTIAL_RANGE = 3
 FG_SCENARIO_HD_OBSTACLE = 4
 
 EXPORTS = [
-    "fg_abi_version", "fg_last_error", "fg_device_info", "fg_launch_geometry",
+    "fg_abi_version", "fg_last_error", "fg_device_info", "fg_launch_geometry", "fg_set_option", "fg_get_option",
     "fg_world_step", "fg_world_step_f64", "fg_obs_reward", "fg_obs_reward_f64",
     "fg_step_fused", "fg_step_fused_f64", "fg_reset", "fg_reset_f64",
     "fg_random_actions", "fg_random_actions_f64", "fg_fp32_probe", "fg_write_probe", "fg_policy_bfs", "fg_policy_bfs_f64",
@@ -60,6 +60,7 @@ class fg_buffers(C.Structure):
         ("step", C.c_void_p), ("obs", C.c_void_p), ("reward", C.c_void_p), ("indiv", C.c_void_p),
         ("done", C.c_void_p), ("ep_return", C.c_void_p), ("ep_collisions", C.c_void_p),
         ("stats", C.c_void_p), ("landmark_vel", C.c_void_p), ("tick_dev", C.c_void_p),
+        ("nan_flag", C.c_void_p),
     ]
 
 
@@ -86,6 +87,8 @@ def load():
     lib.fg_last_error.restype = C.c_char_p
     lib.fg_device_info.argtypes = [P(I), P(I), P(I)]
     lib.fg_launch_geometry.argtypes = [I, P(I), P(I)]
+    lib.fg_set_option.argtypes = [C.c_char_p, I]
+    lib.fg_get_option.argtypes = [C.c_char_p, P(I)]
     for sfx in ("", "_f64"):
         getattr(lib, "fg_world_step" + sfx).argtypes = \
             [P(fg_params), P(fg_buffers), I, I, U64, U32, U32, VP]
@@ -106,6 +109,35 @@ def load():
         raise NativeError("ABI mismatch: library %d, binding %d" % (lib.fg_abi_version(), FG_ABI_VERSION))
     _lib = lib
     return lib
+
+
+def set_option(name, value):
+    """A/B switch of the library (include/formation_gym_b200.h fg_set_option); tests and profiling only."""
+    check(load().fg_set_option(name.encode(), int(value)), "fg_set_option")
+
+
+def get_option(name):
+    v = C.c_int()
+    check(load().fg_get_option(name.encode(), C.byref(v)), "fg_get_option")
+    return v.value
+
+
+class options(object):
+    """``with options(force_tile_kernel=1): ...`` -- set A/B switches for a block and restore them after."""
+
+    def __init__(self, **kw):
+        self.kw, self.old = kw, {}
+
+    def __enter__(self):
+        for k, v in self.kw.items():
+            self.old[k] = get_option(k)
+            set_option(k, v)
+        return self
+
+    def __exit__(self, *exc):
+        for k, v in self.old.items():
+            set_option(k, v)
+        return False
 
 
 def check(rc, what):

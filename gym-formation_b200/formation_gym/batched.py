@@ -154,6 +154,9 @@ class BatchedFormationEnv:
         self.launches = 0                                        # kernels launched by this object
         # device-side tick (CUDA graphs): [0] is added to the host tick, [1] is the kernels' arrival
         # counter.  Stays zero -- and the host counter advances -- until use_device_tick(True).
+        # sticky per-env flag of the reference's failure mode (coincident agents -> NaN state, core.py:312 /
+        # train/README.md:194-197); set by the kernels, cleared by reset() / clear_nan_flags()
+        self.nan_flag = torch.zeros(E, dtype=torch.uint8, device=self.device)
         self._tick_dev = torch.zeros(2, dtype=torch.int32, device=self.device)
         self._device_tick = False
         self._ext_bufs = None
@@ -164,7 +167,9 @@ class BatchedFormationEnv:
         b = nat.fg_buffers()
         b.pos, b.vel = nat.ptr(self.pos), nat.ptr(self.vel)
         b.act = nat.ptr(act) if act is not None else nat.ptr(self.actions)
-        b.comm = nat.ptr(self.comm)
+        # silent agents: c == 0 always (core.py:281-282) and self.comm stays the zeros it was created with, so the
+        # kernels need not store it every step (8N B per env-step, 6 % of the traffic at N = 3)
+        b.comm = None if self.silent else nat.ptr(self.comm)
         b.ideal_shape, b.ideal_vel = nat.ptr(self.ideal_shape), nat.ptr(self.ideal_vel)
         b.landmarks = nat.ptr(self.landmarks)
         b.landmark_vel = nat.ptr(self.landmark_vel)
@@ -174,6 +179,7 @@ class BatchedFormationEnv:
         b.ep_return, b.ep_collisions = nat.ptr(self.ep_return), nat.ptr(self.ep_collisions)
         b.stats = nat.ptr(self.stats)
         b.tick_dev = nat.ptr(self._tick_dev) if self._device_tick else None
+        b.nan_flag = nat.ptr(self.nan_flag)
         return b
 
     def _stream(self):
@@ -240,6 +246,9 @@ class BatchedFormationEnv:
             self.launches += 1
         if mask is None:
             self.stats.zero_()
+            self.nan_flag.zero_()
+        else:
+            self.nan_flag.masked_fill_(m.bool(), 0)
         return self.observe()
 
     def observe(self):
@@ -276,10 +285,21 @@ class BatchedFormationEnv:
         self._launch_fused(b, 1, 0)
         return self.obs, self.reward, self.done, {"individual_reward": self.indiv}
 
-    def step_random(self):
-        """Random policy (test.py:20) drawn in-kernel from Philox, then the fused step."""
-        self._launch_fused(self._bufs, 1, 1)
+    def step_random(self, record_actions=False):
+        """Random policy (test.py:20) drawn in-kernel from Philox, then the fused step -- ONE launch.
+        ``record_actions=True`` also writes the drawn actions into ``self.actions`` (what a trainer's replay
+        buffer needs), i.e. the same result as ``sample_actions(); step(self.actions)`` in one kernel."""
+        self._launch_fused(self._bufs, 1, 2 if record_actions else 1)
         return self.obs, self.reward, self.done, {"individual_reward": self.indiv}
+
+    def nan_envs(self, clear=False):
+        """Indices of envs that hit the reference's documented failure mode since the flags were last cleared:
+        coincident agents make ``delta_pos / dist`` NaN (core.py:312) and the env's state and rewards stay NaN until
+        its next reset (train/README.md:194-197).  Synchronises."""
+        idx = torch.nonzero(self.nan_flag, as_tuple=False).flatten()
+        if clear:
+            self.nan_flag.zero_()
+        return idx
 
     def sample_actions(self, out=None):
         """``[space.sample() for space in env.action_space]`` for every env: U(-1,1), on device.
@@ -328,34 +348,38 @@ class BatchedFormationEnv:
             nat.check(rc, "fg_step_fused")
             self.launches += 1
 
-    def capture_steps(self, n_steps=1, policy=None):
+    def capture_steps(self, n_steps=1, policy=None, fused_random=False):
         """Capture ``n_steps`` x (policy, fused env step) into ONE CUDA graph and return it; call
         ``graph.replay()`` to run them.  ``policy=None`` is the random policy (test.py:20) written
         into ``self.actions``; otherwise ``policy(env)`` is called during capture and must enqueue,
-        on the current stream, whatever fills ``self.actions`` from ``self.obs``.  Replays cost no
-        host work per step, which is what small batches (launch-bound per step) need.  Turns the
-        device tick on."""
+        on the current stream, whatever fills ``self.actions`` from ``self.obs``.
+        ``fused_random=True``: the random policy is drawn AND recorded into ``self.actions`` inside the
+        step kernel (``step_random(record_actions=True)``): one launch per step, same results.
+        Replays cost no host work per step, which is what small batches (launch-bound per step) need.
+        Turns the device tick on."""
         self.use_device_tick(True)
         torch.cuda.synchronize(self.device)
         side = torch.cuda.Stream(device=self.device)
         side.wait_stream(torch.cuda.current_stream(self.device))
 
-        def body():
-            for _ in range(int(n_steps)):
-                if policy is None:
-                    self.sample_actions()
-                else:
-                    policy(self)
-                self._launch_fused(self._bufs, 1, 0)
+        def one():
+            if fused_random:
+                self._launch_fused(self._bufs, 1, 2)
+                return
+            if policy is None:
+                self.sample_actions()
+            else:
+                policy(self)
+            self._launch_fused(self._bufs, 1, 0)
 
         with torch.cuda.stream(side):          # warm-up outside capture (lazy module loading, statics)
-            self.sample_actions() if policy is None else policy(self)
-            self._launch_fused(self._bufs, 1, 0)
+            one()
         torch.cuda.current_stream(self.device).wait_stream(side)
         torch.cuda.synchronize(self.device)
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
-            body()
+            for _ in range(int(n_steps)):
+                one()
         return graph
 
     def render(self, env_index=0, mode='rgb_array', cam_range=None):

@@ -105,14 +105,17 @@ class MultiAgentEnv(object):
         cls = type(sc)
         from .envs import (formation_hd_env, basic_formation_env, formation_hd_partial_env,
                            formation_hd_partial_range_env, formation_hd_obs_env)
-        for stock in (formation_hd_env.Scenario, basic_formation_env.Scenario,
-                      formation_hd_partial_env.Scenario, formation_hd_partial_range_env.Scenario,
-                      formation_hd_obs_env.Scenario):
-            if isinstance(sc, stock):
-                if cls.observation is not stock.observation or cls.reward is not stock.reward:
-                    return None
-                return sc
-        return None
+        # most-derived stock class first: formation_hd_partial_range_env.Scenario subclasses the partial one
+        # (and overrides its hooks), so a plain isinstance() walk would match the wrong stock class
+        stocks = (formation_hd_partial_range_env.Scenario, formation_hd_partial_env.Scenario,
+                  formation_hd_obs_env.Scenario, formation_hd_env.Scenario, basic_formation_env.Scenario)
+        stock = next((s for s in stocks if cls is s), None) or next((s for s in stocks if isinstance(sc, s)), None)
+        if stock is None or stock.native_kind != kind:
+            return None
+        # a user subclass that overrides a hook gets the callback path (its Python code must run)
+        if cls.observation is not stock.observation or cls.reward is not stock.reward:
+            return None
+        return sc
 
     def _decode_u(self, action, agent):
         """The physical part of ``_set_action`` BEFORE the sensitivity scaling
@@ -186,8 +189,13 @@ class MultiAgentEnv(object):
             for i, agent in enumerate(self.agents):
                 a_u, a_c = self._split_action(action_n[i], agent)
                 acts.append(self._decode_u(a_u, agent))
+                # host records as _set_action leaves them (environment.py:188-236): callbacks and render code
+                # that read agent.action see the same values on the fused and on the callback path
+                agent.action.u = acts[-1] * (5.0 if agent.accel is None else agent.accel)
+                agent.action.c = np.zeros(self.world.dim_c)
                 if not silent:
                     acts_c.append(np.array(a_c, dtype=np.float64))
+                    agent.action.c = acts_c[-1].copy()
             self.world.world_step += 1
             out = self.world.backend().step_fused(
                 self.world, sc, sc.native_kind, np.stack(acts), self.current_step - 1,

@@ -42,7 +42,7 @@
 extern "C" {
 #endif
 
-#define FG_ABI_VERSION 6
+#define FG_ABI_VERSION 7
 #define FG_MAX_AGENTS 256      /* one CTA holds at least one whole env; 3^5 = 243 fits */
 #define FG_MAX_LANDMARKS 256
 #define FG_MAX_WALLS 8
@@ -144,10 +144,32 @@ typedef struct fg_buffers {
                                   advance it by the number of env steps they ran ([1] is their arrival
                                   counter).  Lets a CUDA graph of step launches be replayed with fresh
                                   random numbers although its kernel arguments are frozen. */
+    uint8_t* nan_flag;         /* (opt) [E] in/out, zero-initialised by the caller: set to 1 (and never cleared by
+                                  the library) when, after a step's physics, the env holds a non-finite position --
+                                  the reference's documented failure mode (coincident agents -> 0/0 in core.py:312,
+                                  NaN state and rewards until the next reset; train/README.md:194-197).  Written by
+                                  fg_step_fused and fg_obs_reward; costs no traffic while every env is finite. */
 } fg_buffers;
 
 int fg_abi_version(void);
 const char* fg_last_error(void);
+
+/* A/B switches for tests and profiling (never needed in production; defaults select the product kernels).  They are
+ * process-global, read once from the environment variables FG_<NAME IN UPPER CASE> when the library is first used
+ * (never on the launch path) and can be changed at run time here.  Names and ranges:
+ *   force_tile_kernel 0/1  fg_step_fused always takes the generic tile kernel instead of the warp-autonomous one
+ *   no_fast_pairs 0/1      tile kernel: scalar pair loops instead of the packed ones (N >= 32)
+ *   force_fast_pairs 0/1   tile kernel: packed pair loops also for 32 <= N < 64 with observations
+ *   no_cells 0/1           packed pair loops: O(N^2) group filters instead of the hashed cell lists
+ *   row_nbuf 1/2           long-row observation writer: staging buffers per warp
+ *   no_early_rows 0/1      long-row observation writer: rows leave after the reward pass
+ *   no_tile_image 0/1      short-row observation writer: flat item loop instead of the tile image
+ *   no_persistent_tiles 0/1  tile kernel: one CTA per tile instead of a persistent grid
+ *   waves 1..64            warp kernel: grid = waves x one resident wave
+ *   nvtx 0/1               NVTX ranges (domain-less, named after the entry point) around every launch
+ * Unknown names / out-of-range values return FG_ERR_ARG. */
+int fg_set_option(const char* name, int value);
+int fg_get_option(const char* name, int* value);
 /* SM count and compute capability of the current device (host logic sizes grids with it). */
 int fg_device_info(int* sm_count, int* cc_major, int* cc_minor);
 
@@ -178,7 +200,10 @@ int fg_obs_reward_f64(const fg_params* p, const fg_buffers* b, int scenario, int
  * terminal reward/done are returned together with the RESET observation).
  * n_steps > 1 runs a whole rollout inside the kernel with state held on chip; then actions are
  * drawn in-kernel from the random policy U(-1,1) (test.py:20) and b->act is ignored.
- * n_steps == 1 and random_actions == 0 is the plain step on caller-provided actions. */
+ * n_steps == 1 and random_actions == 0 is the plain step on caller-provided actions.
+ * random_actions == 2: as 1, and the drawn actions are also WRITTEN to b->act [E,N,2] (the one case in which the
+ * library writes that buffer) so that the caller has the (obs, action, reward) triple of the step -- the random
+ * policy and the step in one launch instead of fg_random_actions + fg_step_fused. */
 int fg_step_fused(const fg_params* p, const fg_buffers* b, int scenario, int E, int N, int L,
                   int n_steps, int random_actions, int auto_reset,
                   uint64_t seed, uint32_t tick, uint32_t env_offset, void* stream);

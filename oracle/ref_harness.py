@@ -26,7 +26,32 @@ import types
 
 import numpy as np
 
-REFERENCE_ROOT = os.environ.get("FG_REFERENCE_ROOT", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+STAGED_ROOT = os.path.join(_HERE, "_ref")           # written by oracle/make_ref.py (git-ignored; travels to the GPU box)
+
+
+def _pick_root():
+    """FG_REFERENCE_ROOT, else the read-only checkout (/root/reference, this container only), else the staged
+    byte-for-byte copy under oracle/_ref (the GPU box), verified against its sha256 manifest."""
+    env = os.environ.get("FG_REFERENCE_ROOT")
+    if env:
+        return env
+    if os.path.isfile("/root/reference/formation_gym/core.py"):
+        return "/root/reference"
+    try:
+        sys.path.insert(0, _HERE)
+        import make_ref
+        if make_ref.staged_ok(STAGED_ROOT):
+            return STAGED_ROOT
+    except Exception:
+        pass
+    finally:
+        if sys.path and sys.path[0] == _HERE:
+            sys.path.pop(0)
+    return "/root/reference"
+
+
+REFERENCE_ROOT = _pick_root()
 
 
 def reference_available():
@@ -200,13 +225,75 @@ def time_reference(scenario, num_agents, seconds=3.0, episode_length=25, seed=0)
             return steps, dt
 
 
+def _timed_worker(q, scenario, num_agents, episode_length, seed, max_steps, seconds, warmup):
+    """One env of the reference, random policy U(-1,1) (test.py:20), reset when all agents are done
+    (test.py:26-27).  Stops after `max_steps` env steps or `seconds`, whichever comes first."""
+    import time
+    np.random.seed(seed)
+    env = make_reference_env(scenario, num_agents, episode_length)
+    env.reset()
+    n = num_agents
+
+    def one():
+        act_n = [np.random.uniform(-1, 1, 2) for _ in range(n)]
+        _, _, done_n, _ = env.step(act_n)
+        if np.all(done_n):
+            env.reset()
+
+    for _ in range(warmup):
+        one()
+    steps, t0 = 0, time.perf_counter()
+    while steps < max_steps:
+        one()
+        steps += 1
+        if seconds is not None and time.perf_counter() - t0 >= seconds:
+            break
+    q.put((steps, time.perf_counter() - t0))
+
+
+def time_reference_parallel(scenario, num_agents, procs=None, seconds=3.0, max_steps=10 ** 9, episode_length=25,
+                            warmup=None):
+    """The reference's own way of running many envs (one OS process per env, SubprocVecEnv,
+    train/maddpg-v2/utils/env_wrappers.py:48-55): `procs` forked processes, one unmodified env each.
+    Returns a dict with the aggregate agent-steps/s (sum of env steps x N / slowest worker's wall time)."""
+    import multiprocessing as mp
+    procs = procs or (os.cpu_count() or 1)
+    if warmup is None:
+        warmup = 3 if num_agents > 100 else episode_length
+    load_reference()                                        # import once in the parent; the forks inherit it
+    ctx = mp.get_context("fork")
+    q = ctx.Queue()
+    ps = [ctx.Process(target=_timed_worker, args=(q, scenario, num_agents, episode_length, 100 + k, max_steps,
+                                                  seconds, warmup)) for k in range(procs)]
+    for p in ps:
+        p.start()
+    res = [q.get() for _ in ps]
+    for p in ps:
+        p.join()
+    env_steps = sum(r[0] for r in res)
+    wall = max(r[1] for r in res)
+    import scipy
+    return {"scenario": scenario, "agents": num_agents, "procs": procs, "env_steps": env_steps, "wall_s": wall,
+            "steps_per_worker": [r[0] for r in res][:4],
+            "env_steps_per_s": env_steps / wall, "agent_steps_per_s": env_steps * num_agents / wall,
+            "reference_root": REFERENCE_ROOT, "numpy": np.__version__, "scipy": scipy.__version__}
+
+
 if __name__ == "__main__":
     import argparse
-    ap = argparse.ArgumentParser(description="time the unmodified reference (this container only)")
+    import json
+    ap = argparse.ArgumentParser(description="time the unmodified reference on the host cores (prints one JSON line)")
     ap.add_argument("--scenario", default="formation_hd_env")
     ap.add_argument("--agents", type=int, default=9)
     ap.add_argument("--seconds", type=float, default=3.0)
+    ap.add_argument("--procs", type=int, default=0, help="0 = os.cpu_count()")
+    ap.add_argument("--max-steps", type=int, default=10 ** 9)
+    ap.add_argument("--episode-length", type=int, default=25)
+    ap.add_argument("--warmup", type=int, default=-1)
     a = ap.parse_args()
-    s, dt = time_reference(a.scenario, a.agents, a.seconds)
-    print({"scenario": a.scenario, "agents": a.agents, "env_steps_per_s": s / dt,
-           "agent_steps_per_s": s * a.agents / dt})
+    if not reference_available():
+        print(json.dumps({"unavailable": "no reference tree at %s" % REFERENCE_ROOT}))
+        sys.exit(0)
+    r = time_reference_parallel(a.scenario, a.agents, a.procs or None, a.seconds, a.max_steps, a.episode_length,
+                                None if a.warmup < 0 else a.warmup)
+    print(json.dumps(r))

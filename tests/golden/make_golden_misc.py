@@ -99,7 +99,29 @@ def run_scripted(seed):
     return {k: np.array(v) for k, v in d.items()}
 
 
+def run_bfs_inconsistent(seed, n_layer=3, layers=2):
+    """get_action_BFS(ezpolicy, obs_n, 3) of the unmodified reference (formation_gym/__init__.py:19-98) on
+    observations that do NOT describe one consistent state: some agents' other_pos slices are perturbed (what a
+    noisy / clipping observation wrapper produces).  The reference reads every leader's and member's OWN
+    observation, so the result differs from what agent 0's observation alone would give."""
+    fg = rh.load_reference()
+    N = n_layer ** layers
+    np.random.seed(seed)
+    env = fg.make_env("formation_hd_env", False, N)
+    obs_n = [np.array(o, np.float64) for o in env.reset()]
+    rng = np.random.default_rng(seed)
+    clean = np.stack(obs_n)
+    act_clean = np.stack(fg.get_action_BFS(fg.ezpolicy, [o.copy() for o in obs_n], n_layer))
+    for j in (1, 3, 4, 8):
+        obs_n[j][2:2 * N] += rng.normal(0.0, 0.2, 2 * N - 2)
+    noisy = np.stack(obs_n)
+    act_noisy = np.stack(fg.get_action_BFS(fg.ezpolicy, [o.copy() for o in obs_n], n_layer))
+    assert np.abs(act_noisy - act_clean).max() > 1e-3
+    return dict(obs_clean=clean, act_clean=act_clean, obs_noisy=noisy, act_noisy=act_noisy, n=np.int64(n_layer))
+
+
 if __name__ == "__main__":
+    np.savez_compressed(os.path.join(HERE, "policy_bfs_inconsistent_n9.npz"), **run_bfs_inconsistent(5))
     out = {}
     for k, v in run_scripted(31).items():
         out["scripted/" + k] = v

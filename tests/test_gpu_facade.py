@@ -216,3 +216,38 @@ def test_scripted_agent_and_callbacks():
         assert all(set(i.keys()) == {"individual_reward", "fail"} for i in info_n)
         assert np.abs(np.stack([a.state.p_pos for a in world.agents]) - key("pos")[t]).max() <= 1e-9
     assert calls["post"] == int(key("post_calls")) == 4
+
+
+@pytest.mark.parametrize("scenario,n", [("formation_hd_env", 9), ("basic_formation_env", 3),
+                                        ("formation_hd_partial_env", 5), ("formation_hd_partial_range_env", 4),
+                                        ("formation_hd_obs_env", 4)])
+def test_every_stock_scenario_steps_in_one_fused_launch(scenario, n):
+    """env.step of every stock scenario = ONE kernel launch (fg_step_fused), and the host records of the actions
+    are what the reference's _set_action leaves (environment.py:188-236: u = action * sensitivity, c = 0)."""
+    np.random.seed(2)
+    env = formation_gym.make_env(scenario, False, n, 10)
+    env.reset()
+    be = env.world.backend()
+    for _ in range(3):
+        before = be.launches
+        acts = [np.random.uniform(-1, 1, 2) for _ in range(n)]
+        obs_n, reward_n, done_n, info_n = env.step([a.copy() for a in acts])
+        assert be.launches == before + 1
+        for a, ag in zip(acts, env.world.agents):
+            assert np.allclose(ag.action.u, a * 5.0, rtol=0, atol=0) and np.all(ag.action.c == 0)
+    assert len(obs_n) == n and obs_n[0].shape == tuple(env.observation_space[0].shape)
+
+
+def test_hook_cache_sees_changed_constants():
+    """The scenario hooks share one cached launch per state; the cache key must cover the constants the kernels read
+    (round-1 advice: agent.size sets the reward's collision threshold)."""
+    np.random.seed(4)
+    env = formation_gym.make_env("formation_hd_env", False, 3, 10)
+    env.reset()
+    w, sc = env.world, env.observation_callback.__self__
+    w.agents[0].state.p_pos = np.array([0.0, 0.0]); w.agents[1].state.p_pos = np.array([0.04, 0.0])
+    r_small = sc.reward(w.agents[0], w)                  # |dp| = 0.04 >= (0.03 + 0.03) / 2: no collision
+    for a in w.agents:
+        a.size = 0.05                                    # threshold (0.05 + 0.05) / 2 = 0.05 > 0.04: collision
+    r_big = sc.reward(w.agents[0], w)
+    assert abs((r_small - r_big) - 1.0) <= 1e-12

@@ -18,6 +18,7 @@ import torch
 pytestmark = pytest.mark.gpu
 
 import formation_gym  # noqa: E402
+from formation_gym import _native as nat  # noqa: E402
 from formation_gym.batched import BatchedFormationEnv  # noqa: E402
 from oracle import mpe_oracle as mo  # noqa: E402
 
@@ -53,13 +54,18 @@ HD_SINGLE = sorted(os.path.basename(p) for p in glob.glob(os.path.join(GOLD, "hd
                    + glob.glob(os.path.join(GOLD, "hd_n*_clustered.npz")))
 
 
+@pytest.mark.parametrize("track_landmarks", [True, False], ids=["tile+landmarks", "product"])
 @pytest.mark.parametrize("dtype", [torch.float32, torch.float64], ids=["f32", "f64"])
 @pytest.mark.parametrize("name", HD_SINGLE)
-def test_hd_single_step_golden(name, dtype):
+def test_hd_single_step_golden(name, dtype, track_landmarks):
+    """Fixtures frozen from the unmodified reference.  track_landmarks=True also checks the landmark shift of the
+    observation hook (formation_hd_env.py:40-44) and therefore runs on the tile kernel; track_landmarks=False is the
+    product configuration: N = 3 / 9 / 27 take the warp-autonomous kernel k_hd_warp (the headline kernel), N = 243 the
+    tile kernel with the packed pair loops."""
     g = load(name)
     E, N = g["pos0"].shape[:2]
     env = BatchedFormationEnv("formation_hd_env", E, N, episode_length=25, dtype=dtype,
-                              auto_reset=False, track_landmarks=True)
+                              auto_reset=False, track_landmarks=track_landmarks)
     inject_hd(env, g)
     obs, rew, done, info = env.step(dev(g["act"], dtype))
     tol = F32_TOL if dtype == torch.float32 else 1e-12
@@ -73,7 +79,8 @@ def test_hd_single_step_golden(name, dtype):
     assert np.all(np.abs(rew[:, :, 0].double().cpu().numpy() - R) <= tol + rtol * np.abs(R))
     assert np.array_equal(done.cpu().numpy(), g["done"])
     assert np.array_equal(env.step_count.cpu().numpy(), g["step0"] + 1)
-    assert maxerr(env.landmarks, g["landmarks"]) <= (1e-5 if dtype == torch.float32 else 1e-12)
+    if track_landmarks:
+        assert maxerr(env.landmarks, g["landmarks"]) <= (1e-5 if dtype == torch.float32 else 1e-12)
 
 
 @pytest.mark.parametrize("n", [3, 9, 27, 243])
@@ -217,6 +224,46 @@ def test_hd_vs_oracle_random(E, N, spread):
         assert bool((rew == rew[:, :1]).all())
 
 
+@pytest.mark.parametrize("cells", [1, 0], ids=["cells", "filters"])
+@pytest.mark.parametrize("E,N,scale", [(6, 32, 0.12), (5, 81, 0.12), (3, 243, 0.12), (2, 256, 0.12), (3, 243, 1.0),
+                                       (4, 100, 0.3), (9, 64, 0.05)])
+def test_no_obs_kernel_vs_oracle(E, N, scale, cells):
+    """write_obs=False at N >= 32 runs the packed pair loops with cell lists (fg_pairs.cuh) -- the kernel the FP32
+    figure is quoted on.  Against the ORACLE (not another kernel), dense clusters (scale 0.12: tens of contact partners
+    and reward collisions per agent), fp32 single step: 1e-5 abs on pos / vel / individual reward, shared reward
+    atol 1e-5 + rtol 1e-6; collision counts exact (they are integers inside the rewards)."""
+    rng = np.random.default_rng(E * 7919 + N)
+    f32 = lambda x: x.astype(np.float32).astype(np.float64)  # noqa: E731
+    pos = f32(rng.uniform(-scale, scale, (E, N, 2)))
+    vel = f32(rng.uniform(-0.5, 0.5, (E, N, 2)))
+    act = f32(rng.uniform(-1, 1, (E, N, 2)))
+    lm = rng.uniform(-1, 1, (E, N, 2))
+    shape = f32(lm - lm.mean(1, keepdims=True))
+    ivel = f32(rng.uniform(-1, 1, (E, 2)))
+    step0 = rng.integers(0, 25, E)
+    ref = mo.hd_env_step(pos, vel, act, shape, ivel, step0, mo.WorldParams(world_length=25))
+    with nat.options(no_cells=int(not cells)):
+        env = BatchedFormationEnv("formation_hd_env", E, N, episode_length=25, auto_reset=False, write_obs=False)
+        inject_hd(env, dict(pos0=pos, vel0=vel, shape=shape, ivel=ivel, step0=step0), lm=False)
+        obs, rew, done, info = env.step(dev(act, torch.float32))
+        torch.cuda.synchronize()
+    assert obs is None
+    assert maxerr(env.pos, ref["pos"]) <= F32_TOL
+    assert maxerr(env.vel, ref["vel"]) <= F32_TOL
+    assert maxerr(info["individual_reward"], ref["indiv"]) <= F32_TOL
+    R = ref["reward"]
+    assert np.all(np.abs(rew[:, 0, 0].double().cpu().numpy() - R) <= F32_TOL + 1e-6 * np.abs(R))
+    assert np.array_equal(done[:, 0].cpu().numpy(), ref["done"])
+    # reward collisions: the per-agent count is the integer part separating indiv from the shared base term
+    base = ref["indiv"].max(axis=1, keepdims=True)                       # an agent without collisions (if any)
+    col_ref = np.rint(base - ref["indiv"])
+    got = info["individual_reward"].double().cpu().numpy()
+    col_got = np.rint(got.max(axis=1, keepdims=True) - got)
+    assert np.array_equal(col_ref, col_got)
+    if scale <= 0.12:
+        assert col_ref.sum() > 0                                          # the dense case does exercise collisions
+
+
 @pytest.mark.parametrize("dtype", [torch.float32, torch.float64], ids=["f32", "f64"])
 def test_separate_entry_points_match_fused(dtype):
     """fg_world_step + fg_obs_reward == fg_step_fused: bit-exact in the fp64 build (no FMA
@@ -243,8 +290,7 @@ def test_separate_entry_points_match_fused(dtype):
 def _run_steps(E, N, dtype, steps, force_tile, episode_length=7, u_noise=None, rollout=False, seed=11):
     """`steps` random-policy steps with auto-reset; FG_FORCE_TILE_KERNEL=1 routes fg_step_fused to
     the generic tile kernel (fg_kernels.cuh) instead of the warp-autonomous one (fg_warp.cuh)."""
-    os.environ["FG_FORCE_TILE_KERNEL"] = "1" if force_tile else "0"
-    try:
+    with nat.options(force_tile_kernel=int(force_tile)):
         env = BatchedFormationEnv("formation_hd_env", E, N, episode_length=episode_length, dtype=dtype,
                                   seed=seed, auto_reset=True, u_noise=u_noise)
         env.reset()
@@ -262,8 +308,6 @@ def _run_steps(E, N, dtype, steps, force_tile, episode_length=7, u_noise=None, r
                                                     "stats")}
         out["done"] = env.done.clone()
         return out, hist
-    finally:
-        os.environ.pop("FG_FORCE_TILE_KERNEL", None)
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.float64], ids=["f32", "f64"])
@@ -362,9 +406,7 @@ def test_graph_replay_equals_stepwise(N, E):
 # ------------------------------------------------------------------ packed pair loops vs scalar tile kernel
 def _run_tile(E, N, steps, fast, scale, rollout=False, obs=True, seed=31):
     """fp32 tile kernel with (fast) or without (FG_NO_FAST_PAIRS=1) the packed pair loops of fg_pairs.cuh."""
-    os.environ["FG_NO_FAST_PAIRS"] = "0" if fast else "1"
-    os.environ["FG_FORCE_FAST_PAIRS"] = "1" if fast else "0"
-    try:
+    with nat.options(no_fast_pairs=int(not fast), force_fast_pairs=int(fast)):
         env = BatchedFormationEnv("formation_hd_env", E, N, episode_length=5, seed=seed, auto_reset=True,
                                   write_obs=obs)
         env.reset()
@@ -380,9 +422,6 @@ def _run_tile(E, N, steps, fast, scale, rollout=False, obs=True, seed=31):
         out = {k: getattr(env, k).clone() for k in keys}
         out["done"] = env.done.clone()
         return out
-    finally:
-        os.environ.pop("FG_NO_FAST_PAIRS", None)
-        os.environ.pop("FG_FORCE_FAST_PAIRS", None)
 
 
 @pytest.mark.parametrize("E,N,scale", [(7, 32, 0.3), (5, 81, 0.5), (6, 100, 1.0), (3, 243, 1.0), (2, 243, 0.12),
@@ -415,9 +454,7 @@ def test_fast_pairs_nan_env_matches_reference_pattern():
     """Coincident agents (core.py:312) inside a large env: the NaN spreads exactly as in the scalar kernel."""
     outs = []
     for fast in (True, False):
-        os.environ["FG_NO_FAST_PAIRS"] = "0" if fast else "1"
-        os.environ["FG_FORCE_FAST_PAIRS"] = "1" if fast else "0"
-        try:
+        with nat.options(no_fast_pairs=int(not fast), force_fast_pairs=int(fast)):
             env = BatchedFormationEnv("formation_hd_env", 3, 81, episode_length=25, seed=2, auto_reset=False)
             env.reset()
             env.pos[1, 40] = env.pos[1, 7]                 # env 1: agents 7 and 40 coincide
@@ -426,9 +463,6 @@ def test_fast_pairs_nan_env_matches_reference_pattern():
                 env.step(act)
             torch.cuda.synchronize()
             outs.append({k: getattr(env, k).clone() for k in ("pos", "vel", "reward", "indiv", "obs")})
-        finally:
-            os.environ.pop("FG_NO_FAST_PAIRS", None)
-            os.environ.pop("FG_FORCE_FAST_PAIRS", None)
     a, b = outs
     assert bool(torch.isnan(a["pos"][1]).all()) and not bool(torch.isnan(a["pos"][0]).any())
     for k in a:
@@ -440,9 +474,7 @@ def test_fast_pairs_far_agents_take_the_exhaustive_fallback():
     same contacts, same collision counts as the scalar kernel (the far agent has a partner in contact range)."""
     outs = []
     for fast in (True, False):
-        os.environ["FG_NO_FAST_PAIRS"] = "0" if fast else "1"
-        os.environ["FG_FORCE_FAST_PAIRS"] = "1" if fast else "0"
-        try:
+        with nat.options(no_fast_pairs=int(not fast), force_fast_pairs=int(fast)):
             env = BatchedFormationEnv("formation_hd_env", 4, 243, episode_length=25, seed=5, auto_reset=False,
                                       write_obs=False)
             env.reset()
@@ -455,9 +487,6 @@ def test_fast_pairs_far_agents_take_the_exhaustive_fallback():
                 env.step(act)
             torch.cuda.synchronize()
             outs.append({k: getattr(env, k).clone() for k in ("pos", "vel", "reward", "indiv", "ep_collisions")})
-        finally:
-            os.environ.pop("FG_NO_FAST_PAIRS", None)
-            os.environ.pop("FG_FORCE_FAST_PAIRS", None)
     a, b = outs
     assert torch.equal(a["ep_collisions"], b["ep_collisions"]) and int(a["ep_collisions"][2]) >= 2
     assert float((a["vel"][2, 11] - a["vel"][2, 200]).abs().max()) > 1.0        # the far pair pushed each other apart
@@ -479,8 +508,7 @@ def test_tile_image_writer_equals_flat_writer(scen, E, N, kw, dtype):
     observation buffer that starts on an odd 8-byte slot."""
     outs = []
     for off in ("0", "1"):
-        os.environ["FG_NO_TILE_IMAGE"] = off
-        try:
+        with nat.options(no_tile_image=int(off)):
             env = BatchedFormationEnv(scen, E, N, episode_length=3, seed=11, dtype=dtype, **kw)
             big = torch.zeros(E * N * env.D + 4, dtype=dtype, device="cuda")
             env.obs = big[2:2 + E * N * env.D].view(E, N, env.D)            # fp32: odd 8-byte slot of a 16-byte line
@@ -494,8 +522,6 @@ def test_tile_image_writer_equals_flat_writer(scen, E, N, kw, dtype):
             res.append(env.obs.clone())
             assert float(big[:2].abs().sum()) == 0.0 and float(big[-2:].abs().sum()) == 0.0   # nothing outside the buffer
             outs.append(res)
-        finally:
-            os.environ.pop("FG_NO_TILE_IMAGE", None)
     for x, y in zip(*outs):
         assert torch.equal(torch.nan_to_num(x), torch.nan_to_num(y))
 
@@ -512,8 +538,7 @@ def test_misaligned_vector_buffers_are_rejected():
 
 
 def _run_basic(E, dtype, steps, force_tile, rollout=False, u_noise=None):
-    os.environ["FG_FORCE_TILE_KERNEL"] = "1" if force_tile else "0"
-    try:
+    with nat.options(force_tile_kernel=int(force_tile)):
         env = BatchedFormationEnv("basic_formation_env", E, 3, episode_length=7, dtype=dtype, seed=13,
                                   auto_reset=True, u_noise=u_noise)
         env.reset()
@@ -530,8 +555,6 @@ def _run_basic(E, dtype, steps, force_tile, rollout=False, u_noise=None):
                                                     "ep_return", "ep_collisions", "stats")}
         out["done"] = env.done.clone()
         return out, hist
-    finally:
-        os.environ.pop("FG_FORCE_TILE_KERNEL", None)
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.float64], ids=["f32", "f64"])

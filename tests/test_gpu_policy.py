@@ -86,3 +86,15 @@ def test_policy_drives_formation_and_facade_functions():
     got2 = formation_gym.get_action_BFS(lambda ob: (calls.append(len(ob)), formation_gym.ezpolicy(ob))[1], obs_n, 3)
     assert len(calls) == 3 + 9 and set(calls) == {18}
     assert np.abs(np.stack(got2) - want).max() <= 1e-9
+
+
+def test_get_action_BFS_reads_every_observation_like_the_reference():
+    """Host API get_action_BFS(ezpolicy, obs_n, 3): consistent observations take the one-launch device tree;
+    observations a wrapper has perturbed (round-1 advice: the shortcut used obs[0] only) take the host tree walk
+    that reads each leader's / member's own row.  Both against the unmodified reference (fixture)."""
+    g = np.load(os.path.join(GOLD, "policy_bfs_inconsistent_n9.npz"))
+    n = int(g["n"])
+    act = np.stack(formation_gym.get_action_BFS(formation_gym.ezpolicy, list(g["obs_clean"]), n))
+    assert np.abs(act - g["act_clean"]).max() <= 1e-12
+    act = np.stack(formation_gym.get_action_BFS(formation_gym.ezpolicy, list(g["obs_noisy"]), n))
+    assert np.abs(act - g["act_noisy"]).max() <= 1e-12

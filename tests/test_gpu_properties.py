@@ -250,3 +250,46 @@ def test_non_silent_agents_communicate(N):
     noisy.step(a4)
     c = noisy.comm.double().flatten()
     assert abs(float(c.mean())) < 2e-3 and abs(float(c.std()) - 0.05) < 2e-3
+
+
+@pytest.mark.parametrize("scen,N,E", [("formation_hd_env", 9, 777), ("formation_hd_env", 27, 50), ("formation_hd_env", 81, 9),
+                                      ("basic_formation_env", 3, 1000), ("basic_formation_env", 5, 300)])
+def test_fused_random_policy_records_the_same_actions(scen, N, E):
+    """step_random(record_actions=True) (fg_step_fused random_actions = 2: the policy drawn AND recorded inside the step
+    kernel, one launch) == sample_actions() + step(actions) (two launches): same actions, bit-identical results,
+    across auto-resets; warp kernel (N = 9, 27, basic 3) and tile kernel (N = 81, basic 5)."""
+    a = BatchedFormationEnv(scen, E, N, episode_length=4, seed=9, auto_reset=True)
+    b = BatchedFormationEnv(scen, E, N, episode_length=4, seed=9, auto_reset=True)
+    a.reset(); b.reset()
+    for _ in range(9):
+        a.step_random(record_actions=True)
+        b.sample_actions(); b.step(b.actions)
+        assert torch.equal(a.actions, b.actions)
+    for k in ("pos", "vel", "obs", "reward", "indiv", "step_count", "ep_return"):
+        assert torch.equal(getattr(a, k), getattr(b, k)), k
+    assert float(a.actions.abs().max()) <= 1.0 and float(a.actions.abs().max()) > 0.9
+
+
+@pytest.mark.parametrize("scen,N", [("formation_hd_env", 9), ("formation_hd_env", 40), ("formation_hd_env", 243),
+                                    ("basic_formation_env", 3), ("basic_formation_env", 6), ("formation_hd_partial_env", 5),
+                                    ("formation_hd_obs_env", 4)])
+def test_nan_flag_marks_exactly_the_failed_envs(scen, N):
+    """fg_buffers.nan_flag: sticky per-env flag of the reference's documented failure mode (coincident agents ->
+    delta_pos / dist = 0/0, core.py:312; train/README.md:194-197).  Only the env with two coincident agents is flagged;
+    the flag survives further steps, an auto-reset heals the env but not the flag, reset() clears it."""
+    E = 12
+    env = BatchedFormationEnv(scen, E, N, episode_length=3, seed=3, auto_reset=True)
+    env.reset()
+    assert int(env.nan_flag.sum()) == 0
+    env.step_random()
+    assert int(env.nan_flag.sum()) == 0 and env.nan_envs().numel() == 0
+    env.pos[5, 1] = env.pos[5, 0]                                   # env 5: agents 0 and 1 coincide
+    env.step_random()
+    torch.cuda.synchronize()
+    assert env.nan_envs().tolist() == [5]
+    assert bool(torch.isnan(env.reward[5]).all()) and not bool(torch.isnan(env.reward[:5]).any())
+    for _ in range(3):                                              # episode ends -> env 5 is reset and healthy again
+        env.step_random()
+    assert not bool(torch.isnan(env.pos).any())
+    assert env.nan_envs(clear=True).tolist() == [5]                 # sticky until cleared
+    assert env.nan_envs().numel() == 0
