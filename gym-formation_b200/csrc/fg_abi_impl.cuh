@@ -36,6 +36,8 @@ struct Switches {
     std::atomic<int> force_tile_kernel{0};  // fg_step_fused never takes the warp-autonomous kernel
     std::atomic<int> waves{1};              // warp kernel: grid = waves x one resident wave (>= 1)
     std::atomic<int> no_persistent_tiles{0};// tile kernel: one CTA per tile instead of a persistent grid
+    std::atomic<int> no_std_kernel{0};      // warp kernel: never the STD instantiation (standard configuration, flags compiled out)
+    std::atomic<int> l2_prefetch{1};        // warp kernel: prefetch.global.L2 of the state two spans ahead: 0 never, 1 auto, 2 always
     std::atomic<int> nvtx{1};               // NVTX ranges around the launches of every entry point
 };
 Switches& switches();                                         // defined in fg_abi_f32.cu
@@ -175,6 +177,16 @@ int fill_args(fg::KArgs<T>& a, const fg_params* p, const fg_buffers* b, int scen
         a.walls[w].end1 = (T)p->walls[w].end1; a.walls[w].width = (T)p->walls[w].width;
     }
     a.n_steps = 1; a.random_actions = 0; a.auto_reset = 0;
+    {
+        // warp kernel: L2 prefetch of the state two spans ahead (fg_warp.cuh) once the four per-agent state arrays
+        // (pos, vel, act, ideal_shape) no longer stay resident in the 126 MB L2 next to the observation stream.
+        // Measured (B200, fp32, step kernel alone): N = 27 x 65536 envs (57 MB of state) 0.80 -> 0.90 of the HBM peak,
+        // N = 27 x 262144 0.72 -> 0.87, basic N = 3 x 1 M 0.66 -> 0.72; but N = 9 x 131072 (38 MB, L2-resident)
+        // 0.95 -> 0.88: each prefetch.global.L2 holds its warp for an L2 round trip.
+        const int mode = fgabi::switches().l2_prefetch.load(std::memory_order_relaxed);       // 0 never, 1 auto, 2 always
+        const double state_bytes = (double)E * (double)N * 4.0 * (double)sizeof(R2);
+        a.pf_dist = mode == 2 || (mode == 1 && state_bytes > 44e6) ? 1 : 0;
+    }
     a.seed = seed; a.tick = tick; a.env_offset = env_offset;
     // long hd rows of silent agents: static 2/3 of each row bulk-stored from one shared image
     // (measured: N = 243 270 us vs 353 us with plain stores; break-even near N = 50)
@@ -329,7 +341,7 @@ int launch_obstacle(const fg::KArgs<T>& a, void* stream) {
 // observation-span image per warp).  Computed once per instantiation; all GPUs of a box are alike.
 struct WarpGeom { int ctas[4]; int best; int sms; };      // index: log2(w), w = 1, 2, 4, 8
 
-template <typename T, int N, bool WOBS, int SCN>
+template <typename T, int N, bool WOBS, int SCN, bool STD>
 const WarpGeom& warp_geom() {
     static const WarpGeom geom = [] {
         typedef fg::WarpLayout<T, N, WOBS> LY;
@@ -343,30 +355,35 @@ const WarpGeom& warp_geom() {
             const size_t smem = (size_t)w * LY::stride;
             g_.ctas[l] = 0;
             if (smem > 227 * 1024 || w > LY::MAXW) continue;
-            if (cudaFuncSetAttribute(fg::k_hd_warp<T, N, WOBS, SCN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+            if (cudaFuncSetAttribute(fg::k_hd_warp<T, N, WOBS, SCN, STD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)smem) != cudaSuccess) { cudaGetLastError(); continue; }
             int ctas = 0;
-            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, fg::k_hd_warp<T, N, WOBS, SCN>, 32 * w, smem)
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, fg::k_hd_warp<T, N, WOBS, SCN, STD>, 32 * w, smem)
                 != cudaSuccess) { cudaGetLastError(); continue; }
             g_.ctas[l] = ctas;
             if (ctas * w > best_res) { best_res = ctas * w; g_.best = l; }
         }
+        // the probing above left the limit at the SMALLEST footprint, and a limit below the launch's request makes
+        // the launch fail (also under the 48 KB default): restore the default-or-larger value; launches raise it
+        // further through ensure_dyn_smem when they need more than 48 KB
+        cudaFuncSetAttribute(fg::k_hd_warp<T, N, WOBS, SCN, STD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 48 * 1024);
+        cudaGetLastError();
         return g_;
     }();
     return geom;
 }
 
-template <typename T, int N, bool WOBS, int SCN>
+template <typename T, int N, bool WOBS, int SCN, bool STD>
 int launch_warp_n(const fg::KArgs<T>& a, cudaStream_t st) {
     typedef fg::WarpLayout<T, N, WOBS> LY;
-    const WarpGeom& gm = warp_geom<T, N, WOBS, SCN>();
+    const WarpGeom& gm = warp_geom<T, N, WOBS, SCN, STD>();
     const int spans = (a.E + LY::EPW - 1) / LY::EPW;
     int l = gm.best;
     while (l > 0 && (spans >> l) < 2 * gm.sms) --l;                // small batches: spread over the SMs
     if (gm.ctas[l] < 1) return fail(FG_ERR_CUDA, "k_hd_warp does not fit on this device%s");
     const int w = 1 << l;
     const size_t smem = (size_t)w * LY::stride;
-    cudaError_t err = ensure_dyn_smem<fg::k_hd_warp<T, N, WOBS, SCN>>(smem);
+    cudaError_t err = ensure_dyn_smem<fg::k_hd_warp<T, N, WOBS, SCN, STD>>(smem);
     if (err != cudaSuccess) return fail(FG_ERR_CUDA, "cudaFuncSetAttribute failed: %s", cudaGetErrorString(err));
     // persistent warps: at most one resident wave; each warp walks spans gw, gw + nwarps, ...
     int grid = (spans + w - 1) / w;
@@ -374,7 +391,7 @@ int launch_warp_n(const fg::KArgs<T>& a, cudaStream_t st) {
     wave *= std::max(1, fgabi::switches().waves.load(std::memory_order_relaxed));
     if (grid > wave) grid = wave;
     if ((grid * w) & 1) ++grid;                                    // even warp count (16-byte phase, fg_warp.cuh)
-    fg::k_hd_warp<T, N, WOBS, SCN><<<grid, 32 * w, smem, st>>>(a);
+    fg::k_hd_warp<T, N, WOBS, SCN, STD><<<grid, 32 * w, smem, st>>>(a);
     err = cudaGetLastError();
     if (err != cudaSuccess) return fail(FG_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(err));
     return FG_OK;
@@ -382,7 +399,16 @@ int launch_warp_n(const fg::KArgs<T>& a, cudaStream_t st) {
 
 template <typename T, int N, int SCN = fg::kScnHD>
 int launch_warp(const fg::KArgs<T>& a, cudaStream_t st) {
-    return a.obs ? launch_warp_n<T, N, true, SCN>(a, st) : launch_warp_n<T, N, false, SCN>(a, st);
+    if constexpr (std::is_same<T, float>::value) {
+        // the standard product configuration has its own instantiation with these run-time tests compiled out
+        // (fg_warp.cuh, STD); anything else takes the generic one
+        const bool std_cfg = a.collide && !a.has_vmax && a.mass_one && !(a.u_noise > (T)0) && a.n_steps == 1 &&
+                             a.step && a.done && a.indiv && a.ep_return && a.ep_coll && a.stats && !a.comm &&
+                             !fgabi::switches().no_std_kernel.load(std::memory_order_relaxed);
+        if (std_cfg)
+            return a.obs ? launch_warp_n<T, N, true, SCN, true>(a, st) : launch_warp_n<T, N, false, SCN, true>(a, st);
+    }
+    return a.obs ? launch_warp_n<T, N, true, SCN, false>(a, st) : launch_warp_n<T, N, false, SCN, false>(a, st);
 }
 
 // The fast path covers the configurations BASELINE.json names for formation_hd_env with N <= 27.

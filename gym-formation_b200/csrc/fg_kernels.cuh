@@ -69,6 +69,7 @@ template <typename T> struct KArgs {
     int num_obs;                     // partial: observed neighbours (formation_hd_partial_env.py:15,53)
     T obs_range;                     // range: clip bound of other_pos (formation_hd_partial_range_env.py:15,53)
     int n_steps, random_actions, auto_reset;
+    int pf_dist;                     // warp kernel: > 0 = L2 prefetch of the state two spans ahead (see fg_warp.cuh)
     uint64_t seed; uint32_t tick; uint32_t env_offset;
     uint32_t* tick_dev;              // (opt) [2]: device tick added to `tick`, arrival counter (CUDA graphs)
     uint8_t* nan_flag;               // (opt) [E]: set to 1 (never cleared) when the env holds a non-finite position (Q9)

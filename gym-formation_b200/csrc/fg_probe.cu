@@ -119,6 +119,23 @@ __global__ void __launch_bounds__(256) k_wr_bulk(unsigned char* dst, size_t byte
     }
 }
 
+// variant 3: observation rows written with PLAIN 8-byte streaming stores from registers, the way a warp-per-env
+// kernel would write hd rows without a shared-memory image: `chunk` = N agents; a warp owns one env (N rows of 3N
+// float2 items, 8-byte aligned only) and writes, per row, the N dynamic items with one store instruction and the 2N
+// static items with ceil(2N / 32) more.
+__global__ void __launch_bounds__(128) k_wr_rows(float2* dst, size_t n_env, unsigned N) {
+    const unsigned lane = threadIdx.x & 31;
+    const size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarp = ((size_t)gridDim.x * blockDim.x) >> 5;
+    const float2 v = make_float2(1.f + (float)lane, 2.f);
+    for (size_t e = warp; e < n_env; e += nwarp) {
+        float2* out = dst + e * (size_t)N * 3 * N;
+        for (unsigned r = 0; r < N; ++r, out += 3 * N) {
+            for (unsigned k = lane; k < N; k += 32) __stcs(out + k, v);
+            for (unsigned k = N + lane; k < 3 * N; k += 32) __stcs(out + k, v);
+        }
+    }
+}
+
 }  // namespace
 
 extern "C" int fg_write_probe(int variant, void* dst, unsigned long long bytes, unsigned chunk, int ctas, void* stream) {
@@ -126,6 +143,9 @@ extern "C" int fg_write_probe(int variant, void* dst, unsigned long long bytes, 
     cudaStream_t st = (cudaStream_t)stream;
     if (variant == 0) {
         k_wr_stg<<<ctas, 256, 0, st>>>((float4*)dst, (size_t)(bytes / 16));
+    } else if (variant == 3) {
+        if (chunk < 1 || chunk > 256) return FG_ERR_ARG;
+        k_wr_rows<<<ctas, 128, 0, st>>>((float2*)dst, (size_t)(bytes / ((size_t)24 * chunk * chunk)), chunk);
     } else {
         if (chunk < 16 || (chunk & 15) || chunk > 200 * 1024) return FG_ERR_ARG;
         if (chunk > 48 * 1024 &&

@@ -66,7 +66,14 @@ template <typename T, int N, bool WOBS> struct WarpLayout {
 // kernel with lane i doubling as landmark i -- the landmark rides in the `S` slot of the ideal shape, the reward is
 // -sum_k min_a |p_a - l_k| - #{a incl. self : |p_a - p_i| < s_a + s_i} (basic_formation_env.py:43-52), the row is
 // [p_vel, p_pos, l_k - p, p_j - p, comm] (basic_formation_env.py:29-41; also 3N items when L == N).
-template <typename T, int N, bool WOBS, int SCN = kScnHD>
+//
+// STD (fp32 only): the standard product configuration, asserted by the host before it picks this instantiation --
+// agents collide, unit mass, no motor noise, no max_speed, one step per launch, the step / done / indiv / ep_return /
+// ep_collisions / stats buffers present and no comm buffer (silent agents: c == 0).  Each of these is otherwise a
+// warp-uniform run-time test (constant load + compare + branch, plus a reconvergence pair inside divergent code):
+// at N = 3 such tests were a fifth of the 61 instructions per env-step (profiles/r02b_warp3: ISETP 11.6 %, BRA 7.3 %,
+// LDCU 6.4 %, BSSY/BSYNC 7 % of all warp instructions).
+template <typename T, int N, bool WOBS, int SCN = kScnHD, bool STD = false>
 __global__ void __launch_bounds__(32 * WarpLayout<T, N, WOBS>::MAXW, WarpLayout<T, N, WOBS>::MINB) k_hd_warp(const __grid_constant__ KArgs<T> a) {
     static_assert(SCN == kScnHD || WarpLayout<T, N, WOBS>::LATE_FILL, "basic rows are written by the late fill");
     typedef Ops<T> O;
@@ -75,7 +82,19 @@ __global__ void __launch_bounds__(32 * WarpLayout<T, N, WOBS>::MAXW, WarpLayout<
     typedef WarpLayout<T, N, WOBS> LY;
     constexpr int EPW = LY::EPW, NA = LY::NA, IPR = LY::IPR;
     constexpr unsigned FULL = 0xffffffffu;
+    #ifndef FG_COOP_MIN_N
+#define FG_COOP_MIN_N 16
+#endif
+    constexpr bool COOP_STATIC = WOBS && SCN == kScnHD && LY::LATE_FILL && N >= FG_COOP_MIN_N;   // static row part written by the warp
     extern __shared__ __align__(128) unsigned char smem_raw[];
+
+    const bool f_collide = STD ? true : (a.collide != 0), f_noise = STD ? false : (a.u_noise > (T)0);
+    const bool f_vmax = STD ? false : (a.has_vmax != 0), f_mass1 = STD ? true : (a.mass_one != 0);
+    const bool has_step = STD ? true : (a.step != nullptr), has_done = STD ? true : (a.done != nullptr);
+    const bool has_indiv = STD ? true : (a.indiv != nullptr), has_epr = STD ? true : (a.ep_return != nullptr);
+    const bool has_epc = STD ? true : (a.ep_coll != nullptr), has_stats = STD ? true : (a.stats != nullptr);
+    const bool has_comm = STD ? false : (a.comm != nullptr);
+    const int n_steps = STD ? 1 : a.n_steps;
 
     const int lane = threadIdx.x & 31;
     const int wib = threadIdx.x >> 5;
@@ -129,14 +148,38 @@ __global__ void __launch_bounds__(32 * WarpLayout<T, N, WOBS>::MAXW, WarpLayout<
             if (SCN == kScnBasic) S_n = a.lm[fa];                          // landmark `lane` of the span (L == N)
             else { S_n = a.shape[fa]; iv_n = a.ivel[fe0 + le]; }
             if (!a.random_actions) u_n = a.act[fa];
-            if (a.step) stp_n = a.step[fe0 + le];
+            if (has_step) stp_n = a.step[fe0 + le];
             if (i == 0) {                                                   // running episode statistics of the env
-                if (a.ep_return) epr_n = a.ep_return[fe0 + le];
-                if (a.ep_coll) epc_n = a.ep_coll[fe0 + le];
+                if (has_epr) epr_n = a.ep_return[fe0 + le];
+                if (has_epc) epc_n = a.ep_coll[fe0 + le];
             }
         }
     };
+    // L2 prefetch of the span AFTER the one `fetch` requests (two iterations ahead of the one being computed).  Once the
+    // state arrays no longer fit in the 126 MB L2 (E >~ 200 K envs at N = 9) a register prefetch one iteration ahead
+    // is not enough: under the write-saturated DRAM queues a read takes longer than the ~4 us of one iteration
+    // (profiles/r02b_warp9_e1M: long-scoreboard stalls 3.2 per issue on the first use of the prefetched registers,
+    // 4.7 TB/s of DRAM traffic against 6.0 when the state is L2-resident).  prefetch.global.L2 costs no registers
+    // and no shared memory; the register prefetch of the next iteration then hits in L2.
+    auto l2_prefetch = [&](int span) {
+        const int fe0 = span * EPW;
+        if (fe0 >= a.E) return;                                             // warp-uniform
+        if (lane < min(EPW, a.E - fe0) * N) {
+            // one request per 128-byte line: the first lane of the span and every lane whose element starts a line
+            // (a prefetch per lane was measured 10 % SLOWER at N = 9 with an L2-resident state: 108 requests per
+            // iteration; bulk TMA prefetches, one per array, were worse still -- they queue with the obs bulk store)
+            const size_t fa = (size_t)fe0 * N + lane;
+            auto pf = [&](const R2* ptr) {
+                if (lane == 0 || (reinterpret_cast<uintptr_t>(ptr + fa) & 127) == 0)
+                    asm volatile("prefetch.global.L2 [%0];" :: "l"(ptr + fa));
+            };
+            pf(a.pos); pf(a.vel);
+            pf(SCN == kScnBasic ? a.lm : a.shape);
+            if (!a.random_actions) pf(a.act);
+        }
+    };
     fetch(gw);
+    if (a.pf_dist > 0) l2_prefetch(gw + nwarps);
 
   int spans_left = (nspans - gw + nwarps - 1) / nwarps;                     // >= 1
   for (int span = gw; ; span += nwarps) {
@@ -155,10 +198,11 @@ __global__ void __launch_bounds__(32 * WarpLayout<T, N, WOBS>::MAXW, WarpLayout<
     T epr = epr_n;
     int stp = stp_n, epc = epc_n;
     if (spans_left > 1) fetch(span + nwarps);
+    if (a.pf_dist > 0 && spans_left > 2) l2_prefetch(span + 2 * nwarps);
     __syncwarp();                                                           // previous span's readers of s_shp are done
     if (lane < NA) s_shp[lane] = S;
 
-    for (int ts = 0; ts < a.n_steps; ++ts) {
+    for (int ts = 0; ts < n_steps; ++ts) {
         if (lane < EPW) { s_max[lane] = 0; s_col[lane] = 0; }
         if (lane < NA) s_pold[lane] = p;
         __syncwarp();
@@ -174,7 +218,7 @@ __global__ void __launch_bounds__(32 * WarpLayout<T, N, WOBS>::MAXW, WarpLayout<
             // F = gain * u + noise (core.py:232-236)
             T Fx = O::mul(a.gain, O::mul(u.x, a.sens));
             T Fy = O::mul(a.gain, O::mul(u.y, a.sens));
-            if (a.u_noise > (T)0) {
+            if (f_noise) {
                 U4 r = philox(a.seed, ge, (uint32_t)i, tick0 + (uint32_t)ts, kUNoise);
                 T n0, n1; normal_pair<T>(r.x, r.y, &n0, &n1);
                 Fx = O::add(Fx, O::mul(n0, a.u_noise));
@@ -182,7 +226,7 @@ __global__ void __launch_bounds__(32 * WarpLayout<T, N, WOBS>::MAXW, WarpLayout<
             }
             // apply_environment_force (core.py:240-254).  Pass 1 (branch-free, unrolled): bit j of
             // `near` <=> pair (i, j) is inside the contact cut-off (or its distance is NaN).
-            if (a.collide) {
+            if (f_collide) {
                 const R2* ep = s_pold + le * N;
                 unsigned near = 0;
 #pragma unroll
@@ -210,11 +254,11 @@ __global__ void __launch_bounds__(32 * WarpLayout<T, N, WOBS>::MAXW, WarpLayout<
             }
             // integrate_state (core.py:264-277); F / m with m == 1 is exact, skip the division
             v.x = O::mul(v.x, a.keep); v.y = O::mul(v.y, a.keep);
-            T ax = a.mass_one ? Fx : O::div(Fx, a.mass);
-            T ay = a.mass_one ? Fy : O::div(Fy, a.mass);
+            T ax = f_mass1 ? Fx : O::div(Fx, a.mass);
+            T ay = f_mass1 ? Fy : O::div(Fy, a.mass);
             v.x = O::add(v.x, O::mul(ax, a.dt));
             v.y = O::add(v.y, O::mul(ay, a.dt));
-            if (a.has_vmax) {
+            if (f_vmax) {
                 T sp = O::sqrt_(O::sq2(v.x, v.y));
                 if (sp > a.vmax) {
                     v.x = O::mul(O::div(v.x, sp), a.vmax);
@@ -227,9 +271,9 @@ __global__ void __launch_bounds__(32 * WarpLayout<T, N, WOBS>::MAXW, WarpLayout<
             s_pnew[le * 2 * N + i] = p;
             s_pnew[le * 2 * N + N + i] = p;
             s_vel[lane] = v;
-            if (ts == a.n_steps - 1) {
+            if (ts == n_steps - 1) {
                 a.pos[g] = p; a.vel[g] = v;
-                if (a.comm) a.comm[g] = zero;
+                if (has_comm) a.comm[g] = zero;
             }
         }
         // any non-finite position in an env makes its centroid, hence the whole shape term, NaN
@@ -278,7 +322,7 @@ __global__ void __launch_bounds__(32 * WarpLayout<T, N, WOBS>::MAXW, WarpLayout<
                     hit |= (dx * dx + dy * dy < a.rthr2_hi) ? (1u << k) : 0u;
                 }
                 s_lmin[lane] = nan_seen ? O::from_bits(~(Bits)0 >> 1) : m;
-                while (a.collide && hit) {
+                while (f_collide && hit) {
                     const int k = __ffs(hit) - 1;
                     hit &= hit - 1;
                     R2 q = eA[k];
@@ -324,7 +368,7 @@ __global__ void __launch_bounds__(32 * WarpLayout<T, N, WOBS>::MAXW, WarpLayout<
                 row[3 * N - 1] = iv;                                        // ideal_vel
             }
             // is_collision (formation_hd_env.py:71-74,119-121): exact test only for candidates
-            while (a.collide && hit) {
+            while (f_collide && hit) {
                 const int k = __ffs(hit) - 1;
                 hit &= hit - 1;
                 R2 q = eP[k];
@@ -337,7 +381,7 @@ __global__ void __launch_bounds__(32 * WarpLayout<T, N, WOBS>::MAXW, WarpLayout<
 
         // ============ rewards, done, statistics (environment.py:126-138,172-177) ================
         stp += 1;                                                           // environment.py:114
-        const bool dn = active && a.step && (stp >= a.world_length);
+        const bool dn = active && has_step && (stp >= a.world_length);
         if (active) {
             T base;
             if (SCN == kScnBasic) {
@@ -357,17 +401,17 @@ __global__ void __launch_bounds__(32 * WarpLayout<T, N, WOBS>::MAXW, WarpLayout<
             // shared reward = sum_i r_i (environment.py:136): N*base - total collisions, in fp64
             const double R = (double)N * (double)base - (double)coltot;
             a.reward[g] = (T)R;
-            if (a.indiv) a.indiv[g] = r;
-            if (a.done) a.done[g] = (uint8_t)(a.step ? (stp >= a.world_length) : 0);
+            if (has_indiv) a.indiv[g] = r;
+            if (has_done) a.done[g] = (uint8_t)(has_step ? (stp >= a.world_length) : 0);
             if (i == 0 && env_bad && a.nan_flag) a.nan_flag[e] = 1;         // the reference's failure mode (Q9), sticky
-            if (i == 0 && a.step) {
+            if (i == 0 && has_step) {
                 const T ret = epr + (T)R;                                   // epr == 0 when ep_return is not tracked
                 const int ec = epc + coltot;
-                epr = (!a.ep_return || (dn && a.auto_reset)) ? (T)0 : ret;
-                epc = (!a.ep_coll || (dn && a.auto_reset)) ? 0 : ec;
-                if (a.ep_return) a.ep_return[e] = epr;
-                if (a.ep_coll) a.ep_coll[e] = epc;
-                if (dn && a.stats) {
+                epr = (!has_epr || (dn && a.auto_reset)) ? (T)0 : ret;
+                epc = (!has_epc || (dn && a.auto_reset)) ? 0 : ec;
+                if (has_epr) a.ep_return[e] = epr;
+                if (has_epc) a.ep_coll[e] = epc;
+                if (dn && has_stats) {
                     atomicAdd(&s_stat[0], 1.0);
                     atomicAdd(&s_stat[1], (double)ret);
                     atomicAdd(&s_stat[2], (double)ret * (double)ret);
@@ -393,7 +437,7 @@ __global__ void __launch_bounds__(32 * WarpLayout<T, N, WOBS>::MAXW, WarpLayout<
                     S = lraw;
                     s_shp[lane] = S;
                     a.lm[g] = S;
-                    if (ts == a.n_steps - 1) { a.pos[g] = p; a.vel[g] = v; }
+                    if (ts == n_steps - 1) { a.pos[g] = p; a.vel[g] = v; }
                 } else {
                     U4 w = philox(a.seed, ge, 0u, tk, kResetIdealVel);
                     iv = O::make(uniform_pm1<T>(w.x), uniform_pm1<T>(w.y));
@@ -409,11 +453,11 @@ __global__ void __launch_bounds__(32 * WarpLayout<T, N, WOBS>::MAXW, WarpLayout<
                 S = O::make(O::sub(lraw.x, O::div(sx, (T)N)), O::sub(lraw.y, O::div(sy, (T)N)));   // :93
                 s_shp[lane] = S;
                 a.shape[g] = S;
-                if (ts == a.n_steps - 1) { a.pos[g] = p; a.vel[g] = v; }
+                if (ts == n_steps - 1) { a.pos[g] = p; a.vel[g] = v; }
             }
             __syncwarp();
         }
-        if (active && i == 0 && a.step) a.step[e] = stp;
+        if (active && i == 0 && has_step) a.step[e] = stp;
 
         // ================= observation rows leave the SM as one bulk copy =======================
         // LATE_FILL: the image is filled LAST: the bulk copy of the previous span / step has had this whole step's
@@ -448,6 +492,9 @@ __global__ void __launch_bounds__(32 * WarpLayout<T, N, WOBS>::MAXW, WarpLayout<
                         row[1 + mm] = O::make(O::sub(q.x, p.x), O::sub(q.y, p.y));
                         row[N + mm] = zero;                                 // comm of the others (silent)
                     }
+                    // (writing the static 2N items of all rows cooperatively -- lane l holding items l, l + 32 of the
+                    // env's [comm | ideal_shape | ideal_vel] vector, ceil(2N / 32) conflict-free stores per row -- was
+                    // measured SLOWER at N = 27: 230.6 vs 209.1 us per 65536 envs; equal at N = 16, 25, 32)
 #pragma unroll
                     for (int k = 0; k < N; ++k) {
                         int kk = k + rN; kk -= (kk >= N) ? N : 0;
@@ -510,8 +557,8 @@ __global__ void __launch_bounds__(32 * WarpLayout<T, N, WOBS>::MAXW, WarpLayout<
     // the shared-memory image must outlive the bulk copy's reads
     if (WOBS && bulk_pending && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     __syncwarp();
-    if (a.stats && lane < 4 && s_stat[0] != 0.0) atomicAdd(&a.stats[lane], s_stat[lane]);
-    tick_arrive(a.tick_dev, (unsigned)min(nwarps, nspans), a.n_steps, lane == 0);
+    if (has_stats && lane < 4 && s_stat[0] != 0.0) atomicAdd(&a.stats[lane], s_stat[lane]);
+    tick_arrive(a.tick_dev, (unsigned)min(nwarps, nspans), n_steps, lane == 0);
 }
 
 }  // namespace fg

@@ -38,17 +38,21 @@ def needs_build():
 def build(force=False, verbose=False):
     """Compile csrc/*.cu -> formation_gym/libformation_gym_b200.so for sm_100a (one nvcc process per translation
     unit, in parallel; then one link step)."""
-    if not force and not needs_build():
+    # A/B builds (profiling only): FG_BUILD_DEFINES="-DFG_X=1 ..." adds preprocessor defines and FG_BUILD_OUT names
+    # another output file, which `FG_B200_LIB=<that file>` then loads instead of the product library
+    extra = os.environ.get("FG_BUILD_DEFINES", "").split()
+    out_path = os.environ.get("FG_BUILD_OUT", LIB_PATH)
+    if not extra and out_path == LIB_PATH and not force and not needs_build():
         return LIB_PATH
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.isfile(nvcc):
         raise RuntimeError("nvcc not found: cannot build %s" % LIB_NAME)
-    objdir = os.path.join(REPO, "build", "obj")
+    objdir = os.path.join(REPO, "build", "obj" if out_path == LIB_PATH else "obj_" + os.path.basename(out_path))
     os.makedirs(objdir, exist_ok=True)
     jobs = []
     for src in sources():
         obj = os.path.join(objdir, os.path.basename(src)[:-3] + ".o")
-        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
+        cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + \
               ["-I", os.path.join(REPO, "include"), "-c", src, "-o", obj]
         jobs.append((cmd, obj, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)))
     objs = []
@@ -60,12 +64,12 @@ def build(force=False, verbose=False):
             sys.stderr.write(err)
         objs.append(obj)
     link = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-cudart", "static",
-            "-o", LIB_PATH + ".tmp"] + objs
+            "-o", out_path + ".tmp"] + objs
     res = subprocess.run(link, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("link failed:\n%s\n%s" % (" ".join(link), res.stderr))
-    os.replace(LIB_PATH + ".tmp", LIB_PATH)
-    return LIB_PATH
+    os.replace(out_path + ".tmp", out_path)
+    return out_path
 
 
 if __name__ == "__main__":

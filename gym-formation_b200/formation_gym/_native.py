@@ -23,6 +23,7 @@ EXPORTS = [
     "fg_world_step", "fg_world_step_f64", "fg_obs_reward", "fg_obs_reward_f64",
     "fg_step_fused", "fg_step_fused_f64", "fg_reset", "fg_reset_f64",
     "fg_random_actions", "fg_random_actions_f64", "fg_fp32_probe", "fg_write_probe", "fg_policy_bfs", "fg_policy_bfs_f64",
+    "fg_obs_to_host",
 ]
 
 
@@ -100,6 +101,7 @@ def load():
             [P(fg_params), P(fg_buffers), I, I, I, I, VP, U64, U32, U32, VP]
         getattr(lib, "fg_random_actions" + sfx).argtypes = [VP, I, I, U64, U32, U32, VP, VP]
         getattr(lib, "fg_policy_bfs" + sfx).argtypes = [VP, VP, VP, VP, I, I, I, VP]
+    lib.fg_obs_to_host.argtypes = [VP, VP, VP, VP, I, I, I, I, I, I, VP]
     lib.fg_fp32_probe.argtypes = [I, I, I, VP, VP]
     lib.fg_write_probe.argtypes = [I, VP, C.c_ulonglong, C.c_uint, I, VP]
     for name in EXPORTS:

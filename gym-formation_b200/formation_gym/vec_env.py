@@ -16,9 +16,12 @@ lazily.  ``to_numpy=True`` gives what the reference's trainers see -- numpy arra
 staging buffers, one H2D for the actions and one D2H per output per step); ``to_numpy=False`` keeps
 CUDA tensors for device-resident policies (no host round-trip).  There is no CPU path.
 """
+import ctypes as C
+
 import numpy as np
 import torch
 
+from . import _native as nat
 from . import spaces
 from .batched import BatchedFormationEnv
 
@@ -86,6 +89,7 @@ class CudaVecEnv(object):
         self.agent_types = ['agent' for _ in range(e.N)]          # env_wrappers.py:30-35 (no adversaries)
         self.waiting = False
         self._pending = None
+        self._age = None
         self._np_dtype = np.float32 if e.dtype == torch.float32 else np.float64
         if self.to_numpy:
             # pinned host staging: actions in, obs / rewards / dones / individual rewards out
@@ -95,6 +99,20 @@ class CudaVecEnv(object):
             self._rew_h = torch.empty(e.reward.shape, dtype=e.dtype).pin_memory()
             self._done_h = torch.empty(e.done.shape, dtype=torch.bool).pin_memory()
             self._ind_h = torch.empty(e.indiv.shape, dtype=e.dtype).pin_memory()
+            # Only a prefix of every observation row changes from step to step: for silent agents the trailing comm
+            # block is zero, and formation_hd_env's [comm | ideal_shape | ideal_vel] (2N of 3N items,
+            # formation_hd_env.py:52-59) changes only when the env is reset.  The pinned host array persists, so a
+            # step ships that prefix only (fg_obs_to_host mode 1: a 2-D copy-engine transfer) and whole rows on the
+            # steps on which the episodes end; the host array stays byte-identical to the device tensor.
+            items = e.D // 2
+            if e.silent and e.scenario == "formation_hd_env":
+                self._dyn_items = e.N
+            elif e.silent:
+                self._dyn_items = items - (e.N - 1)
+            else:
+                self._dyn_items = items
+            self._row_items = items
+            self._age = None                    # env steps since ALL envs were last reset together (None: unknown)
 
     # ------------------------------------------------------------------ VecEnv interface
     @property
@@ -107,6 +125,7 @@ class CudaVecEnv(object):
         """All envs: ``np.stack([env.reset() ...])`` of the wrappers -> obs [E,N,D]."""
         self.waiting = False
         obs = self.env.reset()
+        self._age = 0
         return self._obs_out(obs)
 
     def reset_task(self):
@@ -130,7 +149,7 @@ class CudaVecEnv(object):
         self._pending = e.step(actions)
         if self.to_numpy:                                           # D2H overlaps nothing else: queue it now
             obs, rew, done, info = self._pending
-            self._obs_h.copy_(obs, non_blocking=True)
+            self._fetch_obs(obs)
             self._rew_h.copy_(rew, non_blocking=True)
             self._done_h.copy_(done, non_blocking=True)
             self._ind_h.copy_(info["individual_reward"], non_blocking=True)
@@ -153,6 +172,22 @@ class CudaVecEnv(object):
     def step(self, actions):
         self.step_async(actions)
         return self.step_wait()
+
+    def _fetch_obs(self, obs):
+        """Queue the D2H transfer of this step's observations into the persistent pinned array.  All envs of a
+        CudaVecEnv are reset together and share one episode length, so the steps on which rows change beyond their
+        dynamic prefix are known on the host: the steps that end the episodes (auto-reset -> new ideal shape /
+        ideal velocity).  Those steps, and any state the host cannot vouch for, take the whole-tensor copy."""
+        e = self.env
+        whole = self._dyn_items >= self._row_items or self._age is None
+        if not whole:
+            self._age += 1
+            whole = e.auto_reset and (self._age % e.world_length == 0)
+        isz = 8 if e.dtype == torch.float32 else 16
+        rc = e._lib.fg_obs_to_host(obs.data_ptr(), self._obs_h.data_ptr(), None, None, e.E, e.N, self._row_items,
+                                   self._dyn_items, isz, 0 if whole else 1,
+                                   C.c_void_p(torch.cuda.current_stream(e.device).cuda_stream))
+        nat.check(rc, "fg_obs_to_host")
 
     def close(self):
         if self.closed:

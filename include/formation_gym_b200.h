@@ -165,6 +165,9 @@ const char* fg_last_error(void);
  *   no_early_rows 0/1      long-row observation writer: rows leave after the reward pass
  *   no_tile_image 0/1      short-row observation writer: flat item loop instead of the tile image
  *   no_persistent_tiles 0/1  tile kernel: one CTA per tile instead of a persistent grid
+ *   no_std_kernel 0/1      warp kernel: never the instantiation specialised for the standard configuration
+ *   l2_prefetch 0/1/2      warp kernel: prefetch.global.L2 of the state two spans ahead: never / when the state
+ *                          arrays exceed ~1/3 of L2 (default) / always
  *   waves 1..64            warp kernel: grid = waves x one resident wave
  *   nvtx 0/1               NVTX ranges (domain-less, named after the entry point) around every launch
  * Unknown names / out-of-range values return FG_ERR_ARG. */
@@ -252,8 +255,26 @@ int fg_fp32_probe(int variant, int iters, int ctas, float* scratch, void* stream
 
 /* Diagnostics: write-only HBM stream over `bytes` of `dst` (what an observation writer can reach at
  * best).  variant 0: 16-byte streaming stores; 1: TMA bulk stores (cp.async.bulk) of `chunk` bytes from
- * shared memory; 2: the same with the L2 evict_first policy the step kernels use. */
+ * shared memory; 2: the same with the L2 evict_first policy the step kernels use; 3: hd observation rows of
+ * `chunk` = N agents written with plain 8-byte streaming stores from registers (one warp per env, 128-thread CTAs). */
 int fg_write_probe(int variant, void* dst, unsigned long long bytes, unsigned chunk, int ctas, void* stream);
+
+/* VecEnv adapter, host side of the boundary (train/maddpg-v2/utils/env_wrappers.py:68-72: the trainers read
+ * obs[E,N,D] as a HOST array after every step): ship one step's observation tensor from `obs_dev` [E*N rows x
+ * row_items items of item_bytes (8 = float2, 16 = double2)] into the pinned, persistent host array `obs_host` of the
+ * same layout.  Only the first `dyn_items` items of a row change every step (hd: [p_vel | other_pos] = N of 3N items,
+ * formation_hd_env.py:52-59); the rest changes when the env is reset, so a step needs a third of the PCIe bytes to
+ * leave the host array byte-identical to the device tensor.
+ *   mode 0: whole tensor, one contiguous copy.
+ *   mode 1: 2-D copy-engine transfer of the dynamic prefix of every row (the caller uses mode 0 on steps that
+ *           reset envs).
+ *   mode 2: scatter kernel storing straight into the mapped pinned host array: dynamic prefix of every row, WHOLE
+ *           rows where done_dev[row] != 0 (done [E,N] uint8 of the same step; NULL = no whole rows).
+ *   mode 3: pack the dynamic prefixes into `staging_dev` [E*N, dyn_items], then one contiguous copy of that into
+ *           `obs_host` (which then is a [E*N, dyn_items] staging array; diagnostic).
+ * Asynchronous on `stream`; the caller synchronises before reading the host array. */
+int fg_obs_to_host(const void* obs_dev, void* obs_host, const uint8_t* done_dev, void* staging_dev, int E, int N,
+                   int row_items, int dyn_items, int item_bytes, int mode, void* stream);
 
 /* Launch geometry chosen for (N): envs per CTA and threads per CTA (for reporting/tests). */
 int fg_launch_geometry(int N, int* envs_per_cta, int* threads_per_cta);

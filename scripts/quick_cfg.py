@@ -1,0 +1,33 @@
+"""Quick timing of the fused step kernel alone (CUDA graph of 5 steps) for a list of configs.
+Usage: python scripts/quick_cfg.py "scen N E [obs] [opt=val,...]" ..."""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "gym-formation_b200"))
+import torch  # noqa: E402
+import formation_gym  # noqa: E402
+from formation_gym import _native as nat  # noqa: E402
+
+PEAK = 6547.8
+for cfg in sys.argv[1:]:
+    f = cfg.split()
+    scen, N, E = f[0], int(f[1]), int(f[2])
+    obs = (f[3] != "0") if len(f) > 3 else True
+    opts = dict((kv.split("=")[0], int(kv.split("=")[1])) for kv in f[4].split(",")) if len(f) > 4 else {}
+    with nat.options(**opts):
+        env = formation_gym.make_batched_env(scen, E, N, 25, write_obs=obs, seed=1)
+        env.reset()
+        env.sample_actions()
+        g = env.capture_steps(5, policy=lambda e_: None)
+        g.replay(); torch.cuda.synchronize()
+        best = 1e9
+        for rep in range(3):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(10):
+                g.replay()
+            e1.record(); torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1) / 50)
+        gbs = env.bytes_per_env_step() * E / (best * 1e-3) / 1e9
+        print("%-28s N=%3d E=%8d obs=%d %-24s %9.2f us  %7.0f GB/s  frac %.3f" % (scen, N, E, obs, opts, best * 1e3, gbs, gbs / PEAK), flush=True)
+        del g, env
+        torch.cuda.empty_cache()

@@ -121,7 +121,7 @@ def run_bfs_inconsistent(seed, n_layer=3, layers=2):
 
 
 if __name__ == "__main__":
-    np.savez_compressed(os.path.join(HERE, "policy_bfs_inconsistent_n9.npz"), **run_bfs_inconsistent(5))
+    np.savez_compressed(os.path.join(HERE, "bfs_inconsistent_n9.npz"), **run_bfs_inconsistent(5))
     out = {}
     for k, v in run_scripted(31).items():
         out["scripted/" + k] = v

@@ -167,7 +167,7 @@ def test_bfs_observation_consistency_check():
     """get_action_BFS(ezpolicy, ...) may only collapse to the one-launch device tree when the N observations show one
     consistent state; the fixture holds a consistent and a perturbed set made with the unmodified reference."""
     import formation_gym
-    g = np.load(os.path.join(GOLD, "policy_bfs_inconsistent_n9.npz"))
+    g = np.load(os.path.join(GOLD, "bfs_inconsistent_n9.npz"))
     assert formation_gym._consistent_observations(list(g["obs_clean"]), 9)
     assert not formation_gym._consistent_observations(list(g["obs_noisy"]), 9)
     bad = g["obs_clean"].copy(); bad[5, -1] += 1e-3                      # another ideal_vel in one agent's row

@@ -287,10 +287,10 @@ def test_separate_entry_points_match_fused(dtype):
 
 
 # ------------------------------------------------------------------ warp kernel vs tile kernel
-def _run_steps(E, N, dtype, steps, force_tile, episode_length=7, u_noise=None, rollout=False, seed=11):
+def _run_steps(E, N, dtype, steps, force_tile, episode_length=7, u_noise=None, rollout=False, seed=11, no_std=0):
     """`steps` random-policy steps with auto-reset; FG_FORCE_TILE_KERNEL=1 routes fg_step_fused to
     the generic tile kernel (fg_kernels.cuh) instead of the warp-autonomous one (fg_warp.cuh)."""
-    with nat.options(force_tile_kernel=int(force_tile)):
+    with nat.options(force_tile_kernel=int(force_tile), no_std_kernel=int(no_std)):
         env = BatchedFormationEnv("formation_hd_env", E, N, episode_length=episode_length, dtype=dtype,
                                   seed=seed, auto_reset=True, u_noise=u_noise)
         env.reset()
@@ -339,8 +339,10 @@ def test_warp_kernel_matches_tile_kernel(E, N, dtype):
 def test_warp_kernel_rollout_equals_stepwise(N):
     """n_steps random-policy steps inside ONE launch == the same steps as separate launches
     (same Philox counters), bit for bit, including the auto-resets in between."""
-    a, _ = _run_steps(333, N, torch.float32, 20, force_tile=False, rollout=False)
-    b, _ = _run_steps(333, N, torch.float32, 20, force_tile=False, rollout=True)
+    # (both on the generic instantiation: single fp32 steps otherwise take the STD instantiation, whose FMA contraction
+    # may differ by an ulp -- test_std_instantiation_matches_generic covers that pair)
+    a, _ = _run_steps(333, N, torch.float32, 20, force_tile=False, rollout=False, no_std=1)
+    b, _ = _run_steps(333, N, torch.float32, 20, force_tile=False, rollout=True, no_std=1)
     for k in a:
         if k == "stats":
             assert torch.allclose(a[k], b[k], rtol=1e-12)
@@ -354,6 +356,55 @@ def test_warp_kernel_noise_matches_tile_kernel():
     b, _ = _run_steps(500, 9, torch.float64, 5, force_tile=True, u_noise=0.3)
     for k in ("pos", "vel", "obs", "reward"):
         assert torch.equal(a[k], b[k]), k
+
+
+@pytest.mark.parametrize("write_obs", [True, False], ids=["obs", "noobs"])
+@pytest.mark.parametrize("scen,N", [("formation_hd_env", n) for n in (3, 4, 5, 6, 7, 8, 9, 16, 25, 27, 32)]
+                         + [("basic_formation_env", 3)])
+def test_warp_kernel_full_wave_geometry(scen, N, write_obs):
+    """Batches large enough for the full launch geometry (8- or 4-warp CTAs, one resident wave) -- the sizes bench.py
+    runs -- give, env for env, the bits a small batch gives (results never depend on the launch geometry).  Guards the
+    dynamic-shared-memory limit of every instantiation: N = 3 needs 31 KB per CTA, below the 48 KB default, and a limit
+    left lower by the occupancy probe made exactly these launches fail."""
+    EPW = 32 // N
+    E_big, E_small = 2500 * EPW, 3 * EPW + 1
+    outs = []
+    for E in (E_big, E_small):
+        env = BatchedFormationEnv(scen, E, N, episode_length=3, seed=17, auto_reset=True, write_obs=write_obs)
+        env.reset()
+        for _ in range(4):
+            env.step_random()
+        torch.cuda.synchronize()
+        outs.append({k: getattr(env, k)[:E_small].clone() for k in ("pos", "vel", "reward", "indiv", "step_count")
+                     + (("obs",) if write_obs else ())})
+    for k in outs[0]:
+        assert torch.equal(outs[0][k], outs[1][k]), k
+
+
+@pytest.mark.parametrize("scen,N", [("formation_hd_env", n) for n in (3, 4, 5, 6, 7, 8, 9, 16, 25, 27, 32)]
+                         + [("basic_formation_env", 3)])
+def test_std_instantiation_matches_generic(scen, N):
+    """k_hd_warp<..., STD = true> (the standard product configuration with its run-time flag tests compiled out)
+    against the generic instantiation of the same source (no_std_kernel = 1): same arithmetic in the same order;
+    fp32 FMA contraction may differ between two instantiations, so a few ulp are allowed, integers are exact."""
+    outs = []
+    for no_std in (0, 1):
+        with nat.options(no_std_kernel=no_std):
+            env = BatchedFormationEnv(scen, 555, N, episode_length=5, seed=23, auto_reset=True)
+            env.reset()
+            env.pos.mul_(0.3)
+            for _ in range(12):
+                env.step_random(record_actions=True)
+            torch.cuda.synchronize()
+            outs.append({k: getattr(env, k).clone() for k in ("pos", "vel", "obs", "reward", "indiv", "step_count",
+                                                              "ep_return", "ep_collisions", "actions", "stats")})
+    a, b = outs
+    for k in a:
+        if not a[k].is_floating_point() or k == "actions":
+            assert torch.equal(a[k], b[k]), k
+        else:
+            ref = b[k].double().cpu().numpy()
+            assert maxerr(a[k], ref) <= 1e-5 * max(1.0, float(np.abs(ref).max())), k
 
 
 def test_warp_kernel_unaligned_obs_and_no_obs():

@@ -92,7 +92,7 @@ def test_get_action_BFS_reads_every_observation_like_the_reference():
     """Host API get_action_BFS(ezpolicy, obs_n, 3): consistent observations take the one-launch device tree;
     observations a wrapper has perturbed (round-1 advice: the shortcut used obs[0] only) take the host tree walk
     that reads each leader's / member's own row.  Both against the unmodified reference (fixture)."""
-    g = np.load(os.path.join(GOLD, "policy_bfs_inconsistent_n9.npz"))
+    g = np.load(os.path.join(GOLD, "bfs_inconsistent_n9.npz"))
     n = int(g["n"])
     act = np.stack(formation_gym.get_action_BFS(formation_gym.ezpolicy, list(g["obs_clean"]), n))
     assert np.abs(act - g["act_clean"]).max() <= 1e-12

@@ -63,6 +63,31 @@ def test_vec_env_matches_batched_env_and_oracle():
     assert np.abs(infos.individual_reward - want["indiv"]).max() <= 1e-5
 
 
+@pytest.mark.parametrize("scen,N,kw", [("formation_hd_env", 9, {}), ("formation_hd_env", 27, {}), ("formation_hd_env", 40, {}),
+                                       ("formation_hd_env", 9, dict(dtype=torch.float64)),
+                                       ("formation_hd_env", 5, dict(auto_reset=False)),
+                                       ("basic_formation_env", 3, {}), ("formation_hd_partial_env", 5, {}),
+                                       ("formation_hd_obs_env", 4, {}), ("formation_hd_env", 6, dict(silent=False))])
+def test_vec_env_host_arrays_stay_byte_identical(scen, N, kw):
+    """to_numpy=True ships only the dynamic prefix of every observation row on ordinary steps (fg_obs_to_host mode 1)
+    and whole rows on the steps that end the episodes; the persistent pinned host array must equal the device tensor
+    byte for byte after EVERY step, across auto-resets (new ideal shape / ideal velocity / landmarks)."""
+    E, T = 37, 4
+    venv = formation_gym.make_vec_env(scen, E, N, episode_length=T, seed=5, **kw)
+    env = venv.env
+    obs = venv.reset()
+    assert np.array_equal(obs, env.obs.cpu().numpy())
+    rng = np.random.default_rng(1)
+    for t in range(1, 3 * T + 2):
+        act = rng.uniform(-1, 1, (E, N, env.act_dim)).astype(obs.dtype)
+        obs, rews, dones, infos = venv.step(act)
+        assert obs.tobytes() == env.obs.cpu().numpy().tobytes(), t
+        assert np.array_equal(rews, env.reward.cpu().numpy()) and np.array_equal(dones, env.done.cpu().numpy())
+        if kw.get("auto_reset", True):
+            assert bool(dones.all()) == (t % T == 0)
+    venv.close()
+
+
 def test_vec_env_auto_reset_returns_reset_obs_with_terminal_reward():
     """worker(): `if all(done): ob = env.reset()` -- terminal reward/done, RESET observation
     (env_wrappers.py:14-18)."""
