@@ -4,9 +4,11 @@
     python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's CUDA path
     python bench.py --impl reference [--gpus N] --steps K --warmup W   # CPU reference arm
 
-One "step" = one env step (MultiAgentEnv.step semantics) of EVERY env of the batch: the random
-policy kernel (fg_random_actions: act ~ U(-1,1), test.py:20) followed by the fused step kernel
-(fg_step_fused: _set_action + World.step + observation + reward + done + auto-reset).  Workload
+One "step" = one env step (MultiAgentEnv.step semantics) of EVERY env of the batch under the random policy
+(act ~ U(-1,1), test.py:20): ONE launch of the fused step kernel (fg_step_fused with random_actions = 2: the
+actions are drawn from Philox inside the kernel AND recorded in the action buffer, then _set_action + World.step +
+observation + reward + done + auto-reset).  `--two-kernels` runs the round-1 form instead (fg_random_actions
+kernel, then fg_step_fused reading the action buffer); both give bit-identical results.  Workload
 (config.workload): formation_hd_env, 9 agents, 131072 envs per GPU (= the north star's 1M envs on
 8 GPUs), episode_length 25, fp32.  A step moves 131072 * 2437 B = 319 MB > the 126 MB L2, so
 every timed iteration streams from/to HBM (no L2 flush needed).
@@ -57,6 +59,8 @@ def parse():
     ap.add_argument("--no-also", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling lines and the state hash")
+    ap.add_argument("--two-kernels", action="store_true",
+                    help="random-policy kernel + step kernel per step instead of the policy fused into the step kernel")
     ap.add_argument("--u-noise", type=float, default=0.0, help="motor noise of the headline workload (core.py:232-236)")
     return ap.parse_args()
 
@@ -211,7 +215,10 @@ def workload_config(a, envs_per_unit, where):
                            a.episode_length),
             "scenario": a.scenario, "agents": a.agents, "envs_per_gpu": envs_per_unit if where == "gpu" else None,
             "episode_length": a.episode_length, "obs": not a.no_obs,
-            "launch": ("cuda graph of per-step launches" if a.graph_steps > 0 else "per-step launches") if where == "gpu" else None,
+            "launch": (("cuda graph of per-step launches" if a.graph_steps > 0 else "per-step launches") +
+                       ("; random-policy kernel + fused step kernel per step" if a.two_kernels else
+                        "; one kernel per step (random policy drawn and recorded inside the fused step kernel)"))
+            if where == "gpu" else None,
             "l2": "inputs larger than L2 (step traffic > 126 MB), no flush" if where == "gpu" else None}
 
 
@@ -249,8 +256,10 @@ def run_b200(a):
             dist.barrier()
 
     def one_step():
-        env.sample_actions()
-        return env.step(env.actions)
+        if a.two_kernels:
+            env.sample_actions()
+            return env.step(env.actions)
+        return env.step_random(record_actions=True)
 
     for _ in range(W):
         one_step()
@@ -262,7 +271,7 @@ def run_b200(a):
     chunk = max(1, min(K, a.graph_steps))
     while K % chunk:
         chunk -= 1
-    graph = env.capture_steps(chunk) if a.graph_steps > 0 else None
+    graph = env.capture_steps(chunk, fused_random=not a.two_kernels) if a.graph_steps > 0 else None
     if graph is not None:
         graph.replay()
     torch.cuda.synchronize()
@@ -282,7 +291,7 @@ def run_b200(a):
             one_step()
     ev1.record()
     torch.cuda.synchronize(); barrier()
-    launches = 2 * K                                              # fg::k_random_actions + step kernel per step
+    launches = (2 if a.two_kernels else 1) * K                    # (fg::k_random_actions +) step kernel per step
     ms = ev0.elapsed_time(ev1)
 
     # ---- timed region 2 (-> roofline): the fused step kernel ALONE.  G steps are captured into a CUDA graph, each
@@ -522,8 +531,8 @@ def _tensor_hash(torch, t, first_elem, salt):
 
 def strong_scaling(formation_gym, fgd, torch, dist, device, dtype, rank, world, barrier):
     """(1) BASELINE configs[2] (hd N=27, 65536 envs) and configs[3] (hd N=243, 8192 envs) split evenly over the ranks
-    (strong scaling: the TOTAL is fixed), whole step = random-policy kernel + fused step from a CUDA graph, device
-    timed, max over ranks.  (2) state hash: hd N=27, 65536 envs in total, episode_length 10, seed 0, 25 random-policy
+    (strong scaling: the TOTAL is fixed), whole step = fused step kernel with the in-kernel random policy from a CUDA
+    graph, device timed, max over ranks.  (2) state hash: hd N=27, 65536 envs in total, episode_length 10, seed 0, 25 random-policy
     steps (two auto-resets per env): a 64-bit checksum of pos / vel / reward / ideal_shape / ideal_vel / step /
     observations over ALL envs (per-rank partial sums all-reduced) -- Philox is keyed by the global env id, so the
     value must be identical at 1 / 2 / 4 / 8 ranks."""
@@ -534,7 +543,7 @@ def strong_scaling(formation_gym, fgd, torch, dist, device, dtype, rank, world, 
         env = formation_gym.make_batched_env("formation_hd_env", hi - lo, N, 25, device=device, dtype=dtype, seed=0,
                                              auto_reset=True, env_offset=lo)
         env.reset()
-        g = env.capture_steps(5)
+        g = env.capture_steps(5, fused_random=True)
         g.replay(); torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier(); torch.cuda.synchronize()
@@ -652,14 +661,19 @@ def also_configs(formation_gym, torch, device, dtype, peak, a):
         env.reset()
         nbytes = env.bytes_per_env_step() * E
         per_graph = 25 if mode in ("graph", "rollout") else 5
-        if mode == "launch":                                      # plain per-step launches: host-bound at small E
+        if mode in ("launch", "launch2"):                         # plain per-step launches: host-bound at small E
+            def host_step():
+                if mode == "launch2":
+                    env.sample_actions(); env.step(env.actions)
+                else:
+                    env.step_random(record_actions=True)
             for _ in range(5):
-                env.sample_actions(); env.step(env.actions)
+                host_step()
             torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             for _ in range(steps):
-                env.sample_actions(); env.step(env.actions)
+                host_step()
             e1.record(); torch.cuda.synchronize()
             ms = e0.elapsed_time(e1) / steps
         elif mode == "rollout":
@@ -674,8 +688,8 @@ def also_configs(formation_gym, torch, device, dtype, peak, a):
             g = env.capture_steps(5, policy=lambda env_: env_.bfs_actions(3))
             ms = _time_graph(torch, g, max(2, steps // 5)) / 5
             del g
-        elif mode == "fusedrandom":                               # random policy drawn AND recorded inside the step kernel
-            g = env.capture_steps(5, policy=lambda env_: None, fused_random=True)
+        elif mode == "twokernels":                                # round-1 form: policy kernel + step kernel per step
+            g = env.capture_steps(5)
             ms = _time_graph(torch, g, max(2, steps // 5)) / 5
             del g
         elif mode == "noobs":
@@ -683,15 +697,15 @@ def also_configs(formation_gym, torch, device, dtype, peak, a):
             g = env.capture_steps(5, policy=lambda env_: None)
             ms = _time_graph(torch, g, max(2, steps // 5)) / 5
             del g
-        else:                                                     # "graph" / "step": policy kernel + fused step per step
-            g = env.capture_steps(per_graph)
+        else:                                                     # "graph" / "step": fused step kernel, in-kernel random policy
+            g = env.capture_steps(per_graph, fused_random=True)
             ms = _time_graph(torch, g, max(2, steps // per_graph)) / per_graph
             del g
         gbs = nbytes / (ms * 1e-3) / 1e9
         row = {"config": name, "agent_steps_per_s": E * N / (ms * 1e-3), "ms_per_env_step": ms,
                "algorithmic_GBps": gbs}
         frac_keys(row, gbs, nbytes)
-        if mode in ("step", "bfs", "fusedrandom"):
+        if mode in ("step", "bfs", "twokernels"):
             # the fused step kernel alone (actions pre-sampled, CUDA graph of 5 launches: no launch gaps, no policy
             # kernel) -- the figure comparable with the headline's roofline.frac
             env.sample_actions()
@@ -715,13 +729,17 @@ def also_configs(formation_gym, torch, device, dtype, peak, a):
         return row
 
     cfgs = [
-        ("configs[1] hd N=9 E=4096 (per-step launches from the host)", "formation_hd_env", 9, 4096, "launch", 500, {}),
-        ("configs[1] hd N=9 E=4096 (CUDA graph of 25 x (policy + step))", "formation_hd_env", 9, 4096, "graph", 250, {}),
+        ("configs[1] hd N=9 E=4096 (per-step launches from the host, one fused kernel per step)", "formation_hd_env", 9,
+         4096, "launch", 1000, {}),
+        ("configs[1] hd N=9 E=4096 (per-step launches from the host, policy kernel + step kernel)", "formation_hd_env", 9,
+         4096, "launch2", 1000, {}),
+        ("configs[1] hd N=9 E=4096 (CUDA graph of 25 fused steps)", "formation_hd_env", 9, 4096, "graph", 250, {}),
         ("configs[1] hd N=9 E=4096 (in-kernel 25-step rollouts)", "formation_hd_env", 9, 4096, "rollout", 40, {}),
         ("hd N=9 E=131072, u_noise=0.1 (Philox motor noise, core.py:232-236)", "formation_hd_env", 9, 131072, "step", 50,
          dict(u_noise=0.1)),
-        ("hd N=9 E=131072, random policy drawn and recorded inside the step kernel (one launch per step)",
-         "formation_hd_env", 9, 131072, "fusedrandom", 50, {}),
+        ("hd N=9 E=131072, round-1 form: random-policy kernel + step kernel per step (two launches)",
+         "formation_hd_env", 9, 131072, "twokernels", 50, {}),
+        ("hd N=3 E=1048576", "formation_hd_env", 3, 1048576, "step", 50, {}),
         ("hd N=9 E=131072, device controller get_action_BFS(ezpolicy) instead of the random policy",
          "formation_hd_env", 9, 131072, "bfs", 50, {}),
         ("configs[2] hd N=27 E=65536", "formation_hd_env", 27, 65536, "step", 50, {}),
@@ -737,8 +755,8 @@ def also_configs(formation_gym, torch, device, dtype, peak, a):
             res.append(measure(name, scen, N, E, mode, steps, **kw))
         except Exception as ex:  # keep the headline line alive
             res.append({"config": name, "error": repr(ex)[:200]})
-    # ---- configs[4]: env-count sweep 1K .. 1M envs x {3, 9, 27} agents on this GPU (whole step = policy kernel + fused
-    # step from a CUDA graph; step kernel alone next to it).  The reference's own scale is 128-200 env processes
+    # ---- configs[4]: env-count sweep 1K .. 1M envs x {3, 9, 27} agents on this GPU (whole step = fused step kernel with
+    # the in-kernel random policy, from a CUDA graph; the step kernel on pre-sampled actions next to it).  The reference's own scale is 128-200 env processes
     # (train/mappo/train_formation.sh:13); the launch-bound -> HBM-bound crossover shows here.
     sweep = []
     for N in (3, 9, 27):

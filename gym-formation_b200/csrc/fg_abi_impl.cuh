@@ -577,11 +577,22 @@ int policy_bfs_impl(const void* pos, const void* shape, const void* ivel, void* 
     const size_t smem = (size_t)4 * a.EPC * N * sizeof(R2);
     const int grid = (E + a.EPC - 1) / a.EPC;
     cudaStream_t st = (cudaStream_t)stream;
-    switch (n) {                                                    // compile-time fan-out for the usual group sizes
-        case 2: fg::k_policy_bfs<T, 2><<<grid, fg::kBlock, smem, st>>>(a); break;
-        case 3: fg::k_policy_bfs<T, 3><<<grid, fg::kBlock, smem, st>>>(a); break;
-        case 4: fg::k_policy_bfs<T, 4><<<grid, fg::kBlock, smem, st>>>(a); break;
-        default: fg::k_policy_bfs<T, 0><<<grid, fg::kBlock, smem, st>>>(a); break;
+    // compile-time tree shapes for the reference's own sizes (README.md:31-51: groups of 3, up to 3^5 agents; test.py
+    // --num-layer) and the binary / quaternary trees up to 32 / 16 agents; run-time shape otherwise
+    const int key = n * 16 + levels;
+    switch (key) {
+#define FG_POLICY_CASE(NF_, LV_) case NF_ * 16 + LV_: fg::k_policy_bfs<T, NF_, LV_><<<grid, fg::kBlock, smem, st>>>(a); break;
+        FG_POLICY_CASE(3, 1) FG_POLICY_CASE(3, 2) FG_POLICY_CASE(3, 3) FG_POLICY_CASE(3, 4) FG_POLICY_CASE(3, 5)
+        FG_POLICY_CASE(2, 2) FG_POLICY_CASE(2, 3) FG_POLICY_CASE(2, 4) FG_POLICY_CASE(2, 5)
+        FG_POLICY_CASE(4, 1) FG_POLICY_CASE(4, 2)
+#undef FG_POLICY_CASE
+        default:
+            switch (n) {                                            // compile-time fan-out for the usual group sizes
+                case 2: fg::k_policy_bfs<T, 2><<<grid, fg::kBlock, smem, st>>>(a); break;
+                case 3: fg::k_policy_bfs<T, 3><<<grid, fg::kBlock, smem, st>>>(a); break;
+                case 4: fg::k_policy_bfs<T, 4><<<grid, fg::kBlock, smem, st>>>(a); break;
+                default: fg::k_policy_bfs<T, 0><<<grid, fg::kBlock, smem, st>>>(a); break;
+            }
     }
     cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess) return fail(FG_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(err));

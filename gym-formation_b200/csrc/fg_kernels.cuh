@@ -348,7 +348,8 @@ __global__ void __launch_bounds__(kBlock, (OM == 3 && SCN == kScnBasic) ? 5 : (O
         // step (then the rows must show the RESET state and everything is written after the reset, below),
         // the rows are sent right after the physics, BEFORE the reward pass, and drain under it.  (Sending the
         // static 2/3 even earlier, before the physics, was measured slower: 327 vs 260 us per 1024 envs of
-        // 243 agents -- the burst fills the SM's TMA queue and the warps block on issuing.)
+        // 243 agents -- the burst fills the SM's TMA queue and the warps block on issuing; round 2 repeated it on
+        // every second CTA only, so that the others compute meanwhile: 293 vs 244 us, still slower.)
         bool early = false;
         if constexpr (OM == 2 && sizeof(R2) == 8) {
             if (a.obs && a.row_early) {

@@ -122,19 +122,86 @@ __device__ __forceinline__ typename Ops<T>::R2 ezpolicy_dev(const typename Ops<T
     return O::make(O::add(act.x, done ? tvel.x : O::mul(tvel.x, g)), O::add(act.y, done ? tvel.y : O::mul(tvel.y, g)));
 }
 
-template <typename T, int NF>
+template <int B, int E_> struct CPow { static constexpr int v = B * CPow<B, E_ - 1>::v; };
+template <int B> struct CPow<B, 0> { static constexpr int v = 1; };
+
+// One BFS layer for the envs of a CTA.  M, NXT > 0: compile-time group / subgroup sizes (loops unrolled, divisions by
+// constants); M == 0: run-time sizes from the argument block with fastdiv magics.
+template <typename T, int NF, int N_, int M_, int NXT_>
+__device__ __forceinline__ void policy_layer(const PArgs<T>& a, int l, int nvalid, const typename Ops<T>::R2* s_p,
+                                             const typename Ops<T>::R2* s_s, const typename Ops<T>::R2* s_tv0,
+                                             typename Ops<T>::R2* s_tv1) {
+    typedef Ops<T> O;
+    typedef typename O::R2 R2;
+    constexpr int CAP = NF > 0 ? NF : kPolicyMaxFan;
+    constexpr bool CT = M_ > 0;
+    const int N = CT ? N_ : a.N, n = NF > 0 ? NF : a.n;
+    const int M = CT ? M_ : a.lev_M[l], nxt = CT ? NXT_ : a.lev_nxt[l];
+    const int nlead = CT ? N_ / (NXT_ > 0 ? NXT_ : 1) : a.lev_nlead[l];       // leaders per env in this layer (:61)
+    const int t = threadIdx.x;
+    // leaders are COMPACTED onto consecutive threads (upper layers have few of them: N / nxt per env), so
+    // a layer costs ceil(envs * leaders / 32) warps instead of every warp of the CTA at 1/nxt efficiency
+    for (int q = t; q < nvalid * nlead; q += 256) {
+        const int qe = CT ? q / nlead : (int)fastdiv((uint32_t)q, a.mg_nlead[l]);
+        const int i = (q - qe * nlead) * nxt;
+        const R2* P = s_p + qe * N;
+        const R2* S = s_s + qe * N;
+        const int gb = CT ? (i / M) * M : (int)fastdiv((uint32_t)i, a.mg_M[l]) * M;      // first agent of my group
+        const int si = CT ? (i - gb) / nxt : (int)fastdiv((uint32_t)(i - gb), a.mg_nxt[l]);   // my subgroup within the group
+        const R2 pi = P[i];
+        R2 cur[CAP], tgt[CAP], others[CAP];
+#pragma unroll
+        for (int k = 0; k < CAP; ++k) {
+            if (k >= n) continue;
+            // centroid of subgroup k in my frame (:65-66) and of its target points (:70-71): np.mean sums
+            // the rows in order and divides by the count
+            T cx = 0, cy = 0, tx = 0, ty = 0;
+            const int b0 = gb + k * nxt;
+#pragma unroll CT ? 9 : 1
+            for (int b = b0; b < b0 + nxt; ++b) {
+                const R2 q2 = P[b];
+                const T rx = (b == i) ? (T)0 : O::sub(q2.x, pi.x);            // own slot is the inserted (0,0)
+                const T ry = (b == i) ? (T)0 : O::sub(q2.y, pi.y);
+                cx = O::add(cx, rx); cy = O::add(cy, ry);
+                const R2 sb = S[b];
+                tx = O::add(tx, sb.x); ty = O::add(ty, sb.y);
+            }
+            cur[k] = O::make(O::div_count(cx, nxt), O::div_count(cy, nxt));
+            tgt[k] = O::make(O::div_count(tx, nxt), O::div_count(ty, nxt));
+        }
+        R2 own = cur[0];                                                      // :67-68
+#pragma unroll
+        for (int k = 1; k < CAP; ++k) if (k < n && k == si) own = cur[k];
+#pragma unroll
+        for (int k = 0; k < CAP - 1; ++k) {                                   // np.delete(cur - cur[si], si, 0)
+            if (k < n - 1) {
+                const R2 c = (k < si) ? cur[k] : cur[k + 1];
+                others[k] = O::make(O::sub(c.x, own.x), O::sub(c.y, own.y));
+            }
+        }
+        R2 out = ezpolicy_dev<T, NF>(others, tgt, s_tv0[qe * N + i], n);      // :76-79
+        out = O::make(O::mul(out.x, a.mult[l]), O::mul(out.y, a.mult[l]));
+        if (nxt == 1) a.act[((size_t)blockIdx.x * a.EPC + qe) * N + i] = out;              // :81-83
+        else for (int b = 0; b < nxt; ++b) s_tv1[qe * N + i + b] = out;       // tar_vel of my subgroup (:84-97)
+    }
+}
+
+// LV > 0: the tree shape is a compile-time constant (N = NF^LV; every layer's loops unroll and its index divisions are
+// by constants -- the run-time version spent a quarter of its instructions on them and on loop control); LV == 0: any
+// N = n^levels from the argument block.
+template <typename T, int NF, int LV = 0>
 __global__ void __launch_bounds__(256) k_policy_bfs(const __grid_constant__ PArgs<T> a) {
     typedef Ops<T> O;
     typedef typename O::R2 R2;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    constexpr int CAP = NF > 0 ? NF : kPolicyMaxFan;
-    const int N = a.N, n = NF > 0 ? NF : a.n, nA = a.EPC * N;
+    constexpr int NC = LV > 0 ? CPow<NF, (LV > 0 ? LV : 0)>::v : 0;
+    const int N = LV > 0 ? NC : a.N, nA = a.EPC * N;
     R2* s_p = reinterpret_cast<R2*>(smem_raw);
     R2* s_s = s_p + nA;
     R2* s_tv0 = s_s + nA;                 // target velocity of the group each agent is in (ping-pong)
     R2* s_tv1 = s_tv0 + nA;
     const int t = threadIdx.x;
-    const int le = (int)fastdiv((uint32_t)t, a.magic_n);
+    const int le = LV > 0 ? t / NC : (int)fastdiv((uint32_t)t, a.magic_n);
     const int i = t - le * N;
     const int e = blockIdx.x * a.EPC + le;
     const bool active = t < nA && e < a.E;
@@ -146,55 +213,31 @@ __global__ void __launch_bounds__(256) k_policy_bfs(const __grid_constant__ PArg
     }
     __syncthreads();
     const int nvalid = min(a.EPC, a.E - blockIdx.x * a.EPC);
-    for (int l = 0; l < a.levels; ++l) {
-        const int M = a.lev_M[l], nxt = a.lev_nxt[l];
-        const int nlead = a.lev_nlead[l];                                     // leaders per env in this layer (:61)
-        // leaders are COMPACTED onto consecutive threads (upper layers have few of them: N / nxt per env), so
-        // a layer costs ceil(envs * leaders / 32) warps instead of every warp of the CTA at 1/nxt efficiency
-        for (int q = t; q < nvalid * nlead; q += kBlock) {
-            const int qe = (int)fastdiv((uint32_t)q, a.mg_nlead[l]);
-            const int i = (q - qe * nlead) * nxt;
-            const R2* P = s_p + qe * N;
-            const R2* S = s_s + qe * N;
-            const int gb = (int)fastdiv((uint32_t)i, a.mg_M[l]) * M;          // first agent of my group
-            const int si = (int)fastdiv((uint32_t)(i - gb), a.mg_nxt[l]);     // my subgroup within the group
-            const R2 pi = P[i];
-            R2 cur[CAP], tgt[CAP], others[CAP];
-#pragma unroll
-            for (int k = 0; k < CAP; ++k) {
-                if (k >= n) continue;
-                // centroid of subgroup k in my frame (:65-66) and of its target points (:70-71): np.mean sums
-                // the rows in order and divides by the count
-                T cx = 0, cy = 0, tx = 0, ty = 0;
-                const int b0 = gb + k * nxt;
-                for (int b = b0; b < b0 + nxt; ++b) {
-                    const R2 q2 = P[b];
-                    const T rx = (b == i) ? (T)0 : O::sub(q2.x, pi.x);        // own slot is the inserted (0,0)
-                    const T ry = (b == i) ? (T)0 : O::sub(q2.y, pi.y);
-                    cx = O::add(cx, rx); cy = O::add(cy, ry);
-                    const R2 sb = S[b];
-                    tx = O::add(tx, sb.x); ty = O::add(ty, sb.y);
-                }
-                cur[k] = O::make(O::div_count(cx, nxt), O::div_count(cy, nxt));
-                tgt[k] = O::make(O::div_count(tx, nxt), O::div_count(ty, nxt));
-            }
-            R2 own = cur[0];                                                  // :67-68
-#pragma unroll
-            for (int k = 1; k < CAP; ++k) if (k < n && k == si) own = cur[k];
-#pragma unroll
-            for (int k = 0; k < CAP - 1; ++k) {                               // np.delete(cur - cur[si], si, 0)
-                if (k < n - 1) {
-                    const R2 c = (k < si) ? cur[k] : cur[k + 1];
-                    others[k] = O::make(O::sub(c.x, own.x), O::sub(c.y, own.y));
-                }
-            }
-            R2 out = ezpolicy_dev<T, NF>(others, tgt, s_tv0[qe * N + i], n);  // :76-79
-            out = O::make(O::mul(out.x, a.mult[l]), O::mul(out.y, a.mult[l]));
-            if (nxt == 1) a.act[((size_t)blockIdx.x * a.EPC + qe) * N + i] = out;          // :81-83
-            else for (int b = 0; b < nxt; ++b) s_tv1[qe * N + i + b] = out;   // tar_vel of my subgroup (:84-97)
+    if constexpr (LV > 0) {
+        policy_layer<T, NF, NC, CPow<NF, LV>::v, CPow<NF, LV - 1>::v>(a, 0, nvalid, s_p, s_s, s_tv0, s_tv1);
+        if constexpr (LV >= 2) {
+            __syncthreads();
+            policy_layer<T, NF, NC, CPow<NF, LV - 1>::v, CPow<NF, LV - 2>::v>(a, 1, nvalid, s_p, s_s, s_tv1, s_tv0);
         }
-        __syncthreads();
-        R2* tmp = s_tv0; s_tv0 = s_tv1; s_tv1 = tmp;
+        if constexpr (LV >= 3) {
+            __syncthreads();
+            policy_layer<T, NF, NC, CPow<NF, LV - 2>::v, CPow<NF, LV - 3>::v>(a, 2, nvalid, s_p, s_s, s_tv0, s_tv1);
+        }
+        if constexpr (LV >= 4) {
+            __syncthreads();
+            policy_layer<T, NF, NC, CPow<NF, LV - 3>::v, CPow<NF, LV - 4>::v>(a, 3, nvalid, s_p, s_s, s_tv1, s_tv0);
+        }
+        if constexpr (LV >= 5) {
+            __syncthreads();
+            policy_layer<T, NF, NC, CPow<NF, LV - 4>::v, CPow<NF, LV - 5>::v>(a, 4, nvalid, s_p, s_s, s_tv0, s_tv1);
+        }
+        static_assert(LV <= 5, "instantiate more layers");
+    } else {
+        for (int l = 0; l < a.levels; ++l) {
+            policy_layer<T, NF, 0, 0, 0>(a, l, nvalid, s_p, s_s, s_tv0, s_tv1);
+            __syncthreads();
+            R2* tmp = s_tv0; s_tv0 = s_tv1; s_tv1 = tmp;
+        }
     }
 }
 

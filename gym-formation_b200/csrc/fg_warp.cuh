@@ -82,10 +82,6 @@ __global__ void __launch_bounds__(32 * WarpLayout<T, N, WOBS>::MAXW, WarpLayout<
     typedef WarpLayout<T, N, WOBS> LY;
     constexpr int EPW = LY::EPW, NA = LY::NA, IPR = LY::IPR;
     constexpr unsigned FULL = 0xffffffffu;
-    #ifndef FG_COOP_MIN_N
-#define FG_COOP_MIN_N 16
-#endif
-    constexpr bool COOP_STATIC = WOBS && SCN == kScnHD && LY::LATE_FILL && N >= FG_COOP_MIN_N;   // static row part written by the warp
     extern __shared__ __align__(128) unsigned char smem_raw[];
 
     const bool f_collide = STD ? true : (a.collide != 0), f_noise = STD ? false : (a.u_noise > (T)0);

@@ -12,6 +12,7 @@ import numpy as np
 import torch
 
 from . import _native as nat
+from . import core as _core
 
 
 def _uniform(values, what, allow_mixed=False):
@@ -34,6 +35,7 @@ class FacadeBackend(object):
                  ("pos", 2, "N"), ("vel", 2, "N"), ("comm", 2, "N"), ("lm", 2, "L"), ("lmv", 2, "L"), ("step", 0, "i32"),
                  ("reward", 1, "N"), ("indiv", 1, "N"), ("done", 0, "u8"), ("obs", 0, "obs"))
     _INOUT_FIRST, _OUT_FIRST = "pos", "reward"
+    ZERO_COPY_MAX_BYTES = 64 * 1024
 
     def __init__(self, world):
         self.lib = nat.load()
@@ -53,6 +55,7 @@ class FacadeBackend(object):
         self._pval = None
         self._cache_key = None
         self._cache_val = None
+        self._bufcache = {}
         self.launches = 0
 
     def _alloc(self, obs_dim):
@@ -65,13 +68,20 @@ class FacadeBackend(object):
             self._off[name] = (off, nbytes)
             off = (off + nbytes + 15) & ~15
         self._obs_cap = obs_dim
-        self.d = torch.zeros(off, dtype=torch.uint8, device=self.device)
         self.h = torch.zeros(off, dtype=torch.uint8).pin_memory()
+        # Small arenas (a few KB at N = 3 .. 27) are used ZERO-COPY: the kernels read and write the pinned host arena
+        # directly through its unified address, so a step is one launch + one stream synchronisation instead of
+        # H2D copy + launch + D2H copy + synchronisation (two copy-engine round trips and two API calls less; the
+        # step is pure latency at E = 1).  Large arenas (N = 243: 2.8 MB of observations) keep the device copy:
+        # streaming them over PCIe from the SMs would be slower than the copy engine.
+        self.zero_copy = off <= self.ZERO_COPY_MAX_BYTES
+        self.d = self.h if self.zero_copy else torch.zeros(off, dtype=torch.uint8, device=self.device)
+        self._base = self.d.data_ptr()
         hn = self.h.numpy()
 
         def views(name, dtype_t, dtype_n, shape):
             o, nb = self._off[name]
-            return (self.d[o:o + nb].view(dtype_t).view(shape), hn[o:o + nb].view(dtype_n).reshape(shape))
+            return (None, hn[o:o + nb].view(dtype_n).reshape(shape))
         T, Tn = self.dtype, self.np_dtype
         self.act, self.h_act = views("act", T, Tn, (1, N, 4))
         self.shape, self.h_shape = views("shape", T, Tn, (1, N, 2))
@@ -94,17 +104,27 @@ class FacadeBackend(object):
     # ------------------------------------------------------------------ host <-> device
     def _h2d(self):
         """Everything the kernels read: [act .. step]."""
+        if self.zero_copy:
+            return
         end = self._off["step"][0] + 16
         self.d[:end].copy_(self.h[:end], non_blocking=True)
 
     def _d2h(self, last):
         """Everything the kernels wrote, from ``pos`` up to and including segment ``last`` (+ used obs rows)."""
-        start = self._off[self._INOUT_FIRST][0]
-        o, nb = self._off[last]
-        if last == "obs":
-            nb = self.N * self._D * self.np_dtype.itemsize
-        end = (o + nb + 15) & ~15
-        self.h[start:end].copy_(self.d[start:end], non_blocking=True)
+        if not self.zero_copy:
+            start = self._off[self._INOUT_FIRST][0]
+            o, nb = self._off[last]
+            if last == "obs":
+                nb = self.N * self._D * self.np_dtype.itemsize
+            end = (o + nb + 15) & ~15
+            self.h[start:end].copy_(self.d[start:end], non_blocking=True)
+        self._sync()
+
+    def _p(self, name):
+        """Address the kernels use for arena segment ``name`` (device arena, or the pinned host arena when zero-copy)."""
+        return self._base + self._off[name][0]
+
+    def _sync(self):
         torch.cuda.current_stream(self.device).synchronize()
 
     def _h_obs(self):
@@ -112,14 +132,12 @@ class FacadeBackend(object):
 
     def _params(self, world, scenario_kind, prescaled, scenario=None):
         """fg_params of the world's constants; rebuilt only when one of them changed."""
-        agents = world.agents
-        key = (scenario_kind, bool(prescaled), world.dt, world.damping, world.contact_force, world.contact_margin,
-               world.world_length, world.dim_c, getattr(scenario, "num_obs", None), getattr(scenario, "obs_range", None),
-               tuple((a.movable, a.collide, a.silent, a.u_noise, a.c_noise, a.mass, a.size, a.accel, a.max_speed,
-                      getattr(a, "ghost", False)) for a in agents),
-               tuple((l.movable, l.collide, l.size, l.mass, l.max_speed) for l in world.landmarks),
+        # every attribute assignment on a World / Entity / Wall record bumps core.config_version(); the scenario's
+        # own knobs and the (in-place mutable) wall geometry are compared by value
+        key = (scenario_kind, bool(prescaled), _core.config_version(), len(world.agents), len(world.landmarks),
+               getattr(scenario, "num_obs", None), getattr(scenario, "obs_range", None),
                tuple((w.orient, float(w.axis_pos), float(w.endpoints[0]), float(w.endpoints[1]), float(w.width),
-                      bool(w.hard)) for w in world.walls))
+                      bool(w.hard)) for w in world.walls) if world.walls else ())
         if key == self._pkey:
             return self._pval
         self._pval = self._build_params(world, scenario_kind, prescaled, scenario)
@@ -205,12 +223,24 @@ class FacadeBackend(object):
                 a.state.c = Cm[i, :world.dim_c].copy() if world.dim_c <= 2 else np.zeros(world.dim_c)
 
     def _buffers(self, scenario_kind, with_obs, scenario=None):
+        """fg_buffers block for one entry point; cached (the arena only moves when it is re-allocated)."""
+        ck = (scenario_kind, bool(with_obs), int(getattr(scenario, "num_obs", 3) or 0))
+        hit = self._bufcache.get(ck)
+        if hit is not None and hit[2] == self.d.data_ptr():
+            if with_obs:
+                self._D = hit[1]
+            return hit[0]
+        b = self._build_buffers(scenario_kind, with_obs, scenario)
+        self._bufcache[ck] = (b, getattr(self, "_D", 0), self.d.data_ptr())
+        return b
+
+    def _build_buffers(self, scenario_kind, with_obs, scenario=None):
         b = nat.fg_buffers()
-        b.pos, b.vel, b.act, b.comm = nat.ptr(self.pos), nat.ptr(self.vel), nat.ptr(self.act), nat.ptr(self.comm)
-        b.ideal_shape, b.ideal_vel = nat.ptr(self.shape), nat.ptr(self.ivel)
-        b.landmarks = nat.ptr(self.lm) if self.L > 0 else None
-        b.landmark_vel = nat.ptr(self.lmv) if (self.L > 0 and scenario_kind == nat.FG_SCENARIO_HD_OBSTACLE) else None
-        b.step = nat.ptr(self.step)
+        b.pos, b.vel, b.act, b.comm = self._p("pos"), self._p("vel"), self._p("act"), self._p("comm")
+        b.ideal_shape, b.ideal_vel = self._p("shape"), self._p("ivel")
+        b.landmarks = self._p("lm") if self.L > 0 else None
+        b.landmark_vel = self._p("lmv") if (self.L > 0 and scenario_kind == nat.FG_SCENARIO_HD_OBSTACLE) else None
+        b.step = self._p("step")
         if with_obs:
             from .batched import obs_dim, SCENARIOS
             name = [k for k, v in SCENARIOS.items() if v == scenario_kind][0]
@@ -223,13 +253,13 @@ class FacadeBackend(object):
                     if nm != "obs":
                         o2, _ = self._off[nm]
                         self.h[o2:o2 + nb] = keep[o:o + nb]
-                return self._buffers(scenario_kind, with_obs, scenario)
-            b.obs = nat.ptr(self.obs)
-        b.reward, b.indiv, b.done = nat.ptr(self.reward), nat.ptr(self.indiv), nat.ptr(self.done)
+                return self._build_buffers(scenario_kind, with_obs, scenario)
+            b.obs = self._p("obs")
+        b.reward, b.indiv, b.done = self._p("reward"), self._p("indiv"), self._p("done")
         return b
 
     def _stream(self):
-        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        return C.c_void_p(torch._C._cuda_getCurrentRawStream(self.device.index))
 
     def _stage_actions(self, U, silent, Cact=None):
         if silent:

@@ -73,6 +73,7 @@ class BatchedFormationEnv:
         if dtype not in (torch.float32, torch.float64):
             raise ValueError("dtype must be torch.float32 or torch.float64")
         self._lib = nat.load()                      # raises when the CUDA extension is missing
+        self._fns = {}
         if not torch.cuda.is_available():
             raise nat.NativeError("no CUDA device: formation_gym has no CPU fallback")
         self.scenario = scenario
@@ -97,6 +98,7 @@ class BatchedFormationEnv:
             raise nat.NativeError("device must be a CUDA device: there is no CPU fallback")
         if self.device.index is None:
             self.device = torch.device("cuda", torch.cuda.current_device())
+        self._dev_index = self.device.index
         self.dtype = dtype
         self._sfx = "" if dtype == torch.float32 else "_f64"
         d = _DEFAULTS[scenario]
@@ -183,12 +185,14 @@ class BatchedFormationEnv:
         return b
 
     def _stream(self):
-        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        # raw cudaStream_t of torch's CURRENT stream on this device (what torch.cuda.current_stream(dev).cuda_stream
+        # returns, without building a Stream object: the step path is launch-bound for small batches)
+        return C.c_void_p(torch._C._cuda_getCurrentRawStream(self._dev_index))
 
     def _on_device(self):
         """Context that makes ``self.device`` current; free when it already is (the common case --
         one process per GPU), so a step costs one ctypes call on the host."""
-        if torch.cuda.current_device() == self.device.index:
+        if torch._C._cuda_getDevice() == self._dev_index:
             return _NULL_CTX
         return torch.cuda.device(self.device)
 
@@ -212,7 +216,10 @@ class BatchedFormationEnv:
         self._ext_bufs = None
 
     def _fn(self, name):
-        return getattr(self._lib, name + self._sfx)
+        f = self._fns.get(name)
+        if f is None:
+            f = self._fns[name] = getattr(self._lib, name + self._sfx)
+        return f
 
     def _check_actions(self, actions):
         if not torch.is_tensor(actions):

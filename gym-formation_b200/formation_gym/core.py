@@ -10,6 +10,24 @@ Python/numpy implementation of the physics in this package.
 """
 import numpy as np
 
+# Bumped whenever a constant the kernels read (sizes, masses, flags, walls, world constants ...) is assigned on a
+# World / Entity / Wall record, so that the device backend rebuilds its parameter block only then instead of
+# comparing every attribute of every agent on every step.  Per-step records (state, action, counters) do not count.
+_config_version = [0]
+_PER_STEP_ATTRS = frozenset(("state", "action", "world_step", "cached_dist_vect", "cached_dist_mag", "_backend",
+                             "seed", "color", "name", "i", "channel", "goal"))
+
+
+def config_version():
+    return _config_version[0]
+
+
+class _Tracked(object):
+    def __setattr__(self, name, value):
+        if name not in _PER_STEP_ATTRS:
+            _config_version[0] += 1
+        object.__setattr__(self, name, value)
+
 
 class EntityState(object):
     def __init__(self):
@@ -29,7 +47,7 @@ class Action(object):
         self.c = None          # communication action
 
 
-class Wall(object):
+class Wall(_Tracked):
     def __init__(self, orient='H', axis_pos=0.0, endpoints=(-1, 1), width=0.1, hard=True):
         self.orient = orient                   # 'H'orizontal or 'V'ertical
         self.axis_pos = axis_pos               # y for H, x for V
@@ -39,7 +57,7 @@ class Wall(object):
         self.color = np.array([0.0, 0.0, 0.0])
 
 
-class Entity(object):
+class Entity(_Tracked):
     def __init__(self):
         self.i = 0
         self.name = ''
@@ -81,7 +99,7 @@ class Agent(Entity):
         self.goal = None
 
 
-class World(object):
+class World(_Tracked):
     """Multi-agent world.  Same public attributes as the reference (core.py:112-139)."""
 
     def __init__(self, world_length=50):

@@ -185,29 +185,46 @@ class MultiAgentEnv(object):
         obs_n, reward_n, done_n, info_n = [], [], [], []
         if fused:
             silent = all(a.silent for a in self.agents)
-            acts, acts_c = [], []
+            n, dim_p = len(self.agents), self.world.dim_p
+            acts_c = []
+            plain = silent and not (self.discrete_action_input or self.discrete_action_space
+                                    or self.force_discrete_action)
+            U = None
+            if plain:
+                try:                                        # the common case in one conversion: N arrays of dim_p floats
+                    U = np.array(action_n, dtype=np.float64)
+                    if U.shape != (n, dim_p):
+                        U = U[:, :dim_p] if (U.ndim == 2 and U.shape[0] == n and U.shape[1] >= dim_p) else None
+                except (ValueError, TypeError):
+                    U = None
+            if U is None:
+                U = np.empty((n, dim_p))
+                for i, agent in enumerate(self.agents):
+                    a_u, a_c = self._split_action(action_n[i], agent)
+                    U[i] = self._decode_u(a_u, agent)
+                    if not silent:
+                        acts_c.append(np.array(a_c, dtype=np.float64))
+            # host records as _set_action leaves them (environment.py:188-236): callbacks and render code that read
+            # agent.action see the same values on the fused and on the callback path
+            zc = np.zeros(self.world.dim_c)
             for i, agent in enumerate(self.agents):
-                a_u, a_c = self._split_action(action_n[i], agent)
-                acts.append(self._decode_u(a_u, agent))
-                # host records as _set_action leaves them (environment.py:188-236): callbacks and render code
-                # that read agent.action see the same values on the fused and on the callback path
-                agent.action.u = acts[-1] * (5.0 if agent.accel is None else agent.accel)
-                agent.action.c = np.zeros(self.world.dim_c)
-                if not silent:
-                    acts_c.append(np.array(a_c, dtype=np.float64))
-                    agent.action.c = acts_c[-1].copy()
+                agent.action.u = U[i] * (5.0 if agent.accel is None else agent.accel)
+                agent.action.c = zc.copy() if silent else acts_c[i].copy()
             self.world.world_step += 1
             out = self.world.backend().step_fused(
-                self.world, sc, sc.native_kind, np.stack(acts), self.current_step - 1,
+                self.world, sc, sc.native_kind, U, self.current_step - 1,
                 None if silent else np.stack(acts_c))
+            obs_n = list(out["obs"])                        # rows of a fresh array (nothing aliases the backend)
+            indiv = out["indiv"].tolist()
+            done = bool(out["done"])
             for i, agent in enumerate(self.agents):
-                obs_n.append(out["obs"][i].copy())
-                reward_n.append([float(out["indiv"][i])])
-                done_n.append(bool(out["done"]))
-                info = {'individual_reward': float(out["indiv"][i])}
-                env_info = self._get_info(agent)
-                if 'fail' in env_info.keys():
-                    info['fail'] = env_info['fail']
+                reward_n.append([indiv[i]])
+                done_n.append(done)
+                info = {'individual_reward': indiv[i]}
+                if self.info_callback is not None:
+                    env_info = self._get_info(agent)
+                    if 'fail' in env_info.keys():
+                        info['fail'] = env_info['fail']
                 info_n.append(info)
             reward = out["reward"]
         else:

@@ -16,11 +16,13 @@ class Box(Space):
         self.dtype = np.dtype(dtype)
         self.low = np.full(self.shape, low, dtype=self.dtype)
         self.high = np.full(self.shape, high, dtype=self.dtype)
+        # sampling bounds (unbounded sides fall back to [-1, 1]); computed once: sample() is on the per-step path of
+        # the reference's demo loop (test.py:20)
+        self._lo = np.where(np.isfinite(self.low), self.low, -1.0).astype(np.float64)
+        self._hi = np.where(np.isfinite(self.high), self.high, 1.0).astype(np.float64)
 
     def sample(self):
-        lo = np.where(np.isfinite(self.low), self.low, -1.0)
-        hi = np.where(np.isfinite(self.high), self.high, 1.0)
-        return np.random.uniform(lo, hi, self.shape).astype(self.dtype)
+        return np.random.uniform(self._lo, self._hi, self.shape).astype(self.dtype)
 
     def contains(self, x):
         x = np.asarray(x)

@@ -588,8 +588,8 @@ def test_misaligned_vector_buffers_are_rejected():
         env.step_random()
 
 
-def _run_basic(E, dtype, steps, force_tile, rollout=False, u_noise=None):
-    with nat.options(force_tile_kernel=int(force_tile)):
+def _run_basic(E, dtype, steps, force_tile, rollout=False, u_noise=None, no_std=0):
+    with nat.options(force_tile_kernel=int(force_tile), no_std_kernel=int(no_std)):
         env = BatchedFormationEnv("basic_formation_env", E, 3, episode_length=7, dtype=dtype, seed=13,
                                   auto_reset=True, u_noise=u_noise)
         env.reset()
@@ -631,9 +631,11 @@ def test_basic_warp_kernel_matches_tile_kernel(E, dtype):
         assert torch.equal(da, db)
         if dtype == torch.float64:
             assert torch.equal(ra, rb) and torch.equal(ia, ib)
-    c, _ = _run_basic(E, dtype, 16, force_tile=False, rollout=True)
-    for k in a:
-        assert torch.allclose(a[k], c[k], rtol=1e-12) if k == "stats" else torch.equal(a[k], c[k]), k
+    # in-kernel rollout == stepwise, bit for bit, on ONE instantiation (single fp32 steps otherwise take the STD one)
+    a0, _ = _run_basic(E, dtype, 16, force_tile=False, no_std=1)
+    c, _ = _run_basic(E, dtype, 16, force_tile=False, rollout=True, no_std=1)
+    for k in a0:
+        assert torch.allclose(a0[k], c[k], rtol=1e-12) if k == "stats" else torch.equal(a0[k], c[k]), k
     if dtype == torch.float64:
         n1, _ = _run_basic(E, dtype, 5, force_tile=False, u_noise=0.2)
         n2, _ = _run_basic(E, dtype, 5, force_tile=True, u_noise=0.2)
