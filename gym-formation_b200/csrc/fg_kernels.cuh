@@ -855,11 +855,11 @@ __global__ void __launch_bounds__(kBlock, (OM == 3 && SCN == kScnBasic) ? 5 : (O
                 bool nan_seen = false;
                 for (int j = 0; j < N; ++j) {
                     R2 pj = envp[j];
-                    T d = O::norm2(O::sub(pj.x, l.x), O::sub(pj.y, l.y));
+                    T d = O::norm2sq(O::sub(pj.x, l.x), O::sub(pj.y, l.y));     // one sqrt after the loop (monotonic)
                     nan_seen |= (d != d);
                     m = fmin(m, d);
                 }
-                s_lmin[q] = nan_seen ? O::from_bits(~(Bits)0 >> 1) : m;
+                s_lmin[q] = nan_seen ? O::from_bits(~(Bits)0 >> 1) : O::sqrt_(m);
             }
         }
         __syncthreads();

@@ -30,6 +30,9 @@ template <> struct Ops<float> {
     static __device__ __forceinline__ void sincos_(float a, float* s, float* c) { sincosf(a, s, c); }
     static __device__ __forceinline__ float sq2(float x, float y) { return x * x + y * y; }
     static __device__ __forceinline__ float norm2(float x, float y) { return sqrtf(x * x + y * y); }
+    // the argument of norm2's square root: min_k norm2(v_k) == sqrt_(min_k norm2sq(v_k)) exactly (sqrt is monotonic and
+    // correctly rounded), which replaces k square roots by one
+    static __device__ __forceinline__ float norm2sq(float x, float y) { return x * x + y * y; }
     // Ordering key of a 2-vector's length for argsort / argmin decisions: the squared length (sqrt is
     // monotonic, so the order is the same except for sub-ulp ties the fp32 build cannot reproduce anyway).
     static __device__ __forceinline__ float lenkey(float x, float y) { return x * x + y * y; }
@@ -62,6 +65,7 @@ template <> struct Ops<double> {
     static __device__ __forceinline__ double norm2(double x, double y) {
         return __dsqrt_rn(__fma_rn(y, y, __dmul_rn(x, x)));
     }
+    static __device__ __forceinline__ double norm2sq(double x, double y) { return __fma_rn(y, y, __dmul_rn(x, x)); }
     static __device__ __forceinline__ double lenkey(double x, double y) { return norm2(x, y); }   // as np.linalg.norm
     static __device__ __forceinline__ double div_count(double x, int n) { return __ddiv_rn(x, (double)n); }
     static __device__ __forceinline__ Bits bits(double a) { return (Bits)__double_as_longlong(a); }

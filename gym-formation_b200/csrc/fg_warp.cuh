@@ -304,20 +304,20 @@ __global__ void __launch_bounds__(32 * WarpLayout<T, N, WOBS>::MAXW, WarpLayout<
             if (active) {
                 const R2* eA = s_pnew + le * 2 * N;                         // eA[k] = agent k
                 // reward part 1 (basic_formation_env.py:45-47), lane i <-> landmark i = S
-                T m = (T)INFINITY;
+                T m = (T)INFINITY;                                          // min_a |p_a - l|^2; one sqrt after the loop
                 bool nan_seen = false;
                 unsigned hit = 0;
 #pragma unroll
                 for (int k = 0; k < N; ++k) {
                     R2 q = eA[k];
-                    T d = O::norm2(O::sub(q.x, S.x), O::sub(q.y, S.y));
+                    T d = O::norm2sq(O::sub(q.x, S.x), O::sub(q.y, S.y));
                     nan_seen |= (d != d);
                     m = fmin(m, d);
                     // is_collision candidates, self included (basic_formation_env.py:48-51,89-91)
                     T dx = O::sub(q.x, p.x), dy = O::sub(q.y, p.y);
                     hit |= (dx * dx + dy * dy < a.rthr2_hi) ? (1u << k) : 0u;
                 }
-                s_lmin[lane] = nan_seen ? O::from_bits(~(Bits)0 >> 1) : m;
+                s_lmin[lane] = nan_seen ? O::from_bits(~(Bits)0 >> 1) : O::sqrt_(m);
                 while (f_collide && hit) {
                     const int k = __ffs(hit) - 1;
                     hit &= hit - 1;

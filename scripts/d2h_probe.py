@@ -62,3 +62,24 @@ print("host scatter of packed rows (torch, %d threads): %.3f ms" % (torch.get_nu
 done.fill_(1)
 t = run(2, host, 5, done)
 print("mode 2, every env done (whole rows): %.3f ms  %.2f GB/s" % (t * 1e3, full_b / t / 1e9))
+
+# ---- 2-D copies split over K streams (K copy-engine queues): does the small-row DMA scale beyond one engine?
+for K in (1, 2, 3, 4, 6, 8):
+    streams = [torch.cuda.Stream(device=dev) for _ in range(K)]
+    per = E // K
+
+    def once():
+        for k, s in enumerate(streams):
+            e0 = k * per
+            ne = per if k < K - 1 else E - e0
+            off = e0 * N * 6 * N * 4
+            nat.check(lib.fg_obs_to_host(obs.data_ptr() + off, host.data_ptr() + off, None, None, ne, N, row_items, dyn, 8, 1,
+                                         C.c_void_p(s.cuda_stream)), "fg_obs_to_host")
+        for s in streams:
+            s.synchronize()
+    once(); once()
+    t0 = time.perf_counter()
+    for _ in range(10):
+        once()
+    t = (time.perf_counter() - t0) / 10
+    print("mode 1 over %d streams: %.3f ms  %.2f GB/s useful" % (K, t * 1e3, dyn_b / t / 1e9), flush=True)

@@ -293,3 +293,21 @@ def test_nan_flag_marks_exactly_the_failed_envs(scen, N):
     assert not bool(torch.isnan(env.pos).any())
     assert env.nan_envs(clear=True).tolist() == [5]                 # sticky until cleared
     assert env.nan_envs().numel() == 0
+
+
+@pytest.mark.parametrize("scen,N,E", [("formation_hd_env", 9, 3000), ("formation_hd_env", 27, 200), ("basic_formation_env", 3, 5000)])
+def test_l2_prefetch_does_not_change_results(scen, N, E):
+    """The warp kernel's prefetch.global.L2 of the state two spans ahead (on by default only for batches whose state
+    exceeds ~1/3 of L2) is a pure hint: forcing it on / off gives bit-identical trajectories."""
+    from formation_gym import _native as nat
+    outs = []
+    for mode in (0, 2):
+        with nat.options(l2_prefetch=mode):
+            env = BatchedFormationEnv(scen, E, N, episode_length=4, seed=8, auto_reset=True)
+            env.reset()
+            for _ in range(6):
+                env.step_random()
+            torch.cuda.synchronize()
+            outs.append({k: getattr(env, k).clone() for k in ("pos", "vel", "obs", "reward", "step_count")})
+    for k in outs[0]:
+        assert torch.equal(outs[0][k], outs[1][k]), k

@@ -132,3 +132,44 @@ def test_render_bridge_batched():
     venv.reset()
     assert venv.render('rgb_array').shape == (700, 700, 3)
     venv.close()
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64], ids=["f32", "f64"])
+@pytest.mark.parametrize("N,E", [(9, 301), (40, 17), (3, 1000)])
+def test_obs_to_host_modes(N, E, dtype):
+    """fg_obs_to_host: every mode leaves exactly the bytes it promises in the pinned host array -- mode 0 the whole
+    tensor, mode 1 the dynamic prefix of every row, mode 2 the prefix plus WHOLE rows where done != 0 (device-side
+    flags), mode 3 the packed prefixes -- and nothing else (the rest of the host array keeps its old contents)."""
+    import ctypes as C
+    from formation_gym import _native as nat
+    lib = nat.load()
+    row_items, dyn = 3 * N, N
+    obs = torch.randn(E, N, 6 * N, device="cuda", dtype=dtype)
+    done = torch.zeros(E, N, dtype=torch.uint8, device="cuda")
+    done[::5] = 1
+    stage_d = torch.empty(E * N, 2 * dyn, device="cuda", dtype=dtype)
+    isz = 8 if dtype == torch.float32 else 16
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    oc = obs.cpu()
+
+    def run(mode, dst, dn=None):
+        nat.check(lib.fg_obs_to_host(obs.data_ptr(), dst.data_ptr(), None if dn is None else dn.data_ptr(),
+                                     stage_d.data_ptr(), E, N, row_items, dyn, isz, mode, st), "fg_obs_to_host")
+        torch.cuda.synchronize()
+    host = torch.full((E, N, 6 * N), -3.0, dtype=dtype).pin_memory()
+    run(0, host)
+    assert torch.equal(host, oc)
+    for mode in (1, 2):
+        host.fill_(-3.0)
+        run(mode, host)
+        assert torch.equal(host[:, :, :2 * N], oc[:, :, :2 * N]) and bool((host[:, :, 2 * N:] == -3.0).all())
+    host.fill_(-3.0)
+    run(2, host, done)
+    assert torch.equal(host[::5], oc[::5])
+    keep = torch.ones(E, dtype=torch.bool); keep[::5] = False
+    assert torch.equal(host[keep][:, :, :2 * N], oc[keep][:, :, :2 * N]) and bool((host[keep][:, :, 2 * N:] == -3.0).all())
+    packed = torch.empty(E * N, 2 * dyn, dtype=dtype).pin_memory()
+    run(3, packed)
+    assert torch.equal(packed, oc.view(E * N, 6 * N)[:, :2 * N])
+    assert lib.fg_obs_to_host(obs.data_ptr(), host.data_ptr(), None, None, E, N, row_items, row_items + 1, isz, 1, st) == -1
+    assert lib.fg_obs_to_host(obs.data_ptr(), host.data_ptr(), None, None, E, N, row_items, dyn, 12, 1, st) == -1
