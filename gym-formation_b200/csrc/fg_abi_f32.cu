@@ -87,6 +87,11 @@ int fg_launch_geometry(int N, int* envs_per_cta, int* threads_per_cta) {
     return FG_OK;
 }
 
+int fg_pair_distances(const void* ent_pos, const void* ent_size, int E, int M, void* dist_vect, void* dist_mag,
+                      uint8_t* collisions, void* min_dists, void* stream) {
+    return pair_distances_impl<float>(ent_pos, ent_size, E, M, dist_vect, dist_mag, collisions, min_dists, stream);
+}
+
 int fg_world_step(const fg_params* p, const fg_buffers* b, int E, int N, uint64_t seed, uint32_t tick,
                   uint32_t env_offset, void* stream) {
     return world_step_impl<float>(p, b, E, N, seed, tick, env_offset, stream);

@@ -8,6 +8,11 @@ int fg_policy_bfs_f64(const void* pos, const void* ideal_shape, const void* idea
     return policy_bfs_impl<double>(pos, ideal_shape, ideal_vel, act, E, N, num_agents_per_layer, stream);
 }
 
+int fg_pair_distances_f64(const void* ent_pos, const void* ent_size, int E, int M, void* dist_vect, void* dist_mag,
+                      uint8_t* collisions, void* min_dists, void* stream) {
+    return pair_distances_impl<double>(ent_pos, ent_size, E, M, dist_vect, dist_mag, collisions, min_dists, stream);
+}
+
 int fg_world_step_f64(const fg_params* p, const fg_buffers* b, int E, int N, uint64_t seed, uint32_t tick,
                       uint32_t env_offset, void* stream) {
     return world_step_impl<double>(p, b, E, N, seed, tick, env_offset, stream);

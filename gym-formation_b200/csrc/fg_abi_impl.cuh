@@ -135,7 +135,7 @@ int fill_args(fg::KArgs<T>& a, const fg_params* p, const fg_buffers* b, int scen
     a.shape = (R2*)b->ideal_shape; a.ivel = (R2*)b->ideal_vel; a.lm = (R2*)b->landmarks;
     a.step = b->step; a.obs = (R2*)b->obs; a.reward = (T*)b->reward; a.indiv = (T*)b->indiv;
     a.done = b->done; a.ep_return = (T*)b->ep_return; a.ep_coll = b->ep_collisions; a.stats = b->stats;
-    a.tick_dev = b->tick_dev; a.nan_flag = b->nan_flag;
+    a.tick_dev = b->tick_dev; a.nan_flag = b->nan_flag; a.cpos = (const R2*)b->contact_pos;
     a.a_mass = (const T*)p->agent_mass; a.a_size = (const T*)p->agent_size_arr;
     a.a_accel = (const T*)p->agent_accel; a.a_vmax = (const T*)p->agent_max_speed;
     a.E = E; a.N = N; a.L = L;
@@ -196,7 +196,7 @@ int fill_args(fg::KArgs<T>& a, const fg_params* p, const fg_buffers* b, int scen
         // 93 -> 59 us per 1024 envs); with observations the kernel is bound by its obs writer and the extra
         // shared memory only pays for large N
         a.fast_pairs = N >= 32 && (!b->obs || N >= 64 || sw.force_fast_pairs.load(std::memory_order_relaxed)) &&
-                       !sw.no_fast_pairs.load(std::memory_order_relaxed);
+                       !sw.no_fast_pairs.load(std::memory_order_relaxed) && !b->contact_pos;
     }
     {
         // hashed cell lists of the packed pair loops (fg_pairs.cuh): buckets per env = largest power of two
@@ -425,7 +425,7 @@ bool warp_path_ok(const fg::KArgs<T>& a, int scenario, const fg_params* p, const
         if (b->landmarks) return false;                             // landmark tracking: tile kernel
     }
     if (p->agent_mass || p->agent_size_arr || p->agent_accel || p->agent_max_speed) return false;
-    if (p->n_walls != 0 || !p->silent) return false;
+    if (p->n_walls != 0 || !p->silent || b->contact_pos) return false;
     if (((uintptr_t)b->obs) % sizeof(typename fg::Ops<T>::R2)) return false;
     return !fgabi::switches().force_tile_kernel.load(std::memory_order_relaxed);   // A/B switch for tests and profiling
 }
@@ -435,6 +435,8 @@ int world_step_impl(const fg_params* p, const fg_buffers* b, int E, int N, uint6
                     uint32_t env_offset, void* stream) {
     NvtxRange nvtx_("fg_world_step");
     fg::KArgs<T> a;
+    if (p && b && p->num_obstacles > 0 && b->contact_pos)
+        return fail(FG_ERR_ARG, "fg_world_step: contact_pos (World.cache_dists) is not supported with movable obstacles%s");
     if (p && p->num_obstacles > 0) {
         // World.step on a world with movable colliding landmarks (formation_hd_obs_env's obstacles)
         int rc = fill_args<T>(a, p, b, FG_SCENARIO_HD_OBSTACLE, E, N, p->num_landmarks, seed, tick, env_offset);
@@ -545,6 +547,22 @@ int random_actions_impl(void* act, int E, int N, uint64_t seed, uint32_t tick, u
     if (grid > 148 * 32) grid = 148 * 32;                           // grid-stride beyond 32 CTAs per SM
     fg::k_random_actions<T><<<grid, 256, 0, (cudaStream_t)stream>>>((typename fg::Ops<T>::R2*)act, n, (uint32_t)N,
                                                                    seed, tick, env_offset, tick_dev);
+    cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess) return fail(FG_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(err));
+    return FG_OK;
+}
+
+template <typename T>
+int pair_distances_impl(const void* ent, const void* size, int E, int M, void* vect, void* mag, uint8_t* coll, void* mind,
+                        void* stream) {
+    NvtxRange nvtx_("fg_pair_distances");
+    typedef typename fg::Ops<T>::R2 R2;
+    if (!ent || !size || !vect || !mag || !coll || !mind) return fail(FG_ERR_ARG, "fg_pair_distances: null pointer%s");
+    if (E < 1 || M < 1 || M > FG_MAX_AGENTS + FG_MAX_LANDMARKS) return fail(FG_ERR_ARG, "fg_pair_distances: bad E or M%s");
+    const size_t total = (size_t)E * M * M;
+    int grid = (int)std::min<size_t>((total + 255) / 256, (size_t)148 * 16);
+    fg::k_pair_distances<T><<<grid, 256, 0, (cudaStream_t)stream>>>((const R2*)ent, (const T*)size, E, M, (R2*)vect, (T*)mag,
+                                                                    coll, (T*)mind);
     cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess) return fail(FG_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(err));
     return FG_OK;

@@ -72,6 +72,7 @@ template <typename T> struct KArgs {
     int pf_dist;                     // warp kernel: > 0 = L2 prefetch of the state two spans ahead (see fg_warp.cuh)
     uint64_t seed; uint32_t tick; uint32_t env_offset;
     uint32_t* tick_dev;              // (opt) [2]: device tick added to `tick`, arrival counter (CUDA graphs)
+    const R2* cpos;                  // (opt) [E,N,2] World.cache_dists: positions the contact forces are computed from
     uint8_t* nan_flag;               // (opt) [E]: set to 1 (never cleared) when the env holds a non-finite position (Q9)
     WallT<T> walls[kMaxWalls];
 };
@@ -122,9 +123,11 @@ __device__ __forceinline__ void tick_arrive(uint32_t* tick_dev, unsigned partici
 // get_entity_collision_force (core.py:289-322), both entities movable colliders (agents).
 // (dx,dy) = p_a - p_b with a < b in entity order.  Returns `force` (core.py:312).
 template <typename T>
-__device__ __forceinline__ void contact_force(T dx, T dy, T dmin, T k, T cf, T* fx, T* fy) {
+__device__ __forceinline__ void contact_force(T dx, T dy, T dmin, T k, T cf, T* fx, T* fy, bool cached = false) {
     typedef Ops<T> O;
-    T dist = O::norm2(dx, dy);                                   // core.py:305
+    // core.py:305 np.linalg.norm(delta_pos); with World.cache_dists the distance comes from
+    // np.linalg.norm(cached_dist_vect, axis=2) (core.py:178,299-300): a plain sqrt(x*x + y*y), no dot-product FMA
+    T dist = cached ? O::sqrt_(O::sq2(dx, dy)) : O::norm2(dx, dy);
     T tt = O::div(-O::sub(dist, dmin), k);                       // -(dist - dist_min)/k
     // np.logaddexp(0, tt): stable softplus (core.py:310): tt > 0 ? tt + log1p(exp(-tt)) : log1p(exp(tt)).
     // Both branches share log1p(exp(-|tt|)), evaluated once (bit-identical to either branch).
@@ -279,7 +282,7 @@ __global__ void __launch_bounds__(kBlock, (OM == 3 && SCN == kScnBasic) ? 5 : (O
             u = a.act[g * a.act_r2];
             if (a.act_r2 > 1) uc = a.act[g * a.act_r2 + 1];
         }
-        if (PHYS) s_old[t] = p; else { s_new[t] = p; s_v[t] = v; }
+        if (PHYS) s_old[t] = a.cpos ? a.cpos[g] : p; else { s_new[t] = p; s_v[t] = v; }
         if (OBSREW) {
             if (SCN == kScnHD) {
                 const R2 S0 = a.shape[g];
@@ -448,6 +451,8 @@ __global__ void __launch_bounds__(kBlock, (OM == 3 && SCN == kScnBasic) ? 5 : (O
                         // branch-free (7 instructions per pair), pass 2 evaluates the softplus force only
                         // for set bits, in ascending j (the reference's accumulation order).
                         const T dmin = O::add(a.size, a.size);                  // core.py:307
+                        const bool cached = a.cpos != nullptr;                  // World.cache_dists (core.py:298-301)
+                        const R2 p = envp[i];                                   // my position the contacts see (== p unless cached)
                         for (int j0 = 0; j0 < N; j0 += 32) {
                             const int jn = min(32, N - j0);
                             unsigned near = 0;
@@ -468,12 +473,14 @@ __global__ void __launch_bounds__(kBlock, (OM == 3 && SCN == kScnBasic) ? 5 : (O
                                 T dx = (j < i) ? O::sub(q.x, p.x) : O::sub(p.x, q.x);   // delta = p_a - p_b, a<b
                                 T dy = (j < i) ? O::sub(q.y, p.y) : O::sub(p.y, q.y);
                                 T fx, fy;
-                                contact_force<T>(dx, dy, dmin, a.margin, a.cforce, &fx, &fy);
+                                contact_force<T>(dx, dy, dmin, a.margin, a.cforce, &fx, &fy, cached);
                                 if (j < i) { Fx = O::add(-fx, Fx); Fy = O::add(-fy, Fy); }   // equal masses: ratio 1
                                 else       { Fx = O::add(fx, Fx);  Fy = O::add(fy, Fy); }
                             }
                         }
                     } else {
+                        const bool cached = a.cpos != nullptr;
+                        const R2 p = envp[i];                                   // my position the contacts see
                         for (int j = 0; j < N; ++j) {
                             if (j == i) continue;
                             R2 q = envp[j];
@@ -492,7 +499,7 @@ __global__ void __launch_bounds__(kBlock, (OM == 3 && SCN == kScnBasic) ? 5 : (O
                             // (DESIGN.md "contact cut-off").  !(>=) keeps NaN positions propagating.
                             if (!(d2 >= cut2)) {
                                 T fx, fy;
-                                contact_force<T>(dx, dy, dmin, a.margin, a.cforce, &fx, &fy);
+                                contact_force<T>(dx, dy, dmin, a.margin, a.cforce, &fx, &fy, cached);
                                 if (HET) {
                                     T m_j = s_het[j];
                                     if (j < i) {       // i is entity b: force_b = -(1/ratio)*force, ratio = m_b/m_a
@@ -1275,6 +1282,33 @@ __global__ void __launch_bounds__(256) k_random_actions(typename Ops<T>::R2* __r
         act[g] = Ops<T>::make(uniform_pm1<T>(r.x), uniform_pm1<T>(r.y));
         e += se; i += si;
         if (i >= N) { i -= N; ++e; }
+    }
+}
+
+// World.calculate_distances (core.py:156-180) for every env: entity positions ent [E,M,2] (agents, then landmarks),
+// sizes [M] -> vect [E,M,M,2] (p_a - p_b above the diagonal, its negative below, 0 on it), mag [E,M,M]
+// (np.linalg.norm(axis=2): sqrt(x*x + y*y)), collisions [E,M,M] (mag <= min_dists; min_dists = size_a + size_b off
+// the diagonal, 0 on it -> the diagonal is True, as in the reference), min_dists [M,M].
+template <typename T>
+__global__ void __launch_bounds__(256) k_pair_distances(const typename Ops<T>::R2* __restrict__ ent, const T* __restrict__ size,
+                                                        int E, int M, typename Ops<T>::R2* __restrict__ vect,
+                                                        T* __restrict__ mag, uint8_t* __restrict__ coll, T* __restrict__ mind) {
+    typedef Ops<T> O;
+    const size_t total = (size_t)E * M * M;
+    for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < total; q += (size_t)gridDim.x * blockDim.x) {
+        const int b = (int)(q % M), a_ = (int)((q / M) % M);
+        const size_t e = q / ((size_t)M * M);
+        const int lo = a_ < b ? a_ : b, hi = a_ < b ? b : a_;
+        const typename O::R2 pl = ent[e * M + lo], ph = ent[e * M + hi];
+        T dx = O::sub(pl.x, ph.x), dy = O::sub(pl.y, ph.y);                // delta_pos = p_ia - p_ib, ia < ib (:174)
+        if (a_ == b) { dx = (T)0; dy = (T)0; }
+        else if (a_ > b) { dx = -dx; dy = -dy; }                           // cached_dist_vect[ib, ia] = -delta_pos (:176)
+        const T m = O::sqrt_(O::sq2(dx, dy));
+        const T md = a_ == b ? (T)0 : O::add(size[lo], size[hi]);         // min_dists (:161-168)
+        vect[q] = O::make(dx, dy);
+        mag[q] = m;
+        coll[q] = (uint8_t)(m <= md);                                      // :180
+        if (e == 0) mind[(size_t)a_ * M + b] = md;
     }
 }
 

@@ -31,7 +31,7 @@ class FacadeBackend(object):
     version issued ~15 small copies per step: 312 us per basic_formation_env step; the copies dominated)."""
 
     # (name, elements per unit, unit) in arena order: [in-only | in/out | out-only]; unit 'N' / 'L' / '1' / obs
-    _SEGMENTS = (("act", 4, "N"), ("shape", 2, "N"), ("ivel", 2, "1"),
+    _SEGMENTS = (("act", 4, "N"), ("shape", 2, "N"), ("ivel", 2, "1"), ("cpos", 2, "N"),
                  ("pos", 2, "N"), ("vel", 2, "N"), ("comm", 2, "N"), ("lm", 2, "L"), ("lmv", 2, "L"), ("step", 0, "i32"),
                  ("reward", 1, "N"), ("indiv", 1, "N"), ("done", 0, "u8"), ("obs", 0, "obs"))
     _INOUT_FIRST, _OUT_FIRST = "pos", "reward"
@@ -56,6 +56,8 @@ class FacadeBackend(object):
         self._cache_key = None
         self._cache_val = None
         self._bufcache = {}
+        self._cache_pos = None               # World.cache_dists: agent positions at the last calculate_distances()
+        self._dist_bufs = None
         self.launches = 0
 
     def _alloc(self, obs_dim):
@@ -86,6 +88,7 @@ class FacadeBackend(object):
         self.act, self.h_act = views("act", T, Tn, (1, N, 4))
         self.shape, self.h_shape = views("shape", T, Tn, (1, N, 2))
         self.ivel, self.h_ivel = views("ivel", T, Tn, (1, 2))
+        _, self.h_cpos = views("cpos", T, Tn, (1, N, 2))
         self.pos, self.h_pos = views("pos", T, Tn, (1, N, 2))
         self.vel, self.h_vel = views("vel", T, Tn, (1, N, 2))
         self.comm, self.h_comm = views("comm", T, Tn, (1, N, 2))
@@ -222,15 +225,18 @@ class FacadeBackend(object):
             if with_comm:
                 a.state.c = Cm[i, :world.dim_c].copy() if world.dim_c <= 2 else np.zeros(world.dim_c)
 
-    def _buffers(self, scenario_kind, with_obs, scenario=None):
-        """fg_buffers block for one entry point; cached (the arena only moves when it is re-allocated)."""
-        ck = (scenario_kind, bool(with_obs), int(getattr(scenario, "num_obs", 3) or 0))
+    def _buffers(self, scenario_kind, with_obs, scenario=None, cached=False):
+        """fg_buffers block for one entry point; cached (the arena only moves when it is re-allocated).
+        ``cached``: World.cache_dists -- contact forces from the positions of the last calculate_distances()."""
+        ck = (scenario_kind, bool(with_obs), int(getattr(scenario, "num_obs", 3) or 0), bool(cached))
         hit = self._bufcache.get(ck)
         if hit is not None and hit[2] == self.d.data_ptr():
             if with_obs:
                 self._D = hit[1]
             return hit[0]
         b = self._build_buffers(scenario_kind, with_obs, scenario)
+        if cached:
+            b.contact_pos = self._p("cpos")
         self._bufcache[ck] = (b, getattr(self, "_D", 0), self.d.data_ptr())
         return b
 
@@ -272,6 +278,16 @@ class FacadeBackend(object):
         """core.py:206-225 on the GPU; ``agent.action.u`` is already scaled (action_prescaled).  A world whose
         trailing landmarks are movable colliders (formation_hd_obs_env's obstacles) steps them too."""
         has_obst = any(l.movable or l.collide for l in world.landmarks)
+        cached = bool(getattr(world, "cache_dists", False))
+        if cached:
+            if has_obst:
+                raise NotImplementedError("World.cache_dists with movable / colliding landmarks is not supported")
+            if world.cached_dist_vect is None or self._cache_pos is None:
+                # the reference subscripts the still-empty cache here (core.py:299): a world with cache_dists set
+                # needs one calculate_distances() call before its first step
+                raise TypeError("'NoneType' object is not subscriptable (World.cache_dists: call "
+                                "world.calculate_distances() before the first step, core.py:156,299)")
+            self.h_cpos[0] = self._cache_pos
         p, silent = self._params(world, nat.FG_SCENARIO_HD_OBSTACLE if has_obst else nat.FG_SCENARIO_BASIC, True)
         self._stage_state(world)
         if has_obst:
@@ -279,7 +295,7 @@ class FacadeBackend(object):
         U = np.stack([np.asarray(a.action.u, np.float64) for a in world.agents])
         Cact = None if silent else np.stack([np.asarray(a.action.c, np.float64) for a in world.agents])
         self._stage_actions(U, silent, Cact)
-        b = self._buffers(nat.FG_SCENARIO_HD_OBSTACLE if has_obst else nat.FG_SCENARIO_BASIC, False)
+        b = self._buffers(nat.FG_SCENARIO_HD_OBSTACLE if has_obst else nat.FG_SCENARIO_BASIC, False, cached=cached)
         fn = getattr(self.lib, "fg_world_step" + self.sfx)
         with torch.cuda.device(self.device):
             self._h2d()
@@ -291,6 +307,33 @@ class FacadeBackend(object):
         if has_obst:
             self._scatter_obstacles(world, with_pos=True)        # integrated velocities: no reward hook ran
         self._cache_key = None
+
+    def calculate_distances(self, world):
+        """World.calculate_distances (core.py:156-180) on the device (fg_pair_distances): fills
+        ``world.cached_dist_vect [M,M,2]``, ``cached_dist_mag [M,M]``, ``min_dists [M,M]`` and ``cached_collisions [M,M]``
+        over world.entities (agents, then landmarks) and remembers the agents' positions of this moment -- the
+        positions the NEXT step's contact forces see (core.py:298-301)."""
+        ents = world.entities
+        M = len(ents)
+        P = np.stack([np.asarray(e.state.p_pos, np.float64) for e in ents])
+        kw = dict(dtype=self.dtype, device=self.device)
+        if self._dist_bufs is None or self._dist_bufs[0].shape[0] != M:
+            self._dist_bufs = (torch.empty(M, 2, **kw), torch.empty(M, **kw), torch.empty(M, M, 2, **kw),
+                               torch.empty(M, M, **kw), torch.empty(M, M, dtype=torch.uint8, device=self.device),
+                               torch.empty(M, M, **kw))
+        ent, size, vect, mag, coll, mind = self._dist_bufs
+        ent.copy_(torch.as_tensor(P.astype(self.np_dtype)))
+        size.copy_(torch.as_tensor(np.array([float(e.size) for e in ents], self.np_dtype)))
+        fn = getattr(self.lib, "fg_pair_distances" + self.sfx)
+        with torch.cuda.device(self.device):
+            nat.check(fn(ent.data_ptr(), size.data_ptr(), 1, M, vect.data_ptr(), mag.data_ptr(), coll.data_ptr(),
+                         mind.data_ptr(), self._stream()), "fg_pair_distances")
+        self.launches += 1
+        world.cached_dist_vect = vect.double().cpu().numpy()
+        world.cached_dist_mag = mag.double().cpu().numpy()
+        world.min_dists = mind.double().cpu().numpy()
+        world.cached_collisions = coll.cpu().numpy().astype(bool)
+        self._cache_pos = P[: self.N].copy()
 
     # ------------------------------------------------------------------ scenario hooks
     def _stage_scenario(self, world, scenario, kind):

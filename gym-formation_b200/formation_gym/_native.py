@@ -8,7 +8,7 @@ import os
 
 from . import _build
 
-FG_ABI_VERSION = 7
+FG_ABI_VERSION = 8
 FG_MAX_AGENTS = 256
 FG_MAX_LANDMARKS = 256
 FG_MAX_WALLS = 8
@@ -23,7 +23,7 @@ EXPORTS = [
     "fg_world_step", "fg_world_step_f64", "fg_obs_reward", "fg_obs_reward_f64",
     "fg_step_fused", "fg_step_fused_f64", "fg_reset", "fg_reset_f64",
     "fg_random_actions", "fg_random_actions_f64", "fg_fp32_probe", "fg_write_probe", "fg_policy_bfs", "fg_policy_bfs_f64",
-    "fg_obs_to_host",
+    "fg_obs_to_host", "fg_pair_distances", "fg_pair_distances_f64",
 ]
 
 
@@ -61,7 +61,7 @@ class fg_buffers(C.Structure):
         ("step", C.c_void_p), ("obs", C.c_void_p), ("reward", C.c_void_p), ("indiv", C.c_void_p),
         ("done", C.c_void_p), ("ep_return", C.c_void_p), ("ep_collisions", C.c_void_p),
         ("stats", C.c_void_p), ("landmark_vel", C.c_void_p), ("tick_dev", C.c_void_p),
-        ("nan_flag", C.c_void_p),
+        ("contact_pos", C.c_void_p), ("nan_flag", C.c_void_p),
     ]
 
 
@@ -101,6 +101,7 @@ def load():
             [P(fg_params), P(fg_buffers), I, I, I, I, VP, U64, U32, U32, VP]
         getattr(lib, "fg_random_actions" + sfx).argtypes = [VP, I, I, U64, U32, U32, VP, VP]
         getattr(lib, "fg_policy_bfs" + sfx).argtypes = [VP, VP, VP, VP, I, I, I, VP]
+        getattr(lib, "fg_pair_distances" + sfx).argtypes = [VP, VP, I, I, VP, VP, VP, VP, VP]
     lib.fg_obs_to_host.argtypes = [VP, VP, VP, VP, I, I, I, I, I, I, VP]
     lib.fg_fp32_probe.argtypes = [I, I, I, VP, VP]
     lib.fg_write_probe.argtypes = [I, VP, C.c_ulonglong, C.c_uint, I, VP]

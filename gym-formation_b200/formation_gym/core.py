@@ -15,6 +15,7 @@ import numpy as np
 # comparing every attribute of every agent on every step.  Per-step records (state, action, counters) do not count.
 _config_version = [0]
 _PER_STEP_ATTRS = frozenset(("state", "action", "world_step", "cached_dist_vect", "cached_dist_mag", "_backend",
+                             "min_dists", "cached_collisions",
                              "seed", "color", "name", "i", "channel", "goal"))
 
 
@@ -116,6 +117,8 @@ class World(_Tracked):
         self.cache_dists = False
         self.cached_dist_vect = None
         self.cached_dist_mag = None
+        self.min_dists = None
+        self.cached_collisions = None
         self.world_length = world_length
         self.world_step = 0
         self.num_agents = 0
@@ -165,3 +168,10 @@ class World(_Tracked):
         for agent in self.scripted_agents:
             agent.action = agent.action_callback(agent, self)
         self.backend().world_step(self)
+        if self.cache_dists:                       # core.py:224-225
+            self.calculate_distances()
+
+    def calculate_distances(self):
+        """Reference signature (core.py:156-180): the distance cache behind ``cache_dists`` -- ``cached_dist_vect``,
+        ``cached_dist_mag``, ``min_dists``, ``cached_collisions`` over ``self.entities`` -- computed on the GPU."""
+        self.backend().calculate_distances(self)

@@ -179,8 +179,9 @@ class MultiAgentEnv(object):
     def step(self, action_n):
         self.agents = self.world.policy_agents
         sc = self._native_scenario()
+        # (World.cache_dists keeps World.step() a separate call: the cache is refreshed between the physics and the hooks)
         fused = (sc is not None and self.done_callback is None and not self.world.scripted_agents
-                 and all(a.movable for a in self.agents))
+                 and all(a.movable for a in self.agents) and not getattr(self.world, "cache_dists", False))
         self.current_step += 1
         obs_n, reward_n, done_n, info_n = [], [], [], []
         if fused:

@@ -42,7 +42,7 @@
 extern "C" {
 #endif
 
-#define FG_ABI_VERSION 7
+#define FG_ABI_VERSION 8
 #define FG_MAX_AGENTS 256      /* one CTA holds at least one whole env; 3^5 = 243 fits */
 #define FG_MAX_LANDMARKS 256
 #define FG_MAX_WALLS 8
@@ -144,6 +144,12 @@ typedef struct fg_buffers {
                                   advance it by the number of env steps they ran ([1] is their arrival
                                   counter).  Lets a CUDA graph of step launches be replayed with fresh
                                   random numbers although its kernel arguments are frozen. */
+    const void* contact_pos;   /* (opt) [E,N,2] in: World.cache_dists (core.py:132,224-225,298-301).  With the cache on, the
+                                  reference's contact forces use the distances stored at the END of the previous
+                                  World.step -- i.e. the positions of that moment, which differ from the current ones
+                                  only if the state was edited in between (or after a reset without a fresh
+                                  calculate_distances()).  Those positions go here; NULL = current positions.
+                                  fg_world_step / fg_step_fused, agents only (no movable obstacles). */
     uint8_t* nan_flag;         /* (opt) [E] in/out, zero-initialised by the caller: set to 1 (and never cleared by
                                   the library) when, after a step's physics, the env holds a non-finite position --
                                   the reference's documented failure mode (coincident agents -> 0/0 in core.py:312,
@@ -223,6 +229,16 @@ int fg_reset(const fg_params* p, const fg_buffers* b, int scenario, int E, int N
 int fg_reset_f64(const fg_params* p, const fg_buffers* b, int scenario, int E, int N, int L,
                  const uint8_t* mask, uint64_t seed, uint32_t tick, uint32_t env_offset,
                  void* stream);
+
+/* World.calculate_distances (formation_gym/core.py:156-180), the distance cache behind World.cache_dists, for every env:
+ * ent_pos [E,M,2] entity positions in world.entities order (agents, then landmarks), ent_size [M] ->
+ * dist_vect [E,M,M,2] (p_a - p_b above the diagonal, the negative below), dist_mag [E,M,M]
+ * (np.linalg.norm(..., axis=2)), collisions [E,M,M] uint8 (dist_mag <= min_dists; True on the diagonal, as in the
+ * reference), min_dists [M,M] (size_a + size_b, 0 on the diagonal). */
+int fg_pair_distances(const void* ent_pos, const void* ent_size, int E, int M, void* dist_vect, void* dist_mag,
+                      uint8_t* collisions, void* min_dists, void* stream);
+int fg_pair_distances_f64(const void* ent_pos, const void* ent_size, int E, int M, void* dist_vect, void* dist_mag,
+                          uint8_t* collisions, void* min_dists, void* stream);
 
 /* Random policy: act[e,i,:] ~ U(-1,1) (test.py:20 -> Box.sample, environment.py:67-68), same
  * Philox stream the in-kernel rollout uses, so step-by-step and in-kernel rollouts agree. */

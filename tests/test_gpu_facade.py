@@ -251,3 +251,36 @@ def test_hook_cache_sees_changed_constants():
         a.size = 0.05                                    # threshold (0.05 + 0.05) / 2 = 0.05 > 0.04: collision
     r_big = sc.reward(w.agents[0], w)
     assert abs((r_small - r_big) - 1.0) <= 1e-12
+
+
+def test_cache_dists_matches_reference():
+    """World.cache_dists (core.py:132,156-180,224-225,298-301): calculate_distances() runs on the device and fills the
+    reference's four cache arrays; with the cache on, a step's contact forces come from the positions of the previous
+    calculate_distances() -- visible when the state is edited in between (agent 1 is teleported next to agent 0: the
+    next step misses the contact, the one after sees it).  Fixture from the unmodified reference, fp64, 1e-12."""
+    g = load("cache_dists_n5.npz")
+    np.random.seed(1)
+    env = formation_gym.make_env("formation_hd_env", False, 5, 25)
+    env.reset()
+    inject(env, g, "formation_hd_env")
+    w = env.world
+    for l, p in zip(w.landmarks, g["lm0"]):
+        l.state.p_pos = p.copy()
+    w.cache_dists = True
+    with pytest.raises(TypeError):                       # the reference subscripts the empty cache (core.py:299)
+        env.step([np.zeros(2)] * 5)
+    env.current_step = 0
+    w.calculate_distances()
+    assert np.abs(w.cached_dist_vect - g["vect0"]).max() <= 1e-15 and np.abs(w.cached_dist_mag - g["mag0"]).max() <= 1e-15
+    assert np.array_equal(w.min_dists, g["mind"]) and np.array_equal(w.cached_collisions, g["coll0"])
+    assert w.cached_collisions.dtype == np.bool_ and w.cached_collisions.diagonal().all()
+    for t in range(g["acts"].shape[0]):
+        if t == 3:
+            w.agents[1].state.p_pos = w.agents[0].state.p_pos + np.array([0.04, 0.01])
+            assert np.abs(np.stack([a.state.p_pos for a in w.agents]) - g["tele_pos"]).max() <= 1e-12
+        obs_n, reward_n, done_n, info_n = env.step([a.copy() for a in g["acts"][t]])
+        P = np.stack([a.state.p_pos for a in w.agents]); V = np.stack([a.state.p_vel for a in w.agents])
+        assert np.abs(P - g["pos"][t]).max() <= 1e-12 and np.abs(V - g["vel"][t]).max() <= 1e-12, t
+        assert abs(reward_n[0][0] - g["reward"][t]) <= 1e-11 and np.abs(np.stack(obs_n) - g["obs"][t]).max() <= 1e-12
+    assert np.abs(w.cached_dist_vect - g["vect_last"]).max() <= 1e-12
+    assert np.abs(w.cached_dist_mag - g["mag_last"]).max() <= 1e-12 and np.array_equal(w.cached_collisions, g["coll_last"])
