@@ -12,7 +12,7 @@ const OptionDesc kOptions[] = {
     {"no_cells", &Switches::no_cells, 0, 1},                 {"row_nbuf", &Switches::row_nbuf, 1, 2},
     {"no_early_rows", &Switches::no_early_rows, 0, 1},       {"no_tile_image", &Switches::no_tile_image, 0, 1},
     {"force_tile_kernel", &Switches::force_tile_kernel, 0, 1}, {"waves", &Switches::waves, 1, 64},
-    {"no_persistent_tiles", &Switches::no_persistent_tiles, 0, 1}, {"nvtx", &Switches::nvtx, 0, 1},
+    {"nvtx", &Switches::nvtx, 0, 1},
     {"no_std_kernel", &Switches::no_std_kernel, 0, 1}, {"l2_prefetch", &Switches::l2_prefetch, 0, 2},
 };
 }  // namespace

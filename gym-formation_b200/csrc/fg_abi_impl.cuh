@@ -35,7 +35,6 @@ struct Switches {
     std::atomic<int> no_tile_image{0};      // OM == 3 off: flat item loop
     std::atomic<int> force_tile_kernel{0};  // fg_step_fused never takes the warp-autonomous kernel
     std::atomic<int> waves{1};              // warp kernel: grid = waves x one resident wave (>= 1)
-    std::atomic<int> no_persistent_tiles{0};// tile kernel: one CTA per tile instead of a persistent grid
     std::atomic<int> no_std_kernel{0};      // warp kernel: never the STD instantiation (standard configuration, flags compiled out)
     std::atomic<int> l2_prefetch{1};        // warp kernel: prefetch.global.L2 of the state two spans ahead: 0 never, 1 auto, 2 always
     std::atomic<int> nvtx{1};               // NVTX ranges around the launches of every entry point

@@ -170,7 +170,6 @@ const char* fg_last_error(void);
  *   row_nbuf 1/2           long-row observation writer: staging buffers per warp
  *   no_early_rows 0/1      long-row observation writer: rows leave after the reward pass
  *   no_tile_image 0/1      short-row observation writer: flat item loop instead of the tile image
- *   no_persistent_tiles 0/1  tile kernel: one CTA per tile instead of a persistent grid
  *   no_std_kernel 0/1      warp kernel: never the instantiation specialised for the standard configuration
  *   l2_prefetch 0/1/2      warp kernel: prefetch.global.L2 of the state two spans ahead: never / when the state
  *                          arrays exceed ~1/3 of L2 (default) / always
