@@ -14,8 +14,7 @@ for cfg in "$@"; do
   tail -1 gpurun_out/$NAME.log
   ncu -i gpurun_out/$NAME.ncu-rep --page raw --csv > gpurun_out/$NAME.raw.csv 2>/dev/null
   ncu -i gpurun_out/$NAME.ncu-rep --page source --csv > gpurun_out/$NAME.source.csv 2>/dev/null
-  ncu -i gpurun_out/$NAME.ncu-rep --page source --csv --print-source cuda > gpurun_out/$NAME.cuda.csv 2>/dev/null
-  gzip -f gpurun_out/$NAME.source.csv gpurun_out/$NAME.cuda.csv
+  gzip -f gpurun_out/$NAME.source.csv
   [ "$KEEP_REP" = "1" ] || rm -f gpurun_out/$NAME.ncu-rep
 done
 ls -la gpurun_out | tail -20

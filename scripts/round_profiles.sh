@@ -19,5 +19,4 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --cs
 ( time timeout 300 python bench.py --impl reference --steps 100 --warmup 5 ) > gpurun_out/${TAG}_bench_reference.json 2> gpurun_out/${TAG}_bench_reference.err
 ( time timeout 900 python bench.py ) > gpurun_out/${TAG}_bench_n1.json 2> gpurun_out/${TAG}_bench_n1.err
 tail -3 gpurun_out/${TAG}_bench_n1.err
-rm -f gpurun_out/*.cuda.csv.gz
 ls -la gpurun_out | tail -40
