@@ -446,7 +446,7 @@ class BatchedFormationEnv:
 
     def state_dict(self):
         sd = {k: getattr(self, k).clone() for k in
-              ("pos", "vel", "comm", "step_count", "ep_return", "ep_collisions", "stats")}
+              ("pos", "vel", "comm", "step_count", "ep_return", "ep_collisions", "stats", "nan_flag")}
         for k in ("landmarks", "landmark_vel", "ideal_shape", "ideal_vel"):
             if getattr(self, k) is not None:
                 sd[k] = getattr(self, k).clone()
