@@ -160,18 +160,18 @@ __global__ void __launch_bounds__(32 * WarpLayout<T, N, WOBS>::MAXW, WarpLayout<
     auto l2_prefetch = [&](int span) {
         const int fe0 = span * EPW;
         if (fe0 >= a.E) return;                                             // warp-uniform
-        if (lane < min(EPW, a.E - fe0) * N) {
-            // one request per 128-byte line: the first lane of the span and every lane whose element starts a line
-            // (a prefetch per lane was measured 10 % SLOWER at N = 9 with an L2-resident state: 108 requests per
-            // iteration; bulk TMA prefetches, one per array, were worse still -- they queue with the obs bulk store)
+        // One request per 128-byte line: a span's chunk of an array is NA * 8 <= 256 bytes, so the lines holding its
+        // first element, its 17th (+128 B) and its last one cover it.  (A prefetch per lane was measured 10 % SLOWER at
+        // N = 9 with an L2-resident state -- 108 requests per iteration; testing every lane's address for a line start
+        // cost 9 % of the instructions at N = 3; bulk TMA prefetches, one per array, were worse still: they queue with
+        // the observation bulk store.)
+        const int nact = min(EPW, a.E - fe0) * N;
+        if ((lane == 0 || lane == 16 || lane == nact - 1) && lane < nact) {
             const size_t fa = (size_t)fe0 * N + lane;
-            auto pf = [&](const R2* ptr) {
-                if (lane == 0 || (reinterpret_cast<uintptr_t>(ptr + fa) & 127) == 0)
-                    asm volatile("prefetch.global.L2 [%0];" :: "l"(ptr + fa));
-            };
-            pf(a.pos); pf(a.vel);
-            pf(SCN == kScnBasic ? a.lm : a.shape);
-            if (!a.random_actions) pf(a.act);
+            asm volatile("prefetch.global.L2 [%0];" :: "l"(a.pos + fa));
+            asm volatile("prefetch.global.L2 [%0];" :: "l"(a.vel + fa));
+            asm volatile("prefetch.global.L2 [%0];" :: "l"((SCN == kScnBasic ? a.lm : a.shape) + fa));
+            if (!a.random_actions) asm volatile("prefetch.global.L2 [%0];" :: "l"(a.act + fa));
         }
     };
     fetch(gw);
