@@ -37,6 +37,7 @@ struct Switches {
     std::atomic<int> waves{1};              // warp kernel: grid = waves x one resident wave (>= 1)
     std::atomic<int> no_std_kernel{0};      // warp kernel: never the STD instantiation (standard configuration, flags compiled out)
     std::atomic<int> l2_prefetch{1};        // warp kernel: prefetch.global.L2 of the state two spans ahead: 0 never, 1 auto, 2 always
+    std::atomic<int> row_chunks{1};         // OM == 2: chunked row writer (RC whole rows per image, one bulk store per chunk)
     std::atomic<int> nvtx{1};               // NVTX ranges around the launches of every entry point
 };
 Switches& switches();                                         // defined in fg_abi_f32.cu
@@ -212,7 +213,19 @@ int fill_args(fg::KArgs<T>& a, const fg_params* p, const fg_buffers* b, int scen
     a.row_tma = scenario == FG_SCENARIO_HD && p->silent && a.IPR >= 144 && b->obs &&
                 ((uintptr_t)b->obs % sizeof(R2)) == 0;
     a.row_nbuf = fgabi::switches().row_nbuf.load(std::memory_order_relaxed) == 1 ? 1 : 2;
-    a.row_early = a.row_tma && sizeof(R2) == 8 && (N & 1) && ((uintptr_t)b->obs % 16) == 0 &&
+    // chunked row writer (fg_kernels.cuh rows_chunked): the largest power-of-two row count <= 16 whose image fits 32 KB
+    // Measured (B200, fp32, step kernel alone, chunked vs per-row pieces): N = 48 0.76 vs 0.51 of the HBM peak, 56 0.77 vs
+    // 0.57, 63 0.82 vs 0.66, 64 0.74 vs 0.65, 72 0.73 vs 0.66, 75 / 81 equal, 100 0.82 vs 0.84, 128 0.85 vs 0.88,
+    // 243 0.79 vs 0.89 (the single image stalls the CTA while its 23 KB chunk is read): chunks up to N = 80
+    // (row_chunks = 2 forces them for every N).
+    a.row_chunk = 0; a.row_chunk_log2 = 0;
+    const int rc_mode = fgabi::switches().row_chunks.load(std::memory_order_relaxed);
+    if (a.row_tma && (rc_mode == 2 || (rc_mode == 1 && N <= 80))) {
+        int lg = 4;
+        while (lg > 1 && ((size_t)(1 << lg) * a.IPR + 2) * sizeof(R2) > 32 * 1024) --lg;
+        if (((size_t)(1 << lg) * a.IPR + 2) * sizeof(R2) <= 48 * 1024) { a.row_chunk = 1 << lg; a.row_chunk_log2 = lg; }
+    }
+    a.row_early = a.row_tma && sizeof(R2) == 8 && (a.row_chunk || ((N & 1) && ((uintptr_t)b->obs % 16) == 0)) &&
                   !fgabi::switches().no_early_rows.load(std::memory_order_relaxed);
     return FG_OK;
 }
@@ -228,7 +241,9 @@ size_t smem_bytes(const fg::KArgs<T>& a, int scenario, bool het) {
     if (scenario == FG_SCENARIO_BASIC) s += (size_t)a.EPC * a.L * sizeof(T);
     if (het) s += 5 * (size_t)a.N * sizeof(T);
     s += 3 * a.EPC * sizeof(int);
-    if (a.row_tma)                                                      // static row images + per-warp staging
+    if (a.row_tma && a.row_chunk)                                       // one image of row_chunk rows (+ phase slack)
+        s += (size_t)(((size_t)a.row_chunk * a.IPR + 3) & ~(size_t)1) * sizeof(R2);
+    else if (a.row_tma)                                                 // static row images + per-warp staging
         s += ((size_t)2 * (2 * a.N + 1) * a.EPC + (size_t)a.row_nbuf * ((a.N + 3) & ~1) * (fg::kBlock / 32)) * sizeof(R2);
     return (s + 15) & ~(size_t)15;
 }

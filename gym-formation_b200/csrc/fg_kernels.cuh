@@ -56,6 +56,7 @@ template <typename T> struct KArgs {
     int mass_one;                    // mass == 1: F / m is exact without the division
     int row_tma;                     // tile kernel: long hd rows leave through TMA bulk stores (see k_step)
     int row_nbuf;                    // OM == 2: staging buffers per warp (2; 1 when that lets one more CTA fit per SM)
+    int row_chunk, row_chunk_log2;   // OM == 2, chunked writer: rows per shared-memory image (power of two; 0 = per-row pieces)
     int row_early;                   // OM == 2, fp32, odd N, 16-byte aligned obs: rows leave as aligned bulk pieces, the
                                      // static 2/3 before the physics and the dynamic 1/3 before the reward pass
     int fast_pairs;                  // tile kernel: packed pair loops of fg_pairs.cuh (N >= 32; fp32 hd uniform only)
@@ -199,7 +200,9 @@ __global__ void __launch_bounds__(kBlock, (OM == 3 && SCN == kScnBasic) ? 5 : (O
     // their squared norms, centred new positions and norms, centred ideal shape.
     const int NP = (N + 31) & ~31;
     const int NB = a.row_nbuf;
-    float* f_base = reinterpret_cast<float*>(s_rt_dyn + (OM == 2 ? NB * rt_dyn * (kBlock / 32) : 0));
+    float* f_base = (OM == 2 && a.row_chunk)
+        ? reinterpret_cast<float*>(s_rt_img + ((a.row_chunk * a.IPR + 3) & ~1))
+        : reinterpret_cast<float*>(s_rt_dyn + (OM == 2 ? NB * rt_dyn * (kBlock / 32) : 0));
     // Partner data as RECORDS of four partners (one address register + immediate offsets in the pair loops):
     // f_ro [EPC][NP/4] x {x[4], y[4], |p|^2[4]} of the old positions (contact filter),
     // f_rn [EPC][NP/4] x {cx[4], cy[4], |c|^2[4], sx[4], sy[4]} centred new positions and centred ideal shape.
@@ -289,7 +292,7 @@ __global__ void __launch_bounds__(kBlock, (OM == 3 && SCN == kScnBasic) ? 5 : (O
                 s_s[t] = S0;
                 if constexpr (FP) { RN(le, i, 3) = (float)S0.x; RN(le, i, 4) = (float)S0.y; }
                 if constexpr (OM == 2) {
-                    if (a.row_early) {        // static row images [comm zeros (N-1) | ideal_shape (N) | ideal_vel], both phases
+                    if (a.row_early && !a.row_chunk) {   // static row images [comm zeros (N-1) | ideal_shape (N) | ideal_vel], both phases
                         R2* im0 = s_rt_img + (size_t)le * 2 * rt_img;
                         R2* im1 = im0 + rt_img;
                         im0[N - 1 + i] = S0; im1[N - 1 + i] = S0;
@@ -307,7 +310,7 @@ __global__ void __launch_bounds__(kBlock, (OM == 3 && SCN == kScnBasic) ? 5 : (O
                 const R2 iv0 = a.ivel[e];
                 s_iv[le] = iv0;
                 if constexpr (OM == 2) {
-                    if (a.row_early) {
+                    if (a.row_early && !a.row_chunk) {
                         R2* im0 = s_rt_img + (size_t)le * 2 * rt_img;
                         im0[2 * N - 1] = iv0; im0[rt_img + 2 * N - 1] = iv0;
                     }
@@ -331,6 +334,51 @@ __global__ void __launch_bounds__(kBlock, (OM == 3 && SCN == kScnBasic) ? 5 : (O
     auto env_atomic_add = [&](int* dst, int val) {
         if (inA) { int m = __reduce_add_sync(maskA, val); if (m && lane_ == __ffs(maskA) - 1) atomicAdd(&dst[le], m); }
         if (inB) { int m = __reduce_add_sync(maskB, val); if (m && lane_ == __ffs(maskB) - 1) atomicAdd(&dst[le], m); }
+    };
+
+    // Chunked row writer (OM == 2, a.row_chunk = RC rows per chunk, a power of two): the CTA stages RC whole rows
+    // [p_vel | other_pos | comm zeros | ideal_shape | ideal_vel] (formation_hd_env.py:52-59) in ONE shared-memory image --
+    // 256 / RC consecutive threads share a row and walk its segments with plain strided loops -- and the chunk, RC consecutive rows of the [E,N,6N] tensor, leaves as ONE TMA bulk store of
+    // RC * 24N bytes (a lone 8-byte head / tail item by plain stores when the tile starts on an odd 8-byte slot).  The
+    // per-row writer above it spends ~200 warp instructions per row on bookkeeping and two small bulk stores
+    // (profiles/r02_hd_n81: 77 % issue-active, 656 B + 1296 B pieces); this one ~50 and 1 / RC of a 31 KB store.
+    auto rows_chunked = [&]() {
+        const int RC = a.row_chunk, NS = kBlock >> a.row_chunk_log2;
+        // consecutive threads <-> consecutive items of one row (conflict-free for every N; rows along the lanes instead
+        // put rows 3N items apart into the same banks for even N: 0.27 of the HBM peak at N = 64)
+        const int sl = t & (NS - 1), r = t / NS;
+        const int nrows = nvalid * N, IPR = a.IPR;
+        R2* out0 = a.obs + (size_t)tile0 * N * IPR;
+        R2* img = s_rt_img + (((uint32_t)(uintptr_t)out0 & 15u) ? 1 : 0);           // same 16-byte phase as the tile
+        const R2 zero2 = O::make((T)0, (T)0);
+        for (int c0 = 0; c0 < nrows; c0 += RC) {
+            const int nr = min(RC, nrows - c0);
+            if (c0 > 0) {                                   // the image is still being read by the previous chunk's copy
+                if (t == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                __syncthreads();
+            }
+            if (r < nr) {
+                const int R = c0 + r;
+                const int rle = (int)fastdiv((uint32_t)R, a.magic_n), ri = R - rle * N;
+                const R2* P = s_new + rle * N;
+                const R2* S = s_s + rle * N;
+                const R2 pi = P[ri];
+                R2* row = img + (size_t)r * IPR;
+                for (int m = sl; m < N - 1; m += NS) {
+                    const R2 pj = P[m + (m >= ri)];
+                    row[1 + m] = O::make(O::sub(pj.x, pi.x), O::sub(pj.y, pi.y));   // other_pos (formation_hd_env.py:55)
+                    row[N + m] = zero2;                                             // comm of the others (silent)
+                }
+                for (int m = sl; m < N; m += NS) row[2 * N - 1 + m] = S[m];         // ideal_shape.flatten()
+                if (sl == 0) { row[0] = s_v[R]; row[3 * N - 1] = s_iv[rle]; }       // p_vel, ideal_vel
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncthreads();
+            if (t < 32) {
+                row_piece_store<R2>(out0 + (size_t)c0 * IPR, img, (uint32_t)((size_t)nr * IPR * sizeof(R2)), t);
+                if (t == 0) asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+        }
     };
 
     for (int ts = 0; ts < a.n_steps; ++ts) {
@@ -562,6 +610,9 @@ __global__ void __launch_bounds__(kBlock, (OM == 3 && SCN == kScnBasic) ? 5 : (O
             __syncthreads();
         }
         if constexpr (OM == 2 && sizeof(R2) == 8) {
+            if (early && a.row_chunk) {
+                rows_chunked();                                              // drains under the reward pass
+            } else
             if (early) {
                 // Dynamic 1/3 of every row, one warp per row, BEFORE the reward pass so that the stores drain
                 // under it.  Pieces are 16-byte aligned on both ends: an even row sends [p_vel | other_pos | first
@@ -994,7 +1045,12 @@ __global__ void __launch_bounds__(kBlock, (OM == 3 && SCN == kScnBasic) ? 5 : (O
             __syncwarp();
         } else if (a.obs) {
             const int IPR = a.IPR;
-            if (OM == 2) {
+            if (OM == 2 && a.row_chunk) {
+                __syncthreads();                                                 // (reset) state of every env is in place
+                rows_chunked();
+                if (t == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                __syncthreads();
+            } else if (OM == 2) {
                 // Long hd rows, silent agents: 2/3 of every row ([comm zeros | ideal_shape | ideal_vel]) is the
                 // same for all rows of an env, so it is built ONCE per env in shared memory (in both
                 // 16-byte phases) and bulk-stored N times from there; only the N dynamic items of a row

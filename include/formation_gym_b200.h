@@ -167,7 +167,10 @@ const char* fg_last_error(void);
  *   no_fast_pairs 0/1      tile kernel: scalar pair loops instead of the packed ones (N >= 32)
  *   force_fast_pairs 0/1   tile kernel: packed pair loops also for 32 <= N < 64 with observations
  *   no_cells 0/1           packed pair loops: O(N^2) group filters instead of the hashed cell lists
- *   row_nbuf 1/2           long-row observation writer: staging buffers per warp
+ *   row_chunks 0/1/2       long-row observation writer: per-row pieces with the static 2/3 from a shared image /
+ *                          whole rows staged 4-16 at a time with one bulk store per chunk for N <= 80 (default) /
+ *                          chunks for every N
+ *   row_nbuf 1/2           per-row pieces: staging buffers per warp
  *   no_early_rows 0/1      long-row observation writer: rows leave after the reward pass
  *   no_tile_image 0/1      short-row observation writer: flat item loop instead of the tile image
  *   no_std_kernel 0/1      warp kernel: never the instantiation specialised for the standard configuration

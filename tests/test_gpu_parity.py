@@ -577,6 +577,34 @@ def test_tile_image_writer_equals_flat_writer(scen, E, N, kw, dtype):
         assert torch.equal(torch.nan_to_num(x), torch.nan_to_num(y))
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64], ids=["f32", "f64"])
+@pytest.mark.parametrize("E,N", [(7, 48), (10, 49), (9, 64), (5, 72), (4, 81), (3, 100), (2, 243), (2, 256)])
+def test_chunked_row_writer_equals_row_pieces(E, N, dtype):
+    """The two long-row observation writers of the tile kernel -- whole rows staged 4-16 at a time, one bulk store
+    per chunk (row_chunks = 2: forced for every N) and per-row pieces with the static 2/3 from a shared image
+    (row_chunks = 0) -- write bit-identical rows, stepwise with auto-resets (early and late path) and in a rollout,
+    also into an observation buffer that starts on an odd 8-byte slot."""
+    outs = []
+    for mode in (0, 2):
+        with nat.options(row_chunks=mode):
+            env = BatchedFormationEnv("formation_hd_env", E, N, episode_length=3, seed=19, dtype=dtype)
+            big = torch.zeros(E * N * env.D + 4, dtype=dtype, device="cuda")
+            env.obs = big[2:2 + E * N * env.D].view(E, N, env.D)            # fp32: odd 8-byte slot of a 16-byte line
+            env._bufs = env._make_buffers()
+            env.reset()
+            env.pos.mul_(0.4)
+            res = []
+            for _ in range(5):
+                env.step_random()
+                res.append(env.obs.clone())
+            env.rollout_random(4)
+            res.append(env.obs.clone())
+            assert float(big[:2].abs().sum()) == 0.0 and float(big[-2:].abs().sum()) == 0.0   # nothing outside the buffer
+            outs.append(res)
+    for x, y in zip(*outs):
+        assert torch.equal(torch.nan_to_num(x), torch.nan_to_num(y))
+
+
 def test_misaligned_vector_buffers_are_rejected():
     """float2 / double2 access: a 4-byte-aligned obs pointer is an argument error, not a device fault."""
     from formation_gym import _native as nat
