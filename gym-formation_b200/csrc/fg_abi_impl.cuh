@@ -38,6 +38,8 @@ struct Switches {
     std::atomic<int> no_std_kernel{0};      // warp kernel: never the STD instantiation (standard configuration, flags compiled out)
     std::atomic<int> l2_prefetch{1};        // warp kernel: prefetch.global.L2 of the state two spans ahead: 0 never, 1 auto, 2 always
     std::atomic<int> row_chunks{1};         // OM == 2: chunked row writer (RC whole rows per image, one bulk store per chunk)
+    std::atomic<int> row_chunk_max_log2{7}; // chunked row writer: at most 2^k rows per chunk
+    std::atomic<int> row_min_n{10};         // OM == 2 (bulk-store row writers) from this agent count up
     std::atomic<int> nvtx{1};               // NVTX ranges around the launches of every entry point
 };
 Switches& switches();                                         // defined in fg_abi_f32.cu
@@ -210,18 +212,19 @@ int fill_args(fg::KArgs<T>& a, const fg_params* p, const fg_buffers* b, int scen
         a.cell_inv_new = (float)(1.0 / (2.0 * std::sqrt((double)a.rthr2_hi) * (1.0 + 1.0 / 512.0)));
         a.cell_off = 0;
     }
-    a.row_tma = scenario == FG_SCENARIO_HD && p->silent && a.IPR >= 144 && b->obs &&
-                ((uintptr_t)b->obs % sizeof(R2)) == 0;
+    a.row_tma = scenario == FG_SCENARIO_HD && p->silent && b->obs && ((uintptr_t)b->obs % sizeof(R2)) == 0 &&
+                N >= fgabi::switches().row_min_n.load(std::memory_order_relaxed);
     a.row_nbuf = fgabi::switches().row_nbuf.load(std::memory_order_relaxed) == 1 ? 1 : 2;
     // chunked row writer (fg_kernels.cuh rows_chunked): the largest power-of-two row count <= 16 whose image fits 32 KB
-    // Measured (B200, fp32, step kernel alone, chunked vs per-row pieces): N = 48 0.76 vs 0.51 of the HBM peak, 56 0.77 vs
-    // 0.57, 63 0.82 vs 0.66, 64 0.74 vs 0.65, 72 0.73 vs 0.66, 75 / 81 equal, 100 0.82 vs 0.84, 128 0.85 vs 0.88,
-    // 243 0.79 vs 0.89 (the single image stalls the CTA while its 23 KB chunk is read): chunks up to N = 80
-    // (row_chunks = 2 forces them for every N).
+    // Measured (B200, fp32, step kernel alone, chunked vs the round-1 writers): N = 10 0.57 vs 0.45 of the HBM peak (tile
+    // image), 12 0.58 vs 0.34, 20 0.70 vs 0.29, 30 0.72 vs 0.40, 40 0.80 vs 0.42 (warp-per-row plain stores), 48 0.76 vs
+    // 0.51, 56 0.77 vs 0.57, 63 0.82 vs 0.66, 64 0.74 vs 0.65, 72 0.73 vs 0.66 (per-row pieces), 75 / 81 equal, 100 0.82 vs
+    // 0.84, 128 0.85 vs 0.88, 243 0.79 vs 0.89 (the single image stalls the CTA while its 23 KB chunk is read):
+    // chunks for 10 <= N <= 80 (row_chunks = 2 forces them for every N >= row_min_n).
     a.row_chunk = 0; a.row_chunk_log2 = 0;
     const int rc_mode = fgabi::switches().row_chunks.load(std::memory_order_relaxed);
     if (a.row_tma && (rc_mode == 2 || (rc_mode == 1 && N <= 80))) {
-        int lg = 4;
+        int lg = fgabi::switches().row_chunk_max_log2.load(std::memory_order_relaxed);
         while (lg > 1 && ((size_t)(1 << lg) * a.IPR + 2) * sizeof(R2) > 32 * 1024) --lg;
         if (((size_t)(1 << lg) * a.IPR + 2) * sizeof(R2) <= 48 * 1024) { a.row_chunk = 1 << lg; a.row_chunk_log2 = lg; }
     }

@@ -168,8 +168,10 @@ const char* fg_last_error(void);
  *   force_fast_pairs 0/1   tile kernel: packed pair loops also for 32 <= N < 64 with observations
  *   no_cells 0/1           packed pair loops: O(N^2) group filters instead of the hashed cell lists
  *   row_chunks 0/1/2       long-row observation writer: per-row pieces with the static 2/3 from a shared image /
- *                          whole rows staged 4-16 at a time with one bulk store per chunk for N <= 80 (default) /
+ *                          whole rows staged 4-128 at a time with one bulk store per chunk for N <= 80 (default) /
  *                          chunks for every N
+ *   row_min_n 3..256       bulk-store row writers (formation_hd_env, silent agents) from this agent count up (10)
+ *   row_chunk_max_log2 1..7  chunked writer: at most 2^k rows per chunk (7; the image is also capped at 32 KB)
  *   row_nbuf 1/2           per-row pieces: staging buffers per warp
  *   no_early_rows 0/1      long-row observation writer: rows leave after the reward pass
  *   no_tile_image 0/1      short-row observation writer: flat item loop instead of the tile image

@@ -578,15 +578,17 @@ def test_tile_image_writer_equals_flat_writer(scen, E, N, kw, dtype):
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.float64], ids=["f32", "f64"])
-@pytest.mark.parametrize("E,N", [(7, 48), (10, 49), (9, 64), (5, 72), (4, 81), (3, 100), (2, 243), (2, 256)])
+@pytest.mark.parametrize("E,N", [(300, 10), (70, 12), (40, 20), (33, 33), (20, 40), (7, 48), (10, 49), (9, 64), (5, 72),
+                                 (4, 81), (3, 100), (2, 243), (2, 256)])
 def test_chunked_row_writer_equals_row_pieces(E, N, dtype):
-    """The two long-row observation writers of the tile kernel -- whole rows staged 4-16 at a time, one bulk store
-    per chunk (row_chunks = 2: forced for every N) and per-row pieces with the static 2/3 from a shared image
-    (row_chunks = 0) -- write bit-identical rows, stepwise with auto-resets (early and late path) and in a rollout,
-    also into an observation buffer that starts on an odd 8-byte slot."""
+    """The chunked observation writer of the tile kernel -- whole rows staged 4-128 at a time, one bulk store per chunk
+    (row_chunks = 2, row_min_n = 3: forced for every N) -- against the round-1 writers (row_chunks = 0, row_min_n = 48:
+    per-row pieces with the static 2/3 from a shared image for N >= 48, warp-per-row plain stores / the tile image
+    below): bit-identical rows, stepwise with auto-resets (early and late path) and in a rollout, also into an
+    observation buffer that starts on an odd 8-byte slot."""
     outs = []
-    for mode in (0, 2):
-        with nat.options(row_chunks=mode):
+    for mode, min_n in ((0, 48), (2, 3)):
+        with nat.options(row_chunks=mode, row_min_n=min_n):
             env = BatchedFormationEnv("formation_hd_env", E, N, episode_length=3, seed=19, dtype=dtype)
             big = torch.zeros(E * N * env.D + 4, dtype=dtype, device="cuda")
             env.obs = big[2:2 + E * N * env.D].view(E, N, env.D)            # fp32: odd 8-byte slot of a 16-byte line
