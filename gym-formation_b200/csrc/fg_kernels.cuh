@@ -342,6 +342,8 @@ __global__ void __launch_bounds__(kBlock, (OM == 3 && SCN == kScnBasic) ? 5 : (O
     // RC * 24N bytes (a lone 8-byte head / tail item by plain stores when the tile starts on an odd 8-byte slot).  The
     // per-row writer above it spends ~200 warp instructions per row on bookkeeping and two small bulk stores
     // (profiles/r02_hd_n81: 77 % issue-active, 656 B + 1296 B pieces); this one ~50 and 1 / RC of a 31 KB store.
+    // (Two half-size images so that a chunk can be filled while the previous one is read were measured slower for every
+    // N: 0.61 vs 0.70 of the HBM peak at N = 20, 0.73 vs 0.79 at N = 40, 0.61 vs 0.74 at N = 64 -- the chunk size matters more.)
     auto rows_chunked = [&]() {
         const int RC = a.row_chunk, NS = kBlock >> a.row_chunk_log2;
         // consecutive threads <-> consecutive items of one row (conflict-free for every N; rows along the lanes instead
