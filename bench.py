@@ -446,6 +446,13 @@ def run_b200(a):
         return
 
     peak, peak_src = hbm_peak()
+    # One kernel per step (the default): the timed region of `value` IS a sequence of launches of the dominant kernel
+    # (fused step with the in-kernel random policy), so its average launch duration is elapsed / K of that region.
+    # Region 2 (the same kernel READING pre-sampled actions from 20 rotating buffers, as with an external policy) is
+    # reported beside it.  With --two-kernels the step holds two kernels and region 2 is the step kernel's time.
+    reading_ms = kernel_ms
+    if not a.two_kernels and a.graph_steps > 0:
+        kernel_ms = ms / K
     if strong:
         for row in strong:
             gbs = row.pop("_gbs_per_gpu")
@@ -475,9 +482,15 @@ def run_b200(a):
                 "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "kernel_ms": kernel_ms,
                 "algorithmic_bytes_per_env_step": bytes_per_env_step,
                 "share_of_step": kernel_ms / (ms / K),
-                "timing": "CUDA events around replays of a CUDA graph holding only fused-step launches, each on its "
-                          "own pre-sampled action buffer (region 1, which gives `value`, replays random-policy kernel "
-                          "+ fused step per step)"}
+                "reading_actions": {"kernel_ms": reading_ms, "frac": bytes_step / (reading_ms * 1e-3) / 1e9 / peak,
+                                    "what": "the same kernel reading pre-sampled actions (20 rotating action buffers, "
+                                            "CUDA graph of step launches only) instead of drawing them"},
+                "timing": ("CUDA events around the replays of the CUDA graph of the timed region: one launch of this kernel "
+                           "per step (random policy drawn and recorded inside it), so kernel_ms = elapsed / steps"
+                           if (not a.two_kernels and a.graph_steps > 0) else
+                           "CUDA events around replays of a CUDA graph holding only fused-step launches, each on its own "
+                           "pre-sampled action buffer (region 1, which gives `value`, runs random-policy kernel + fused "
+                           "step per step)")}
 
     cpu_baseline = None
     if world == 1 and not a.no_cpu_baseline:
