@@ -419,7 +419,7 @@ int launch_warp(const fg::KArgs<T>& a, cudaStream_t st) {
     if constexpr (std::is_same<T, float>::value) {
         // the standard product configuration has its own instantiation with these run-time tests compiled out
         // (fg_warp.cuh, STD); anything else takes the generic one
-        const bool std_cfg = a.collide && !a.has_vmax && a.mass_one && !(a.u_noise > (T)0) && a.n_steps == 1 &&
+        const bool std_cfg = a.collide && !a.has_vmax && a.mass_one && a.n_steps == 1 &&
                              a.step && a.done && a.indiv && a.ep_return && a.ep_coll && a.stats && !a.comm &&
                              !fgabi::switches().no_std_kernel.load(std::memory_order_relaxed);
         if (std_cfg)

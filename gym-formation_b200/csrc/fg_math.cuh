@@ -133,6 +133,18 @@ template <typename T> __device__ __forceinline__ void normal_pair(uint32_t a, ui
     *n0 = r * c;
     *n1 = r * s;
 }
+// fp32 build: the draws are noise on a 24-bit lattice -- parity with np.random.randn is statistical only -- so the hardware
+// approximations (MUFU.LG2 / MUFU.SIN / MUFU.COS: ~2^-21 absolute on [0, 2 pi)) replace the ~60-instruction IEEE logf /
+// sincosf sequences on the step path (u_noise = 0.1 at N = 9: 57.2 -> see DESIGN.md).  The fp64 build keeps libm.
+template <> __device__ __forceinline__ void normal_pair<float>(uint32_t a, uint32_t b, float* n0, float* n1) {
+    float u1 = ((float)(a >> 8) + 1.0f) * (1.0f / 16777216.0f);     // (0,1]
+    float u2 = (float)(b >> 8) * (1.0f / 16777216.0f);              // [0,1)
+    float r = sqrtf(-2.0f * __logf(u1));
+    float s, c;
+    __sincosf(6.283185307179586f * u2, &s, &c);
+    *n0 = r * c;
+    *n1 = r * s;
+}
 
 // q / d for q*d < 2^32 with magic = floor(2^32 / d) + 1 (exact; see DESIGN.md "index decode")
 __device__ __forceinline__ uint32_t fastdiv(uint32_t q, uint32_t magic) { return magic ? __umulhi(q, magic) : q; }

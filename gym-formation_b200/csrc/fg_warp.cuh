@@ -68,7 +68,7 @@ template <typename T, int N, bool WOBS> struct WarpLayout {
 // [p_vel, p_pos, l_k - p, p_j - p, comm] (basic_formation_env.py:29-41; also 3N items when L == N).
 //
 // STD (fp32 only): the standard product configuration, asserted by the host before it picks this instantiation --
-// agents collide, unit mass, no motor noise, no max_speed, one step per launch, the step / done / indiv / ep_return /
+// agents collide, unit mass, no max_speed, one step per launch, the step / done / indiv / ep_return /
 // ep_collisions / stats buffers present and no comm buffer (silent agents: c == 0).  Each of these is otherwise a
 // warp-uniform run-time test (constant load + compare + branch, plus a reconvergence pair inside divergent code):
 // at N = 3 such tests were a fifth of the 61 instructions per env-step (profiles/r02b_warp3: ISETP 11.6 %, BRA 7.3 %,
@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(32 * WarpLayout<T, N, WOBS>::MAXW, WarpLayout<
     constexpr unsigned FULL = 0xffffffffu;
     extern __shared__ __align__(128) unsigned char smem_raw[];
 
-    const bool f_collide = STD ? true : (a.collide != 0), f_noise = STD ? false : (a.u_noise > (T)0);
+    const bool f_collide = STD ? true : (a.collide != 0), f_noise = a.u_noise > (T)0;   // (motor noise stays a run-time flag)
     const bool f_vmax = STD ? false : (a.has_vmax != 0), f_mass1 = STD ? true : (a.mass_one != 0);
     const bool has_step = STD ? true : (a.step != nullptr), has_done = STD ? true : (a.done != nullptr);
     const bool has_indiv = STD ? true : (a.indiv != nullptr), has_epr = STD ? true : (a.ep_return != nullptr);

@@ -1,5 +1,5 @@
 """Quick timing of the fused step kernel alone (CUDA graph of 5 steps) for a list of configs.
-Usage: python scripts/quick_cfg.py "scen N E [obs] [opt=val,...]" ..."""
+Usage: python scripts/quick_cfg.py "scen N E [obs] [opt=val,...|-] [envkw=val,...]" ..."""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "gym-formation_b200"))
@@ -12,9 +12,10 @@ for cfg in sys.argv[1:]:
     f = cfg.split()
     scen, N, E = f[0], int(f[1]), int(f[2])
     obs = (f[3] != "0") if len(f) > 3 else True
-    opts = dict((kv.split("=")[0], int(kv.split("=")[1])) for kv in f[4].split(",")) if len(f) > 4 else {}
+    opts = dict((kv.split("=")[0], int(kv.split("=")[1])) for kv in f[4].split(",")) if len(f) > 4 and f[4] != "-" else {}
+    envkw = dict((kv.split("=")[0], float(kv.split("=")[1])) for kv in f[5].split(",")) if len(f) > 5 else {}
     with nat.options(**opts):
-        env = formation_gym.make_batched_env(scen, E, N, 25, write_obs=obs, seed=1)
+        env = formation_gym.make_batched_env(scen, E, N, 25, write_obs=obs, seed=1, **envkw)
         env.reset()
         env.sample_actions()
         g = env.capture_steps(5, policy=lambda e_: None)
