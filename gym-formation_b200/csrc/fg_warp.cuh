@@ -74,7 +74,9 @@ template <typename T, int N, bool WOBS> struct WarpLayout {
 // at N = 3 such tests were a fifth of the 61 instructions per env-step (profiles/r02b_warp3: ISETP 11.6 %, BRA 7.3 %,
 // LDCU 6.4 %, BSSY/BSYNC 7 % of all warp instructions).
 template <typename T, int N, bool WOBS, int SCN = kScnHD, bool STD = false>
-__global__ void __launch_bounds__(32 * WarpLayout<T, N, WOBS>::MAXW, WarpLayout<T, N, WOBS>::MINB) k_hd_warp(const __grid_constant__ KArgs<T> a) {
+// (basic_formation_env, N = 3: four 8-warp CTAs per SM -- 64 registers, no spills -- measured 80.9 vs 88.7 us per 1 M envs;
+// the hd instantiation of the same N loses with them: 89.2 vs 82.0 us)
+__global__ void __launch_bounds__(32 * WarpLayout<T, N, WOBS>::MAXW, (SCN == kScnBasic && sizeof(T) == 4) ? 4 : WarpLayout<T, N, WOBS>::MINB) k_hd_warp(const __grid_constant__ KArgs<T> a) {
     static_assert(SCN == kScnHD || WarpLayout<T, N, WOBS>::LATE_FILL, "basic rows are written by the late fill");
     typedef Ops<T> O;
     typedef typename O::R2 R2;
