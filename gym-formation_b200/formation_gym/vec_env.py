@@ -113,6 +113,12 @@ class CudaVecEnv(object):
                 self._dyn_items = items
             self._row_items = items
             self._age = None                    # env steps since ALL envs were last reset together (None: unknown)
+            # What step_wait() / reset() hand out: READ-ONLY numpy views of the persistent pinned buffers.  The obs
+            # buffer is refreshed incrementally, so an in-place edit by the caller (e.g. `obs /= scale`) would survive
+            # in the part of a row that is not re-sent -- numpy refuses the write instead; copy to modify.
+            self._views = tuple(t.numpy() for t in (self._obs_h, self._rew_h, self._done_h, self._ind_h))
+            for v in self._views:
+                v.flags.writeable = False
 
     # ------------------------------------------------------------------ VecEnv interface
     @property
@@ -156,8 +162,8 @@ class CudaVecEnv(object):
         self.waiting = True
 
     def step_wait(self):
-        """-> (obs [E,N,D], rews [E,N,1], dones [E,N], infos); arrays are views of buffers that the next
-        step overwrites (copy them to keep them)."""
+        """-> (obs [E,N,D], rews [E,N,1], dones [E,N], infos); with ``to_numpy`` the arrays are READ-ONLY views of
+        pinned buffers that the next step refreshes (copy them to keep or to modify them)."""
         if not self.waiting:
             raise RuntimeError("step_wait called without step_async")
         self.waiting = False
@@ -165,8 +171,7 @@ class CudaVecEnv(object):
         self._pending = None
         if self.to_numpy:
             torch.cuda.current_stream(self.env.device).synchronize()
-            return (self._obs_h.numpy(), self._rew_h.numpy(), self._done_h.numpy(),
-                    InfoBatch(self._ind_h.numpy()))
+            return (self._views[0], self._views[1], self._views[2], InfoBatch(self._views[3]))
         return obs, rew, done, InfoBatch(info["individual_reward"])
 
     def step(self, actions):
@@ -223,7 +228,7 @@ class CudaVecEnv(object):
     def _obs_out(self, obs):
         if self.to_numpy:
             self._obs_h.copy_(obs)
-            return self._obs_h.numpy()
+            return self._views[0]
         return obs
 
 

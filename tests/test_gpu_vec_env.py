@@ -82,6 +82,7 @@ def test_vec_env_host_arrays_stay_byte_identical(scen, N, kw):
         act = rng.uniform(-1, 1, (E, N, env.act_dim)).astype(obs.dtype)
         obs, rews, dones, infos = venv.step(act)
         assert obs.tobytes() == env.obs.cpu().numpy().tobytes(), t
+        assert not obs.flags.writeable                     # incremental refresh: in-place edits are refused, not lost
         assert np.array_equal(rews, env.reward.cpu().numpy()) and np.array_equal(dones, env.done.cpu().numpy())
         if kw.get("auto_reset", True):
             assert bool(dones.all()) == (t % T == 0)
