@@ -280,7 +280,17 @@ def run_b200(a):
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
         sampler.start()
-        time.sleep(0.3)
+    # Untimed settle phase: ~0.3 s of the same steps so that the clock sampler has samples UNDER LOAD and the SM / memory
+    # clocks are at their steady state when the timed region starts (an idle 0.3 s wait here let the GPU drop to its
+    # idle clocks, and a 1 ms timed region -- 20 steps -- then ran its first steps while they ramped up again).
+    settle_steps, t_settle = 0, time.time()
+    while time.time() - t_settle < 0.3:
+        if graph is not None:
+            graph.replay(); settle_steps += chunk
+        else:
+            one_step(); settle_steps += 1
+        if settle_steps % (8 * chunk) == 0:
+            torch.cuda.synchronize()
     launches0 = env.launches
     barrier(); torch.cuda.synchronize()
     ev0.record()
@@ -521,7 +531,8 @@ def run_b200(a):
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": a.dtype, "data": "synthetic", "config": dict(workload_config(a, hi - lo, "gpu"), u_noise=a.u_noise),
+        "dtype": a.dtype, "data": "synthetic",
+        "config": dict(workload_config(a, hi - lo, "gpu"), u_noise=a.u_noise, clock_settle_steps_untimed=settle_steps),
         "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "clocks": clocks,
         "gpu_launches": launches, "episode_stats": ep, "strong_scaling": strong, "state_hash": state_hash,
         "also": also,
