@@ -194,7 +194,7 @@ int fill_args(fg::KArgs<T>& a, const fg_params* p, const fg_buffers* b, int scen
     // (measured: N = 243 270 us vs 353 us with plain stores; break-even near N = 50)
     {
         const fgabi::Switches& sw = fgabi::switches();                 // A/B switches for tests and profiling
-        // measured (scripts/cfg_time.py): without observations the packed loops win from N = 32 up (N = 243:
+        // measured (scripts/quick_cfg.py): without observations the packed loops win from N = 32 up (N = 243:
         // 93 -> 59 us per 1024 envs); with observations the kernel is bound by its obs writer and the extra
         // shared memory only pays for large N
         a.fast_pairs = N >= 32 && (!b->obs || N >= 64 || sw.force_fast_pairs.load(std::memory_order_relaxed)) &&
