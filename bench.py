@@ -751,6 +751,10 @@ def also_configs(formation_gym, torch, device, dtype, peak, a):
             g = env.capture_steps(5, policy=lambda env_: env_.bfs_actions(3))
             ms = _time_graph(torch, g, max(2, steps // 5)) / 5
             del g
+        elif mode == "bfs_fused":                                 # the controller inside the step kernel: one launch per step
+            g = env.capture_steps(5, fused_bfs=3)
+            ms = _time_graph(torch, g, max(2, steps // 5)) / 5
+            del g
         elif mode == "twokernels":                                # round-1 form: policy kernel + step kernel per step
             g = env.capture_steps(5)
             ms = _time_graph(torch, g, max(2, steps // 5)) / 5
@@ -768,7 +772,7 @@ def also_configs(formation_gym, torch, device, dtype, peak, a):
         row = {"config": name, "agent_steps_per_s": E * N / (ms * 1e-3), "ms_per_env_step": ms,
                "algorithmic_GBps": gbs}
         frac_keys(row, gbs, nbytes)
-        if mode in ("step", "bfs", "twokernels"):
+        if mode in ("step", "bfs", "bfs_fused", "twokernels"):
             # the fused step kernel alone (actions pre-sampled, CUDA graph of 5 launches: no launch gaps, no policy
             # kernel) -- the figure comparable with the headline's roofline.frac
             env.sample_actions()
@@ -805,6 +809,10 @@ def also_configs(formation_gym, torch, device, dtype, peak, a):
         ("hd N=3 E=1048576", "formation_hd_env", 3, 1048576, "step", 50, {}),
         ("hd N=9 E=131072, device controller get_action_BFS(ezpolicy) instead of the random policy",
          "formation_hd_env", 9, 131072, "bfs", 50, {}),
+        ("hd N=3 E=1048576 (test.py's default tree: 3 agents, one layer), device controller kernel + step kernel per step",
+         "formation_hd_env", 3, 1048576, "bfs", 30, {}),
+        ("hd N=3 E=1048576, device controller compiled INTO the step kernel (fg_step_policy: one launch per step)",
+         "formation_hd_env", 3, 1048576, "bfs_fused", 30, {}),
         ("configs[2] hd N=27 E=65536", "formation_hd_env", 27, 65536, "step", 50, {}),
         ("configs[3] hd N=243 E=1024 (one GPU's share of 8192)", "formation_hd_env", 243, 1024, "step", 30, {}),
         ("configs[3] hd N=243 E=8192 (all 8192 envs on one GPU)", "formation_hd_env", 243, 8192, "step", 10, {}),

@@ -358,7 +358,7 @@ int launch_obstacle(const fg::KArgs<T>& a, void* stream) {
 // observation-span image per warp).  Computed once per instantiation; all GPUs of a box are alike.
 struct WarpGeom { int ctas[4]; int best; int sms; };      // index: log2(w), w = 1, 2, 4, 8
 
-template <typename T, int N, bool WOBS, int SCN, bool STD>
+template <typename T, int N, bool WOBS, int SCN, bool STD, int POL = 0>
 const WarpGeom& warp_geom() {
     static const WarpGeom geom = [] {
         typedef fg::WarpLayout<T, N, WOBS> LY;
@@ -372,10 +372,10 @@ const WarpGeom& warp_geom() {
             const size_t smem = (size_t)w * LY::stride;
             g_.ctas[l] = 0;
             if (smem > 227 * 1024 || w > LY::MAXW) continue;
-            if (cudaFuncSetAttribute(fg::k_hd_warp<T, N, WOBS, SCN, STD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+            if (cudaFuncSetAttribute(fg::k_hd_warp<T, N, WOBS, SCN, STD, POL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)smem) != cudaSuccess) { cudaGetLastError(); continue; }
             int ctas = 0;
-            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, fg::k_hd_warp<T, N, WOBS, SCN, STD>, 32 * w, smem)
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, fg::k_hd_warp<T, N, WOBS, SCN, STD, POL>, 32 * w, smem)
                 != cudaSuccess) { cudaGetLastError(); continue; }
             g_.ctas[l] = ctas;
             if (ctas * w > best_res) { best_res = ctas * w; g_.best = l; }
@@ -383,24 +383,24 @@ const WarpGeom& warp_geom() {
         // the probing above left the limit at the SMALLEST footprint, and a limit below the launch's request makes
         // the launch fail (also under the 48 KB default): restore the default-or-larger value; launches raise it
         // further through ensure_dyn_smem when they need more than 48 KB
-        cudaFuncSetAttribute(fg::k_hd_warp<T, N, WOBS, SCN, STD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 48 * 1024);
+        cudaFuncSetAttribute(fg::k_hd_warp<T, N, WOBS, SCN, STD, POL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 48 * 1024);
         cudaGetLastError();
         return g_;
     }();
     return geom;
 }
 
-template <typename T, int N, bool WOBS, int SCN, bool STD>
+template <typename T, int N, bool WOBS, int SCN, bool STD, int POL = 0>
 int launch_warp_n(const fg::KArgs<T>& a, cudaStream_t st) {
     typedef fg::WarpLayout<T, N, WOBS> LY;
-    const WarpGeom& gm = warp_geom<T, N, WOBS, SCN, STD>();
+    const WarpGeom& gm = warp_geom<T, N, WOBS, SCN, STD, POL>();
     const int spans = (a.E + LY::EPW - 1) / LY::EPW;
     int l = gm.best;
     while (l > 0 && (spans >> l) < 2 * gm.sms) --l;                // small batches: spread over the SMs
     if (gm.ctas[l] < 1) return fail(FG_ERR_CUDA, "k_hd_warp does not fit on this device%s");
     const int w = 1 << l;
     const size_t smem = (size_t)w * LY::stride;
-    cudaError_t err = ensure_dyn_smem<fg::k_hd_warp<T, N, WOBS, SCN, STD>>(smem);
+    cudaError_t err = ensure_dyn_smem<fg::k_hd_warp<T, N, WOBS, SCN, STD, POL>>(smem);
     if (err != cudaSuccess) return fail(FG_ERR_CUDA, "cudaFuncSetAttribute failed: %s", cudaGetErrorString(err));
     // persistent warps: at most one resident wave; each warp walks spans gw, gw + nwarps, ...
     int grid = (spans + w - 1) / w;
@@ -408,7 +408,7 @@ int launch_warp_n(const fg::KArgs<T>& a, cudaStream_t st) {
     wave *= std::max(1, fgabi::switches().waves.load(std::memory_order_relaxed));
     if (grid > wave) grid = wave;
     if ((grid * w) & 1) ++grid;                                    // even warp count (16-byte phase, fg_warp.cuh)
-    fg::k_hd_warp<T, N, WOBS, SCN, STD><<<grid, 32 * w, smem, st>>>(a);
+    fg::k_hd_warp<T, N, WOBS, SCN, STD, POL><<<grid, 32 * w, smem, st>>>(a);
     err = cudaGetLastError();
     if (err != cudaSuccess) return fail(FG_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(err));
     return FG_OK;
@@ -619,13 +619,14 @@ int policy_bfs_impl(const void* pos, const void* shape, const void* ivel, void* 
 #define FG_POLICY_CASE(NF_, LV_) case NF_ * 16 + LV_: fg::k_policy_bfs<T, NF_, LV_><<<grid, fg::kBlock, smem, st>>>(a); break;
         FG_POLICY_CASE(3, 1) FG_POLICY_CASE(3, 2) FG_POLICY_CASE(3, 3) FG_POLICY_CASE(3, 4) FG_POLICY_CASE(3, 5)
         FG_POLICY_CASE(2, 2) FG_POLICY_CASE(2, 3) FG_POLICY_CASE(2, 4) FG_POLICY_CASE(2, 5)
-        FG_POLICY_CASE(4, 1) FG_POLICY_CASE(4, 2)
+        FG_POLICY_CASE(4, 1) FG_POLICY_CASE(4, 2) FG_POLICY_CASE(5, 1) FG_POLICY_CASE(5, 2)
 #undef FG_POLICY_CASE
         default:
             switch (n) {                                            // compile-time fan-out for the usual group sizes
                 case 2: fg::k_policy_bfs<T, 2><<<grid, fg::kBlock, smem, st>>>(a); break;
                 case 3: fg::k_policy_bfs<T, 3><<<grid, fg::kBlock, smem, st>>>(a); break;
                 case 4: fg::k_policy_bfs<T, 4><<<grid, fg::kBlock, smem, st>>>(a); break;
+                case 5: fg::k_policy_bfs<T, 5><<<grid, fg::kBlock, smem, st>>>(a); break;
                 default: fg::k_policy_bfs<T, 0><<<grid, fg::kBlock, smem, st>>>(a); break;
             }
     }

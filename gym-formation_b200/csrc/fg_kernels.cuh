@@ -75,6 +75,7 @@ template <typename T> struct KArgs {
     uint32_t* tick_dev;              // (opt) [2]: device tick added to `tick`, arrival counter (CUDA graphs)
     const R2* cpos;                  // (opt) [E,N,2] World.cache_dists: positions the contact forces are computed from
     uint8_t* nan_flag;               // (opt) [E]: set to 1 (never cleared) when the env holds a non-finite position (Q9)
+    T pol_mult[8];                   // fused device controller (fg_warp.cuh, POL): log(M)/log(n) per BFS layer, top first
     WallT<T> walls[kMaxWalls];
 };
 

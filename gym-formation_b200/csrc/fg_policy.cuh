@@ -125,6 +125,70 @@ __device__ __forceinline__ typename Ops<T>::R2 ezpolicy_dev(const typename Ops<T
 template <int B, int E_> struct CPow { static constexpr int v = B * CPow<B, E_ - 1>::v; };
 template <int B> struct CPow<B, 0> { static constexpr int v = 1; };
 
+// One node of the BFS tree (formation_gym/__init__.py:61-79): leader `i` of a subgroup of `nxt` agents inside the
+// group that starts at agent `gb` (subgroup index `si` within the group) builds the n-agent layer observation from the
+// subgroup centroids, runs ezpolicy on it with the group's target velocity `tv` and scales by the layer number.
+// P, S: the env's positions and ideal shape (shared memory).  NXT_ > 0: compile-time subgroup size (loops unrolled).
+template <typename T, int NF, int NXT_>
+__device__ __forceinline__ typename Ops<T>::R2 policy_node(const typename Ops<T>::R2* P, const typename Ops<T>::R2* S,
+                                                           int i, int gb, int si, int n_rt, int nxt_rt,
+                                                           typename Ops<T>::R2 tv, T mult) {
+    typedef Ops<T> O;
+    typedef typename O::R2 R2;
+    constexpr int CAP = NF > 0 ? NF : kPolicyMaxFan;
+    constexpr bool CT = NXT_ > 0;
+    const int n = NF > 0 ? NF : n_rt;
+    const int nxt = CT ? NXT_ : nxt_rt;
+    const R2 pi = P[i];
+    R2 cur[CAP], tgt[CAP], others[CAP];
+#pragma unroll
+    for (int k = 0; k < CAP; ++k) {
+        if (k >= n) continue;
+        // centroid of subgroup k in my frame (:65-66) and of its target points (:70-71): np.mean sums
+        // the rows in order and divides by the count
+        T cx = 0, cy = 0, tx = 0, ty = 0;
+        const int b0 = gb + k * nxt;
+#pragma unroll CT ? 9 : 1
+        for (int b = b0; b < b0 + nxt; ++b) {
+            const R2 q2 = P[b];
+            const T rx = (b == i) ? (T)0 : O::sub(q2.x, pi.x);            // own slot is the inserted (0,0)
+            const T ry = (b == i) ? (T)0 : O::sub(q2.y, pi.y);
+            cx = O::add(cx, rx); cy = O::add(cy, ry);
+            const R2 sb = S[b];
+            tx = O::add(tx, sb.x); ty = O::add(ty, sb.y);
+        }
+        cur[k] = O::make(O::div_count(cx, nxt), O::div_count(cy, nxt));
+        tgt[k] = O::make(O::div_count(tx, nxt), O::div_count(ty, nxt));
+    }
+    R2 own = cur[0];                                                      // :67-68
+#pragma unroll
+    for (int k = 1; k < CAP; ++k) if (k < n && k == si) own = cur[k];
+#pragma unroll
+    for (int k = 0; k < CAP - 1; ++k) {                                   // np.delete(cur - cur[si], si, 0)
+        if (k < n - 1) {
+            const R2 c = (k < si) ? cur[k] : cur[k + 1];
+            others[k] = O::make(O::sub(c.x, own.x), O::sub(c.y, own.y));
+        }
+    }
+    R2 out = ezpolicy_dev<T, NF>(others, tgt, tv, n);                     // :76-79
+    return O::make(O::mul(out.x, mult), O::mul(out.y, mult));
+}
+
+// The chain of nodes above agent `i`, top layer first, for a compile-time tree N = NF^LV: at every layer the agent
+// evaluates the node of ITS subgroup's leader (the agents of a subgroup compute the same value redundantly instead of
+// one of them computing it and handing it down -- no exchange, no divergence), and the last layer's node is its own
+// action (:81-97).  Used by the warp-autonomous step kernel (fg_warp.cuh, POL), where lane <-> agent.
+template <typename T, int NF, int LV, int L = 0>
+__device__ __forceinline__ typename Ops<T>::R2 policy_chain(const typename Ops<T>::R2* P, const typename Ops<T>::R2* S,
+                                                            int i, typename Ops<T>::R2 tv, const T* mult) {
+    constexpr int M = CPow<NF, LV - L>::v, NXT = M / NF;
+    const int il = (i / NXT) * NXT;                                       // the leader of my subgroup in this layer (:61)
+    const int gb = (il / M) * M, si = (il - gb) / NXT;
+    const typename Ops<T>::R2 out = policy_node<T, NF, NXT>(P, S, il, gb, si, NF, NXT, tv, mult[L]);
+    if constexpr (L + 1 < LV) return policy_chain<T, NF, LV, L + 1>(P, S, i, out, mult);
+    else return out;
+}
+
 // One BFS layer for the envs of a CTA.  M, NXT > 0: compile-time group / subgroup sizes (loops unrolled, divisions by
 // constants); M == 0: run-time sizes from the argument block with fastdiv magics.
 template <typename T, int NF, int N_, int M_, int NXT_>
@@ -133,7 +197,6 @@ __device__ __forceinline__ void policy_layer(const PArgs<T>& a, int l, int nvali
                                              typename Ops<T>::R2* s_tv1) {
     typedef Ops<T> O;
     typedef typename O::R2 R2;
-    constexpr int CAP = NF > 0 ? NF : kPolicyMaxFan;
     constexpr bool CT = M_ > 0;
     const int N = CT ? N_ : a.N, n = NF > 0 ? NF : a.n;
     const int M = CT ? M_ : a.lev_M[l], nxt = CT ? NXT_ : a.lev_nxt[l];
@@ -148,39 +211,7 @@ __device__ __forceinline__ void policy_layer(const PArgs<T>& a, int l, int nvali
         const R2* S = s_s + qe * N;
         const int gb = CT ? (i / M) * M : (int)fastdiv((uint32_t)i, a.mg_M[l]) * M;      // first agent of my group
         const int si = CT ? (i - gb) / nxt : (int)fastdiv((uint32_t)(i - gb), a.mg_nxt[l]);   // my subgroup within the group
-        const R2 pi = P[i];
-        R2 cur[CAP], tgt[CAP], others[CAP];
-#pragma unroll
-        for (int k = 0; k < CAP; ++k) {
-            if (k >= n) continue;
-            // centroid of subgroup k in my frame (:65-66) and of its target points (:70-71): np.mean sums
-            // the rows in order and divides by the count
-            T cx = 0, cy = 0, tx = 0, ty = 0;
-            const int b0 = gb + k * nxt;
-#pragma unroll CT ? 9 : 1
-            for (int b = b0; b < b0 + nxt; ++b) {
-                const R2 q2 = P[b];
-                const T rx = (b == i) ? (T)0 : O::sub(q2.x, pi.x);            // own slot is the inserted (0,0)
-                const T ry = (b == i) ? (T)0 : O::sub(q2.y, pi.y);
-                cx = O::add(cx, rx); cy = O::add(cy, ry);
-                const R2 sb = S[b];
-                tx = O::add(tx, sb.x); ty = O::add(ty, sb.y);
-            }
-            cur[k] = O::make(O::div_count(cx, nxt), O::div_count(cy, nxt));
-            tgt[k] = O::make(O::div_count(tx, nxt), O::div_count(ty, nxt));
-        }
-        R2 own = cur[0];                                                      // :67-68
-#pragma unroll
-        for (int k = 1; k < CAP; ++k) if (k < n && k == si) own = cur[k];
-#pragma unroll
-        for (int k = 0; k < CAP - 1; ++k) {                                   // np.delete(cur - cur[si], si, 0)
-            if (k < n - 1) {
-                const R2 c = (k < si) ? cur[k] : cur[k + 1];
-                others[k] = O::make(O::sub(c.x, own.x), O::sub(c.y, own.y));
-            }
-        }
-        R2 out = ezpolicy_dev<T, NF>(others, tgt, s_tv0[qe * N + i], n);      // :76-79
-        out = O::make(O::mul(out.x, a.mult[l]), O::mul(out.y, a.mult[l]));
+        const R2 out = policy_node<T, NF, CT ? NXT_ : 0>(P, S, i, gb, si, n, nxt, s_tv0[qe * N + i], a.mult[l]);
         if (nxt == 1) a.act[((size_t)blockIdx.x * a.EPC + qe) * N + i] = out;              // :81-83
         else for (int b = 0; b < nxt; ++b) s_tv1[qe * N + i + b] = out;       // tar_vel of my subgroup (:84-97)
     }

@@ -25,8 +25,17 @@
 // tile kernel.  Reference citations are on the code below.
 #pragma once
 #include "fg_kernels.cuh"
+#include "fg_policy.cuh"
 
 namespace fg {
+
+// log_NF(N) when N is a power of NF, else 0 (the shapes get_action_BFS accepts, formation_gym/__init__.py:55-56)
+template <int N, int NF> struct PolLevels {
+    static constexpr int v = (NF >= 2 && N > 1 && N % NF == 0 && (N == NF || PolLevels<N / (NF >= 2 ? NF : 2), NF>::v > 0))
+                             ? 1 + PolLevels<N / (NF >= 2 ? NF : 2), NF>::v : 0;
+};
+template <int NF> struct PolLevels<1, NF> { static constexpr int v = 0; };
+template <int NF> struct PolLevels<0, NF> { static constexpr int v = 0; };
 
 // Per-warp shared-memory slice layout (bytes), shared by host (sizing) and device (carving).
 template <typename T, int N, bool WOBS> struct WarpLayout {
@@ -73,11 +82,19 @@ template <typename T, int N, bool WOBS> struct WarpLayout {
 // warp-uniform run-time test (constant load + compare + branch, plus a reconvergence pair inside divergent code):
 // at N = 3 such tests were a fifth of the 61 instructions per env-step (profiles/r02b_warp3: ISETP 11.6 %, BRA 7.3 %,
 // LDCU 6.4 %, BSSY/BSYNC 7 % of all warp instructions).
-template <typename T, int N, bool WOBS, int SCN = kScnHD, bool STD = false>
+//
+// POL > 0 (formation_hd_env, N = POL^k): the reference's demo controller get_action_BFS(ezpolicy, obs_n, POL)
+// (formation_gym/__init__.py:19-98; test.py:23) runs on the NEW state at the end of every step -- the state the
+// observations just returned describe, i.e. the reset state for an env whose episode ended -- and its actions are
+// written to the action buffer for the NEXT step (and carried in registers between the steps of a rollout).  The
+// positions, the ideal shape and ideal_vel are already on chip, so the controller costs its arithmetic only: no second
+// launch, no re-read of the state (fg_policy.cuh: policy_chain; each lane evaluates the nodes of its own leaders).
+template <typename T, int N, bool WOBS, int SCN = kScnHD, bool STD = false, int POL = 0>
 // (basic_formation_env, N = 3: four 8-warp CTAs per SM -- 64 registers, no spills -- measured 80.9 vs 88.7 us per 1 M envs;
 // the hd instantiation of the same N loses with them: 89.2 vs 82.0 us)
 __global__ void __launch_bounds__(32 * WarpLayout<T, N, WOBS>::MAXW, (SCN == kScnBasic && sizeof(T) == 4) ? 4 : WarpLayout<T, N, WOBS>::MINB) k_hd_warp(const __grid_constant__ KArgs<T> a) {
     static_assert(SCN == kScnHD || WarpLayout<T, N, WOBS>::LATE_FILL, "basic rows are written by the late fill");
+    static_assert(POL == 0 || (SCN == kScnHD && PolLevels<N, POL>::v > 0), "POL: formation_hd_env with N = POL^k agents");
     typedef Ops<T> O;
     typedef typename O::R2 R2;
     typedef typename O::Bits Bits;
@@ -548,6 +565,14 @@ __global__ void __launch_bounds__(32 * WarpLayout<T, N, WOBS>::MAXW, (SCN == kSc
                 }
             }
             bulk_pending = true;
+        }
+
+        // ====== device controller on the new state (formation_gym/__init__.py:49-98), under the bulk store ======
+        if constexpr (POL > 0) {
+            if (active) {
+                u = policy_chain<T, POL, PolLevels<N, POL>::v>(s_pnew + le * 2 * N, s_shp + le * N, i, iv, a.pol_mult);
+                if (ts == n_steps - 1) const_cast<R2*>(a.act)[g] = u;       // the next step's actions
+            }
         }
     }
     if (--spans_left == 0) break;

@@ -8,7 +8,7 @@ import os
 
 from . import _build
 
-FG_ABI_VERSION = 8
+FG_ABI_VERSION = 9
 FG_MAX_AGENTS = 256
 FG_MAX_LANDMARKS = 256
 FG_MAX_WALLS = 8
@@ -23,7 +23,7 @@ EXPORTS = [
     "fg_world_step", "fg_world_step_f64", "fg_obs_reward", "fg_obs_reward_f64",
     "fg_step_fused", "fg_step_fused_f64", "fg_reset", "fg_reset_f64",
     "fg_random_actions", "fg_random_actions_f64", "fg_fp32_probe", "fg_write_probe", "fg_policy_bfs", "fg_policy_bfs_f64",
-    "fg_obs_to_host", "fg_pair_distances", "fg_pair_distances_f64",
+    "fg_obs_to_host", "fg_pair_distances", "fg_pair_distances_f64", "fg_step_policy", "fg_step_policy_f64",
 ]
 
 
@@ -96,6 +96,8 @@ def load():
         getattr(lib, "fg_obs_reward" + sfx).argtypes = \
             [P(fg_params), P(fg_buffers), I, I, I, I, VP]
         getattr(lib, "fg_step_fused" + sfx).argtypes = \
+            [P(fg_params), P(fg_buffers), I, I, I, I, I, I, I, U64, U32, U32, VP]
+        getattr(lib, "fg_step_policy" + sfx).argtypes = \
             [P(fg_params), P(fg_buffers), I, I, I, I, I, I, I, U64, U32, U32, VP]
         getattr(lib, "fg_reset" + sfx).argtypes = \
             [P(fg_params), P(fg_buffers), I, I, I, I, VP, U64, U32, U32, VP]

@@ -162,6 +162,7 @@ class BatchedFormationEnv:
         self._tick_dev = torch.zeros(2, dtype=torch.int32, device=self.device)
         self._device_tick = False
         self._ext_bufs = None
+        self._bfs_primed = 0          # fan-out n while self.actions holds the controller's output for the current state (step_bfs)
         self._bufs = self._make_buffers()
 
     # ------------------------------------------------------------------ plumbing
@@ -245,6 +246,7 @@ class BatchedFormationEnv:
             m = torch.as_tensor(mask, device=self.device).to(torch.uint8).contiguous()
             if tuple(m.shape) != (self.E,):
                 raise ValueError("mask must have shape (E,)")
+        self._bfs_primed = 0
         with self._on_device():
             rc = self._fn("fg_reset")(C.byref(self.params), C.byref(self._bufs), self.scn, self.E, self.N,
                                       self.L, nat.ptr(m), self.seed_value, self._next_tick(),
@@ -271,6 +273,7 @@ class BatchedFormationEnv:
         """``World.step`` only (physics; no observation / reward / done)."""
         actions = self._check_actions(actions)
         b = self._make_buffers(act=actions)
+        self._bfs_primed = 0
         with self._on_device():
             rc = self._fn("fg_world_step")(C.byref(self.params), C.byref(b), self.E, self.N,
                                            self.seed_value, self._next_tick(1, True), self.env_offset,
@@ -340,6 +343,30 @@ class BatchedFormationEnv:
             self.launches += 1
         return out
 
+    def step_bfs(self, num_agents_per_layer=3, n_steps=1):
+        """The reference's demo loop body (test.py:23-25) -- ``act_n = get_action_BFS(ezpolicy, obs_n, n)`` then
+        ``env.step(act_n)`` -- for every env, ``n_steps`` times.  ``self.actions`` carries the controller's output
+        from one call to the next: the step runs on it, and the kernel refills it from the NEW state (the reset state
+        for envs whose episode just ended), so on return it holds the actions the controller gives for the returned
+        observations.  One launch per step where the warp-autonomous kernel has the controller compiled in
+        (``fg_step_policy``; N = 3 with 3 agents per layer, 4 / 8 with 2, 16 with 4), the step kernel
+        + the controller kernel otherwise -- same results.  The first call after anything else changed the state
+        (reset, step, load_state_dict, ...) computes the first actions with ``bfs_actions`` (one extra launch)."""
+        n = int(num_agents_per_layer)
+        if self.scn != nat.FG_SCENARIO_HD or not self.silent:
+            raise nat.NativeError("the hand-written controller is defined for formation_hd_env with silent agents")
+        if self._bfs_primed != n:
+            self.bfs_actions(n)
+        n_steps = int(n_steps)
+        with self._on_device():
+            rc = self._fn("fg_step_policy")(C.byref(self.params), C.byref(self._bufs), self.scn, self.E, self.N,
+                                            self.L, n_steps, n, int(self.auto_reset), self.seed_value,
+                                            self._next_tick(n_steps, True), self.env_offset, self._stream())
+            nat.check(rc, "fg_step_policy")
+            self.launches += 1                 # (calls; a configuration without a fused instantiation launches 2 per step)
+        self._bfs_primed = n
+        return self.obs, self.reward, self.done, {"individual_reward": self.indiv}
+
     def rollout_random(self, n_steps):
         """``n_steps`` random-policy steps in ONE launch with the state held on chip; obs / reward /
         done buffers hold the last step's values afterwards."""
@@ -347,6 +374,7 @@ class BatchedFormationEnv:
         return self.obs, self.reward, self.done, {"individual_reward": self.indiv}
 
     def _launch_fused(self, bufs, n_steps, random_actions):
+        self._bfs_primed = 0
         with self._on_device():
             rc = self._fn("fg_step_fused")(C.byref(self.params), C.byref(bufs), self.scn, self.E, self.N,
                                            self.L, n_steps, random_actions, int(self.auto_reset),
@@ -355,13 +383,15 @@ class BatchedFormationEnv:
             nat.check(rc, "fg_step_fused")
             self.launches += 1
 
-    def capture_steps(self, n_steps=1, policy=None, fused_random=False):
+    def capture_steps(self, n_steps=1, policy=None, fused_random=False, fused_bfs=0):
         """Capture ``n_steps`` x (policy, fused env step) into ONE CUDA graph and return it; call
         ``graph.replay()`` to run them.  ``policy=None`` is the random policy (test.py:20) written
         into ``self.actions``; otherwise ``policy(env)`` is called during capture and must enqueue,
         on the current stream, whatever fills ``self.actions`` from ``self.obs``.
         ``fused_random=True``: the random policy is drawn AND recorded into ``self.actions`` inside the
         step kernel (``step_random(record_actions=True)``): one launch per step, same results.
+        ``fused_bfs=n``: the reference's demo controller with n agents per layer inside the step kernel
+        (``step_bfs(n)``).
         Replays cost no host work per step, which is what small batches (launch-bound per step) need.
         Turns the device tick on."""
         self.use_device_tick(True)
@@ -370,6 +400,9 @@ class BatchedFormationEnv:
         side.wait_stream(torch.cuda.current_stream(self.device))
 
         def one():
+            if fused_bfs:
+                self.step_bfs(fused_bfs)
+                return
             if fused_random:
                 self._launch_fused(self._bufs, 1, 2)
                 return
@@ -455,6 +488,7 @@ class BatchedFormationEnv:
         return sd
 
     def load_state_dict(self, sd):
+        self._bfs_primed = 0
         for k, v in sd.items():
             if k == "rng":
                 self.seed_value, self._tick, self.env_offset = v["seed"], v["tick"], v["env_offset"]

@@ -42,7 +42,7 @@
 extern "C" {
 #endif
 
-#define FG_ABI_VERSION 8
+#define FG_ABI_VERSION 9
 #define FG_MAX_AGENTS 256      /* one CTA holds at least one whole env; 3^5 = 243 fits */
 #define FG_MAX_LANDMARKS 256
 #define FG_MAX_WALLS 8
@@ -262,6 +262,24 @@ int fg_policy_bfs(const void* pos, const void* ideal_shape, const void* ideal_ve
                   int num_agents_per_layer, void* stream);
 int fg_policy_bfs_f64(const void* pos, const void* ideal_shape, const void* ideal_vel, void* act, int E, int N,
                       int num_agents_per_layer, void* stream);
+
+/* The reference's demo loop in one call per step (test.py:14-28 without -r):
+ *     act_n = get_action_BFS(ezpolicy, obs_n, n);  obs_n, reward_n, done_n, _ = env.step(act_n)
+ * with the state on the device: n_steps times { fg_step_fused on b->act (random_actions = 0); b->act =
+ * fg_policy_bfs(new state) }.  b->act [E,N,2] is read AND written: on entry it holds the actions of the first step
+ * (fg_policy_bfs of the current state), on return those for the step after the last one -- computed from the state
+ * the returned observations describe, i.e. the reset state for an env whose episode just ended (auto_reset).
+ * formation_hd_env with silent agents only.  Where the warp-autonomous step kernel has an instantiation with the
+ * controller compiled in -- uniform agents, no walls, landmarks not tracked, (N, n) in {(3,3), (4,2), (8,2), (16,4)},
+ * the shapes for which one kernel was measured faster than two; fp32: the standard buffer set of fg_step_fused (step/done/indiv/ep_return/ep_collisions/stats
+ * present, no comm) -- a step is ONE launch and the controller never re-reads the state from HBM; everything else
+ * runs the two kernels above per step, with the same results (same device functions). */
+int fg_step_policy(const fg_params* p, const fg_buffers* b, int scenario, int E, int N, int L, int n_steps,
+                   int num_agents_per_layer, int auto_reset, uint64_t seed, uint32_t tick, uint32_t env_offset,
+                   void* stream);
+int fg_step_policy_f64(const fg_params* p, const fg_buffers* b, int scenario, int E, int N, int L, int n_steps,
+                       int num_agents_per_layer, int auto_reset, uint64_t seed, uint32_t tick, uint32_t env_offset,
+                       void* stream);
 
 /* Diagnostics, not on the step path: FP32 pipe probes used by bench.py to MEASURE the FP32 peak the
  * large-N step+reward kernel is graded against (BASELINE.json north_star: "% of FP32 peak at 243

@@ -38,7 +38,7 @@ def test_library_exports_every_declared_symbol():
     for s in syms:
         assert hasattr(lib, s), "missing export %s" % s
     assert sorted(_native.EXPORTS) == syms          # the binding covers exactly the header
-    assert _native.load().fg_abi_version() == _native.FG_ABI_VERSION == 8
+    assert _native.load().fg_abi_version() == _native.FG_ABI_VERSION == 9
 
 
 def test_ctypes_structs_match_c_layout():

@@ -98,3 +98,94 @@ def test_get_action_BFS_reads_every_observation_like_the_reference():
     assert np.abs(act - g["act_clean"]).max() <= 1e-12
     act = np.stack(formation_gym.get_action_BFS(formation_gym.ezpolicy, list(g["obs_noisy"]), n))
     assert np.abs(act - g["act_noisy"]).max() <= 1e-12
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# fg_step_policy: the demo loop body (test.py:23-25) in one call -- the controller compiled into the step kernel
+FUSED_SHAPES = [(3, 3), (4, 2), (8, 2), (16, 4), (9, 3), (27, 3), (25, 5)]   # the first four are one kernel per step
+
+
+def _pair(E, N, dtype, seed, **kw):
+    mk = lambda: BatchedFormationEnv("formation_hd_env", E, N, dtype=dtype, seed=seed, **kw)  # noqa: E731
+    a, b = mk(), mk()
+    a.reset(); b.reset()
+    return a, b
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64], ids=["f32", "f64"])
+@pytest.mark.parametrize("N,n", FUSED_SHAPES)
+def test_step_bfs_equals_policy_then_step(N, n, dtype):
+    """step_bfs (one launch per step) == bfs_actions + step (two launches), over episode ends: same device functions,
+    so the fp64 build is bit-identical; fp32 may differ by FMA contraction in the surrounding step code."""
+    E = 257                                                          # ragged last span
+    a, b = _pair(E, N, dtype, 11, episode_length=6, auto_reset=True)
+    for t in range(14):                                              # crosses two auto-resets
+        l0 = a.launches
+        oa, ra, da, ia = a.step_bfs(n)
+        assert a.launches - l0 == (2 if t == 0 else 1)               # first call primes the action buffer
+        ob, rb, db, ib = b.step(b.bfs_actions(n))
+        if dtype == torch.float64:
+            for x, y in ((oa, ob), (ra, rb), (a.pos, b.pos), (a.vel, b.vel), (ia["individual_reward"], ib["individual_reward"])):
+                assert torch.equal(x, y), t
+        else:
+            for x, y in ((oa, ob), (ra, rb), (a.pos, b.pos), (a.vel, b.vel)):
+                assert float((x - y).abs().max()) <= 1e-5 * max(1.0, float(y.abs().max())), t
+            b.load_state_dict(a.state_dict())                        # keep fp32 runs from drifting apart
+            b.obs.copy_(a.obs)
+        assert torch.equal(da, db)
+        # the action buffer now holds the controller's output for the NEW state
+        want = b.bfs_actions(n, out=torch.empty_like(b.actions))
+        if dtype == torch.float64:
+            assert torch.equal(a.actions, want), t
+        else:
+            bad = ((a.actions - want).abs().amax(dim=(1, 2)) > 1e-5).float().mean()
+            assert float(bad) <= 0.05, t                             # decision-boundary samples may flip in fp32
+
+
+def test_step_bfs_actions_match_oracle_after_step():
+    """The actions the fused kernel leaves in the buffer == the numpy restatement of get_action_BFS on the new state."""
+    E, N, n = 96, 9, 3
+    env = BatchedFormationEnv("formation_hd_env", E, N, dtype=torch.float64, seed=3, episode_length=4, auto_reset=True)
+    env.reset()
+    for t in range(6):
+        env.step_bfs(n)
+        want = po.bfs_actions_batch(env.pos.cpu().numpy(), env.ideal_shape.cpu().numpy(), env.ideal_vel.cpu().numpy(), n)
+        assert np.abs(env.actions.cpu().numpy() - want).max() <= 1e-11, t
+
+
+def test_step_bfs_rollout_and_unfused_shapes():
+    """n_steps > 1 in one call == single steps; a tree shape without a fused instantiation (N = 64, n = 8), tracked
+    landmarks and no observation buffer take the two-kernel form with the same results."""
+    a, b = _pair(130, 9, torch.float64, 5, episode_length=7, auto_reset=True)
+    a.step_bfs(3, n_steps=10)
+    for _ in range(10):
+        b.step_bfs(3)
+    for k in ("pos", "vel", "obs", "reward", "actions", "ideal_shape", "step_count"):
+        if hasattr(a, k):
+            assert torch.equal(getattr(a, k), getattr(b, k)), k
+    a, b = _pair(130, 9, torch.float32, 5, episode_length=7, auto_reset=True)
+    a.step_bfs(3, n_steps=10)
+    for _ in range(10):
+        b.step_bfs(3)
+    assert torch.equal(a.pos, b.pos) and torch.equal(a.obs, b.obs) and torch.equal(a.actions, b.actions)
+    for kw, N, n in ((dict(), 64, 8), (dict(track_landmarks=True), 9, 3), (dict(write_obs=False), 27, 3)):
+        a, b = _pair(33, N, torch.float64, 9, episode_length=5, auto_reset=True, **kw)
+        for t in range(7):
+            a.step_bfs(n)
+            b.step(b.bfs_actions(n))
+            assert torch.equal(a.pos, b.pos) and torch.equal(a.reward, b.reward), (kw, t)
+    with pytest.raises(Exception, match="power of num_agents_per_layer"):
+        BatchedFormationEnv("formation_hd_env", 4, 10, episode_length=25).step_bfs(3)
+    with pytest.raises(Exception, match="formation_hd_env"):
+        BatchedFormationEnv("basic_formation_env", 4, 3, episode_length=25).step_bfs(3)
+
+
+def test_step_bfs_graph_replay_matches_eager():
+    """CUDA graph of fused controller steps (device tick) == the same steps launched one by one."""
+    a, b = _pair(512, 9, torch.float32, 21, episode_length=9, auto_reset=True)
+    g = a.capture_steps(4, fused_bfs=3)                              # (runs one warm-up step itself)
+    g.replay(); g.replay()
+    torch.cuda.synchronize()
+    for _ in range(9):
+        b.step_bfs(3)
+    assert torch.equal(a.pos, b.pos) and torch.equal(a.actions, b.actions) and torch.equal(a.obs, b.obs)
