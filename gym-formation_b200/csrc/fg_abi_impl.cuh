@@ -72,6 +72,13 @@ cudaError_t ensure_dyn_smem(size_t smem) {
 }
 }
 
+namespace fgabi {
+// warp-autonomous kernel of the partial-observation scenarios (fg_lm_f32.cu / fg_lm_f64.cu): FG_OK / error code, or 1
+// when there is no instantiation for this (scenario, N, L, num_obs)
+int launch_lm_warp(const fg::KArgs<float>& a, int scenario, cudaStream_t st);
+int launch_lm_warp(const fg::KArgs<double>& a, int scenario, cudaStream_t st);
+}  // namespace fgabi
+
 namespace {
 
 using fgabi::g_err;
@@ -447,6 +454,17 @@ bool warp_path_ok(const fg::KArgs<T>& a, int scenario, const fg_params* p, const
     return !fgabi::switches().force_tile_kernel.load(std::memory_order_relaxed);   // A/B switch for tests and profiling
 }
 
+// formation_hd_partial_env / formation_hd_partial_range_env on the warp-autonomous kernel (fg_warp_lm.cuh)
+template <typename T>
+bool lm_warp_ok(const fg::KArgs<T>& a, int scenario, const fg_params* p, const fg_buffers* b) {
+    if (scenario != FG_SCENARIO_HD_PARTIAL && scenario != FG_SCENARIO_HD_PARTIAL_RANGE) return false;
+    if (a.N < 3 || a.N > 9 || !b->landmarks || !b->obs) return false;
+    if (p->agent_mass || p->agent_size_arr || p->agent_accel || p->agent_max_speed) return false;
+    if (p->n_walls != 0 || !p->silent || b->contact_pos) return false;
+    if (((uintptr_t)b->obs) % sizeof(typename fg::Ops<T>::R2)) return false;
+    return !fgabi::switches().force_tile_kernel.load(std::memory_order_relaxed);   // A/B switch for tests and profiling
+}
+
 template <typename T>
 int world_step_impl(const fg_params* p, const fg_buffers* b, int E, int N, uint64_t seed, uint32_t tick,
                     uint32_t env_offset, void* stream) {
@@ -527,6 +545,10 @@ int step_fused_impl(const fg_params* p, const fg_buffers* b, int scenario, int E
             case 32: return launch_warp<T, 32>(a, st);
             default: return launch_warp<T, 27>(a, st);
         }
+    }
+    if (lm_warp_ok<T>(a, scenario, p, b)) {
+        rc = fgabi::launch_lm_warp(a, scenario, (cudaStream_t)stream);
+        if (rc <= 0) return rc;                                     // (1: no instantiation -> tile kernel)
     }
     return launch<T, true, true>(a, scenario, p, stream);
 }

@@ -1,0 +1,6 @@
+// fg_lm_f64.cu -- fp64 instantiations of the partial-observation warp kernel (fg_lm.cuh, fg_warp_lm.cuh).
+#include "fg_lm.cuh"
+
+namespace fgabi {
+int launch_lm_warp(const fg::KArgs<double>& a, int scenario, cudaStream_t st) { return launch_lm_dispatch<double>(a, scenario, st); }
+}  // namespace fgabi

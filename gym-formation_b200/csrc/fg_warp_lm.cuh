@@ -1,0 +1,443 @@
+// fg_warp_lm.cuh -- warp-autonomous fused step kernel for the partial-observation scenarios (sm_100a):
+// formation_hd_partial_env (formation_gym/envs/formation_hd_partial_env.py:15-125) and
+// formation_hd_partial_range_env (formation_hd_partial_range_env.py:15-113) at the agent counts the reference's own
+// training recipes use (train/README.md:40,51,173: 4 and 5 agents; here N = 3 .. 9).
+//
+// Why it exists: these scenarios ran on the generic tile kernel, which at N = 4 / 5 is issue-bound (per-item index
+// arithmetic and six CTA barriers per step): 0.37-0.44 of the HBM peak (262144 envs) where the
+// formation_hd_env kernel of the same layout reaches 0.79-0.91.  This is that kernel's design (fg_warp.cuh: lane <->
+// agent, EPW = floor(32 / N) whole envs per warp, __syncwarp() only, persistent warps with a register prefetch of the
+// next span, the span's observation rows leaving the SM as ONE TMA bulk store) for worlds whose landmarks are
+// free-standing entities:
+//   * L landmarks per env, L != N in general (make_world's defaults: 5 for the partial scenario, 4 for the range
+//     one, whatever num_agents is -- formation_gym/__init__.py:11 passes only num_agents).  A span's landmarks are
+//     EPW * L consecutive items of lm[E,L,2]; lane q holds items q, q + 32, ...
+//   * reward = -max(dH(u, v), dH(v, u)) of the agents and the landmarks, each centred on its own mean
+//     (formation_hd_partial_env.py:67-75), minus one per collision; no velocity term.  Lane i owns row i (min over
+//     the landmarks) and the columns of landmarks i, i + N, ... (min over the agents).
+//   * row = [p_vel | landmark positions (absolute) | other_pos | comm zeros (N-1)]: other_pos are the NOBS agents after
+//     me in cyclic order (partial, :50-53) or all others clipped to +-obs_range (range, :49-52).
+// Restrictions (host: lm_warp_ok in fg_abi_impl.cuh): uniform agent constants, no walls, silent agents, an
+// observation buffer; anything else takes the tile kernel, which implements the same semantics (and is what the fp64
+// goldens of the unmodified reference pin; tests compare the two kernels and each against the oracle).
+#pragma once
+#include "fg_kernels.cuh"
+
+namespace fg {
+
+template <typename T, int N, int L, int SCN, int NOBS> struct LmLayout {
+    typedef typename Ops<T>::R2 R2;
+    typedef typename Ops<T>::Bits Bits;
+    static constexpr int EPW = 32 / N;                 // envs per warp
+    static constexpr int NA = EPW * N;                 // active lanes
+    static constexpr int NL = EPW * L;                 // landmarks of a span
+    static constexpr int NLR = (NL + 31) / 32;         // landmark items per lane
+    static constexpr int NREL = (SCN == kScnPartial) ? NOBS : N - 1;
+    static constexpr int IPR = 1 + L + NREL + (N - 1); // R2 items per observation row
+    static constexpr int MAXW = 8;
+    static constexpr size_t off_obs = 0;                                     // +16 B slack for the 8-byte phase
+    static constexpr size_t off_pold = off_obs + (size_t)NA * IPR * sizeof(R2) + 16;
+    static constexpr size_t off_pnew = off_pold + (size_t)NA * sizeof(R2);   // [EPW][2N]: p_0..p_{N-1} twice
+    static constexpr size_t off_cen = off_pnew + (size_t)2 * NA * sizeof(R2);
+    static constexpr size_t off_vel = off_cen + (size_t)NA * sizeof(R2);
+    static constexpr size_t off_lm = off_vel + (size_t)NA * sizeof(R2);      // [EPW][L] landmark positions
+    static constexpr size_t off_lmc = off_lm + (size_t)NL * sizeof(R2);      // [EPW][L] centred on their mean
+    static constexpr size_t off_mean = off_lmc + (size_t)NL * sizeof(R2);    // [EPW][2]: mean pos, mean landmark
+    static constexpr size_t off_max = off_mean + (size_t)2 * EPW * sizeof(R2);
+    static constexpr size_t off_col = off_max + (size_t)EPW * sizeof(Bits);
+    static constexpr size_t off_stat = (off_col + (size_t)EPW * sizeof(int) + 7) & ~(size_t)7;   // 4 doubles
+    static constexpr size_t raw = off_stat + 4 * sizeof(double);
+    static constexpr size_t stride = (raw + 15) & ~(size_t)15;
+    static_assert(SCN == kScnPartial || SCN == kScnRange, "landmark scenarios");
+    static_assert(N >= 2 && N <= 16 && L >= 1 && NLR <= 4, "small worlds only");
+    static_assert(SCN != kScnPartial || (NOBS >= 1 && NOBS <= N), "the cyclic neighbour window fits the doubled array");
+};
+
+template <typename T, int N, int L, int SCN, int NOBS>
+__global__ void __launch_bounds__(32 * LmLayout<T, N, L, SCN, NOBS>::MAXW, 3) k_lm_warp(const __grid_constant__ KArgs<T> a) {
+    typedef Ops<T> O;
+    typedef typename O::R2 R2;
+    typedef typename O::Bits Bits;
+    typedef LmLayout<T, N, L, SCN, NOBS> LY;
+    constexpr int EPW = LY::EPW, NA = LY::NA, NL = LY::NL, NLR = LY::NLR, IPR = LY::IPR, NREL = LY::NREL;
+    constexpr unsigned FULL = 0xffffffffu;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+
+    const bool f_collide = a.collide != 0, f_noise = a.u_noise > (T)0, f_vmax = a.has_vmax != 0, f_mass1 = a.mass_one != 0;
+    const bool has_step = a.step != nullptr, has_done = a.done != nullptr, has_indiv = a.indiv != nullptr;
+    const bool has_epr = a.ep_return != nullptr, has_epc = a.ep_coll != nullptr, has_stats = a.stats != nullptr;
+    const bool has_comm = a.comm != nullptr;
+    const int n_steps = a.n_steps;
+
+    const int lane = threadIdx.x & 31;
+    const int wib = threadIdx.x >> 5;
+    const int wpc = blockDim.x >> 5;
+    const int gw = blockIdx.x * wpc + wib;                                  // global warp index
+    const int nwarps = gridDim.x * wpc;                                     // EVEN (host): a warp's spans keep one 16-byte phase
+    const int nspans = (a.E + EPW - 1) / EPW;                               // one span = EPW consecutive envs
+    if (gw >= nspans) return;                                               // warp-uniform; no CTA barriers below
+    const uint32_t tick0 = a.tick + (a.tick_dev ? a.tick_dev[0] : 0u);
+    const int le = lane < NA ? lane / N : 0;
+    const int i = lane < NA ? lane - le * N : 0;
+    const unsigned envmask = ((1u << N) - 1u) << (le * N);                  // lanes of this env
+
+    unsigned char* wr = smem_raw + (size_t)wib * LY::stride;
+    R2* s_pold = reinterpret_cast<R2*>(wr + LY::off_pold);
+    R2* s_pnew = reinterpret_cast<R2*>(wr + LY::off_pnew);
+    R2* s_cen = reinterpret_cast<R2*>(wr + LY::off_cen);
+    R2* s_vel = reinterpret_cast<R2*>(wr + LY::off_vel);
+    R2* s_lm = reinterpret_cast<R2*>(wr + LY::off_lm);
+    R2* s_lmc = reinterpret_cast<R2*>(wr + LY::off_lmc);
+    R2* s_mean = reinterpret_cast<R2*>(wr + LY::off_mean);
+    Bits* s_max = reinterpret_cast<Bits*>(wr + LY::off_max);
+    int* s_col = reinterpret_cast<int*>(wr + LY::off_col);
+    double* s_stat = reinterpret_cast<double*>(wr + LY::off_stat);          // per-warp episode statistics (see fg_warp.cuh)
+    if (lane < 4) s_stat[lane] = 0.0;
+
+    const R2 zero = O::make((T)0, (T)0);
+    bool bulk_pending = false;
+
+    // software pipeline over the spans of this (persistent) warp: the next span's state is in flight while this
+    // one is computed
+    R2 p_n = zero, v_n = zero, u_n = zero;
+    R2 lm_n[NLR];
+    T epr_n = (T)0;
+    int stp_n = 0, epc_n = 0;
+    auto fetch = [&](int span) {
+        const int fe0 = span * EPW;
+        const int nv = min(EPW, a.E - fe0);
+        p_n = zero; v_n = zero; u_n = zero; stp_n = 0; epr_n = (T)0; epc_n = 0;
+        if (lane < nv * N) {                                                // coalesced: lane <-> consecutive agent
+            const size_t fa = (size_t)fe0 * N + lane;
+            p_n = a.pos[fa];
+            v_n = a.vel[fa];
+            if (!a.random_actions) u_n = a.act[fa];
+            if (has_step) stp_n = a.step[fe0 + le];
+            if (i == 0) {                                                   // running episode statistics of the env
+                if (has_epr) epr_n = a.ep_return[fe0 + le];
+                if (has_epc) epc_n = a.ep_coll[fe0 + le];
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < NLR; ++r) {
+            const int q = lane + 32 * r;
+            lm_n[r] = (q < nv * L) ? a.lm[(size_t)fe0 * L + q] : zero;
+        }
+    };
+    fetch(gw);
+
+  int spans_left = (nspans - gw + nwarps - 1) / nwarps;                     // >= 1
+  for (int span = gw; ; span += nwarps) {
+    const int env0 = span * EPW;
+    const int nval = min(EPW, a.E - env0);
+    const bool active = lane < nval * N;
+    const int e = env0 + le;
+    const size_t g = (size_t)env0 * N + lane;                               // global agent index
+    const uint32_t ge = a.env_offset + (uint32_t)e;                         // global env id (Philox counter)
+    R2* g_obs = a.obs + (size_t)env0 * N * IPR;
+    const uint32_t obs_bytes = (uint32_t)(nval * N * IPR) * (uint32_t)sizeof(R2);
+    const uint32_t obs_head = (uint32_t)((16u - ((uint32_t)(uintptr_t)g_obs & 15u)) & 15u);   // 0 or 8 (fp32), 0 (fp64)
+    R2* s_obs = reinterpret_cast<R2*>(wr + LY::off_obs + ((16u - obs_head) & 15u));
+
+    R2 p = p_n, v = v_n, u = u_n;
+    R2 lmr[NLR];
+#pragma unroll
+    for (int r = 0; r < NLR; ++r) lmr[r] = lm_n[r];
+    T epr = epr_n;
+    int stp = stp_n, epc = epc_n;
+    if (spans_left > 1) fetch(span + nwarps);
+    __syncwarp();                                                           // previous span's readers of s_lm are done
+#pragma unroll
+    for (int r = 0; r < NLR; ++r) if (lane + 32 * r < NL) s_lm[lane + 32 * r] = lmr[r];
+
+    for (int ts = 0; ts < n_steps; ++ts) {
+        if (lane < EPW) { s_max[lane] = 0; s_col[lane] = 0; }
+        if (lane < NA) s_pold[lane] = p;
+        __syncwarp();
+
+        // =============================== World.step (core.py:206-225) ===========================
+        if (active) {
+            if (a.random_actions) {                                         // test.py:20
+                U4 r = philox(a.seed, ge, (uint32_t)i, tick0 + (uint32_t)ts, kAction);
+                u = O::make(uniform_pm1<T>(r.x), uniform_pm1<T>(r.y));
+                if (a.random_actions == 2) const_cast<R2*>(a.act)[g] = u;   // recorded for the caller (replay buffer)
+            }
+            // _set_action: u *= sensitivity (environment.py:216-221); apply_action_force: F = gain * u + noise
+            // (core.py:232-236)
+            T Fx = O::mul(a.gain, O::mul(u.x, a.sens));
+            T Fy = O::mul(a.gain, O::mul(u.y, a.sens));
+            if (f_noise) {
+                U4 r = philox(a.seed, ge, (uint32_t)i, tick0 + (uint32_t)ts, kUNoise);
+                T n0, n1; normal_pair<T>(r.x, r.y, &n0, &n1);
+                Fx = O::add(Fx, O::mul(n0, a.u_noise));
+                Fy = O::add(Fy, O::mul(n1, a.u_noise));
+            }
+            // apply_environment_force (core.py:240-254): landmarks do not collide (make_world: collide = False), so
+            // the pairs are agent-agent.  Near-pair bitmask first, then the softplus contact force for the set
+            // bits in ascending j = the reference's accumulation order.
+            if (f_collide) {
+                const R2* ep = s_pold + le * N;
+                unsigned near = 0;
+#pragma unroll
+                for (int j = 0; j < N; ++j) {
+                    R2 q = ep[j];
+                    T dx = O::sub(p.x, q.x), dy = O::sub(p.y, q.y);
+                    T d2 = dx * dx + dy * dy;
+                    near |= (!(d2 >= a.cut2)) ? (1u << j) : 0u;             // !(>=) keeps NaN pairs
+                }
+                near &= ~(1u << i);
+                const T dmin = O::add(a.size, a.size);                      // core.py:307
+                while (near) {
+                    const int j = __ffs(near) - 1;
+                    near &= near - 1;
+                    R2 q = ep[j];
+                    T dx = (j < i) ? O::sub(q.x, p.x) : O::sub(p.x, q.x);   // delta = p_a - p_b, a < b
+                    T dy = (j < i) ? O::sub(q.y, p.y) : O::sub(p.y, q.y);
+                    T fx, fy;
+                    contact_force<T>(dx, dy, dmin, a.margin, a.cforce, &fx, &fy);
+                    if (j < i) { Fx = O::add(-fx, Fx); Fy = O::add(-fy, Fy); }   // equal masses: ratio 1
+                    else       { Fx = O::add(fx, Fx);  Fy = O::add(fy, Fy); }
+                }
+            }
+            // integrate_state (core.py:264-277)
+            v.x = O::mul(v.x, a.keep); v.y = O::mul(v.y, a.keep);
+            T ax = f_mass1 ? Fx : O::div(Fx, a.mass);
+            T ay = f_mass1 ? Fy : O::div(Fy, a.mass);
+            v.x = O::add(v.x, O::mul(ax, a.dt));
+            v.y = O::add(v.y, O::mul(ay, a.dt));
+            if (f_vmax) {
+                T sp = O::sqrt_(O::sq2(v.x, v.y));
+                if (sp > a.vmax) {
+                    v.x = O::mul(O::div(v.x, sp), a.vmax);
+                    v.y = O::mul(O::div(v.y, sp), a.vmax);
+                }
+            }
+            p.x = O::add(p.x, O::mul(v.x, a.dt));
+            p.y = O::add(p.y, O::mul(v.y, a.dt));
+            s_pnew[le * 2 * N + i] = p;
+            s_pnew[le * 2 * N + N + i] = p;
+            s_vel[lane] = v;
+            if (ts == n_steps - 1) {
+                a.pos[g] = p; a.vel[g] = v;
+                if (has_comm) a.comm[g] = zero;                             // update_agent_state: silent -> c = 0
+            }
+        }
+        // any non-finite position in an env makes its centroid, hence the whole shape term, NaN
+        const bool bad = !(fabs(p.x) < (T)INFINITY) || !(fabs(p.y) < (T)INFINITY);
+        const bool env_bad = (__ballot_sync(FULL, active && bad) & envmask) != 0u;
+        __syncwarp();
+
+        // ============ Scenario.reward on the NEW state (formation_hd_partial_env.py:67-87; Q16) ============
+        // u - mean(u), v - mean(v): one lane per (env, {agents, landmarks}), summed in entity order like np.mean
+        if (lane < 2 * nval) {
+            const int qe = lane >> 1, which = lane & 1;
+            const R2* src = which ? (s_lm + qe * L) : (s_pnew + qe * 2 * N);
+            const int cnt = which ? L : N;
+            T sx = 0, sy = 0;
+            for (int j = 0; j < cnt; ++j) { R2 q = src[j]; sx = O::add(sx, q.x); sy = O::add(sy, q.y); }
+            s_mean[lane] = O::make(O::div(sx, (T)cnt), O::div(sy, (T)cnt));
+        }
+        __syncwarp();
+        const R2 mp = s_mean[2 * le];
+        const R2 C = O::make(O::sub(p.x, mp.x), O::sub(p.y, mp.y));         // centred agent shape
+        if (lane < NA) s_cen[lane] = C;
+#pragma unroll
+        for (int r = 0; r < NLR; ++r) {
+            const int q = lane + 32 * r;
+            if (q < nval * L) {
+                const R2 ml = s_mean[2 * (q / L) + 1];
+                const R2 l = s_lm[q];
+                s_lmc[q] = O::make(O::sub(l.x, ml.x), O::sub(l.y, ml.y));   // centred landmark shape
+            }
+        }
+        __syncwarp();
+
+        int col = 0;
+        if (active) {
+            const R2* eV = s_lmc + le * L;
+            const R2* eC = s_cen + le * N;
+            const R2* eP = s_pnew + le * 2 * N + i;                         // eP[k] = agent (i + k) mod N
+            T dmax = (T)INFINITY;
+#pragma unroll
+            for (int k = 0; k < L; ++k) {                                   // row i: min_k |C_i - V_k|^2
+                R2 Vk = eV[k];
+                dmax = fmin(dmax, O::sq2(O::sub(C.x, Vk.x), O::sub(C.y, Vk.y)));
+            }
+#pragma unroll
+            for (int k0 = 0; k0 < L; k0 += N) {                             // columns i, i + N, ...: min_j |C_j - V_k|^2
+                const int k = k0 + i;
+                if (k < L) {
+                    const R2 Vk = eV[k];
+                    T colmin = (T)INFINITY;
+#pragma unroll
+                    for (int j = 0; j < N; ++j) {
+                        R2 Cj = eC[j];
+                        colmin = fmin(colmin, O::sq2(O::sub(Cj.x, Vk.x), O::sub(Cj.y, Vk.y)));
+                    }
+                    dmax = fmax(dmax, colmin);
+                }
+            }
+            // is_collision with every other agent (:82-86,123-125): exact test only for candidates
+            unsigned hit = 0;
+#pragma unroll
+            for (int k = 1; k < N; ++k) {
+                R2 q = eP[k];
+                T dx = O::sub(q.x, p.x), dy = O::sub(q.y, p.y);
+                T d2 = dx * dx + dy * dy;
+                hit |= (d2 < a.rthr2_hi) ? (1u << k) : 0u;
+            }
+            while (f_collide && hit) {
+                const int k = __ffs(hit) - 1;
+                hit &= hit - 1;
+                R2 q = eP[k];
+                if (O::norm2(O::sub(q.x, p.x), O::sub(q.y, p.y)) < a.rthr) ++col;
+            }
+            atomicMax(&s_max[le], O::bits(dmax));                           // d2 >= 0: bit order == value order
+            if (col) atomicAdd(&s_col[le], col);
+        }
+        __syncwarp();
+
+        // ============ rewards, done, statistics (environment.py:126-138,172-177) ================
+        stp += 1;                                                           // environment.py:114
+        const bool dn = active && has_step && (stp >= a.world_length);
+        if (active) {
+            T base = -O::sqrt_(O::from_bits(s_max[le]));                    // -max(dH(u,v), dH(v,u)); no velocity term
+            if (env_bad) base = O::from_bits(~(Bits)0 >> 1);                // NaN, as the reference
+            T r = base;
+            for (int c = 0; c < col; ++c) r = O::sub(r, (T)1);              // rew -= 1 per collision
+            const int coltot = s_col[le];
+            // shared reward = sum_i r_i (environment.py:136): N*base - total collisions, in fp64
+            const double R = (double)N * (double)base - (double)coltot;
+            a.reward[g] = (T)R;
+            if (has_indiv) a.indiv[g] = r;
+            if (has_done) a.done[g] = (uint8_t)(has_step ? (stp >= a.world_length) : 0);
+            if (i == 0 && env_bad && a.nan_flag) a.nan_flag[e] = 1;         // the reference's failure mode (Q9), sticky
+            if (i == 0 && has_step) {
+                const T ret = epr + (T)R;                                   // epr == 0 when ep_return is not tracked
+                const int ec = epc + coltot;
+                epr = (!has_epr || (dn && a.auto_reset)) ? (T)0 : ret;
+                epc = (!has_epc || (dn && a.auto_reset)) ? 0 : ec;
+                if (has_epr) a.ep_return[e] = epr;
+                if (has_epc) a.ep_coll[e] = epc;
+                if (dn && has_stats) {
+                    atomicAdd(&s_stat[0], 1.0);
+                    atomicAdd(&s_stat[1], (double)ret);
+                    atomicAdd(&s_stat[2], (double)ret * (double)ret);
+                    atomicAdd(&s_stat[3], (double)ec);
+                }
+            }
+        }
+
+        // ======== VecEnv auto-reset (env_wrappers.py:14-18; reset_world formation_hd_partial_env.py:89-101)
+        if (a.auto_reset && __any_sync(FULL, dn)) {
+            const uint32_t tk = tick0 + (uint32_t)ts;
+            if (dn) {
+                U4 r = philox(a.seed, ge, (uint32_t)i, tk, kResetAgent);
+                p = O::make(uniform_pm1<T>(r.x), uniform_pm1<T>(r.y));
+                v = zero;
+                s_pnew[le * 2 * N + i] = p;
+                s_pnew[le * 2 * N + N + i] = p;
+                s_vel[lane] = v;
+                stp = 0;
+#pragma unroll
+                for (int k0 = 0; k0 < L; k0 += N) {                         // landmarks i, i + N, ... of my env
+                    const int k = k0 + i;
+                    if (k < L) {
+                        U4 q = philox(a.seed, ge, (uint32_t)k, tk, kResetLandmark);
+                        const R2 l = O::make(uniform_pm1<T>(q.x), uniform_pm1<T>(q.y));
+                        s_lm[le * L + k] = l;
+                        a.lm[(size_t)e * L + k] = l;
+                    }
+                }
+                if (ts == n_steps - 1) { a.pos[g] = p; a.vel[g] = v; }
+            }
+            __syncwarp();
+        }
+        if (active && i == 0 && has_step) a.step[e] = stp;
+
+        // ================= observation rows leave the SM as one bulk copy =======================
+        // Filled LAST, from the shared state, which for an env that was just reset already holds the RESET state
+        // (env_wrappers.py:16-17): one code path writes both kinds of observation, and the bulk copy of the
+        // previous span / step has had this whole step to finish reading the image.
+        {
+            if (bulk_pending) {
+                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                bulk_pending = false;
+                __syncwarp();
+            }
+            if (active) {
+                // [p_vel | landmark p_pos (L) | other_pos (NREL) | comm of the others (N-1 zeros)]
+                // (formation_hd_partial_env.py:40-65 / formation_hd_partial_range_env.py:40-54).  Own row per lane; an
+                // EVEN row stride would put "item k of every row" on 32 / gcd(2 IPR, 32) banks, so each lane then walks
+                // every row segment in an order rotated by its lane index (as fg_warp.cuh does for even N).
+                constexpr bool ROT = (IPR % 2) == 0;
+                R2* row = s_obs + lane * IPR;
+                const R2* eL = s_lm + le * L;
+                const R2* eP = s_pnew + le * 2 * N + i;                     // eP[k] = agent (i + k) mod N
+                const R2* eA = s_pnew + le * 2 * N;                         // eA[j] = agent j
+                row[0] = v;
+                const int rL = ROT ? lane % L : 0;
+#pragma unroll
+                for (int k = 0; k < L; ++k) {
+                    int kk = k + rL; kk -= (kk >= L) ? L : 0;
+                    row[1 + kk] = eL[kk];
+                }
+                const int rR = ROT ? lane % NREL : 0;
+#pragma unroll
+                for (int m = 0; m < NREL; ++m) {
+                    int mm = m + rR; mm -= (mm >= NREL) ? NREL : 0;
+                    if (SCN == kScnPartial) {                               // agents i+1 .. i+NOBS, cyclic (:50-53)
+                        R2 q = eP[1 + mm];
+                        row[1 + L + mm] = O::make(O::sub(q.x, p.x), O::sub(q.y, p.y));
+                    } else {                                                // all others, j != i ascending, clipped (:49-52)
+                        R2 q = eA[mm + (mm >= i ? 1 : 0)];
+                        T dx = O::sub(q.x, p.x), dy = O::sub(q.y, p.y);
+                        const T lo = -a.obs_range, hi = a.obs_range;        // np.clip keeps NaN
+                        dx = (dx < lo) ? lo : ((dx > hi) ? hi : dx);
+                        dy = (dy < lo) ? lo : ((dy > hi) ? hi : dy);
+                        row[1 + L + mm] = O::make(dx, dy);
+                    }
+                }
+                const int rC = ROT ? lane % (N - 1) : 0;
+#pragma unroll
+                for (int m = 0; m < N - 1; ++m) {
+                    int mm = m + rC; mm -= (mm >= N - 1) ? (N - 1) : 0;
+                    row[1 + L + NREL + mm] = zero;                          // comm of the others (silent)
+                }
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // generic-proxy writes -> async proxy
+            __syncwarp();
+            const uint32_t head = obs_head < obs_bytes ? obs_head : obs_bytes;
+            const uint32_t mid = (obs_bytes - head) & ~15u;
+            const uint32_t tail = obs_bytes - head - mid;                   // 0 or 8 (fp32)
+            if (lane == 0) {
+                if (mid) {
+                    uint64_t pol;                                           // write-once streaming output (fg_warp.cuh)
+                    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+                    asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;"
+                                 :: "l"(reinterpret_cast<unsigned char*>(g_obs) + head),
+                                    "r"(smem_u32(reinterpret_cast<unsigned char*>(s_obs) + head)), "r"(mid), "l"(pol)
+                                 : "memory");
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+            } else if (lane == 1) {
+                if (head) g_obs[0] = s_obs[0];
+            } else if (lane == 2) {
+                if (tail) {
+                    const uint32_t it = (head + mid) / (uint32_t)sizeof(R2);
+                    g_obs[it] = s_obs[it];
+                }
+            }
+            bulk_pending = true;
+        }
+    }
+    if (--spans_left == 0) break;
+  }  // spans
+    // the shared-memory image must outlive the bulk copy's reads
+    if (bulk_pending && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    __syncwarp();
+    if (has_stats && lane < 4 && s_stat[0] != 0.0) atomicAdd(&a.stats[lane], s_stat[lane]);
+    tick_arrive(a.tick_dev, (unsigned)min(nwarps, nspans), n_steps, lane == 0);
+}
+
+}  // namespace fg
