@@ -40,8 +40,8 @@ template <typename T, int N, int L, int SCN, int NOBS> struct LmLayout {
     static constexpr size_t off_pnew = off_pold + (size_t)NA * sizeof(R2);   // [EPW][2N]: p_0..p_{N-1} twice
     static constexpr size_t off_cen = off_pnew + (size_t)2 * NA * sizeof(R2);
     static constexpr size_t off_vel = off_cen + (size_t)NA * sizeof(R2);
-    static constexpr size_t off_lm = off_vel + (size_t)NA * sizeof(R2);      // [EPW][L] landmark positions
-    static constexpr size_t off_lmc = off_lm + (size_t)NL * sizeof(R2);      // [EPW][L] centred on their mean
+    static constexpr size_t off_lm = off_vel + (size_t)NA * sizeof(R2);      // 2 x [EPW][L] landmark positions (this span, next span)
+    static constexpr size_t off_lmc = off_lm + (size_t)2 * NL * sizeof(R2);  // [EPW][L] centred on their mean
     static constexpr size_t off_mean = off_lmc + (size_t)NL * sizeof(R2);    // [EPW][2]: mean pos, mean landmark
     static constexpr size_t off_max = off_mean + (size_t)2 * EPW * sizeof(R2);
     static constexpr size_t off_col = off_max + (size_t)EPW * sizeof(Bits);
@@ -53,7 +53,11 @@ template <typename T, int N, int L, int SCN, int NOBS> struct LmLayout {
     static_assert(SCN != kScnPartial || (NOBS >= 1 && NOBS <= N), "the cyclic neighbour window fits the doubled array");
 };
 
-template <typename T, int N, int L, int SCN, int NOBS>
+// STD: the standard product configuration, asserted by the host before it picks this instantiation (agents collide,
+// unit mass, no max_speed, one step per launch, step / done / indiv / ep_return / ep_collisions / stats present, no comm
+// buffer): the warp-uniform run-time tests of these are compiled out, as in fg_warp.cuh.  The fp32 build has only
+// this instantiation (anything else takes the tile kernel), the fp64 build only the generic one.
+template <typename T, int N, int L, int SCN, int NOBS, bool STD>
 __global__ void __launch_bounds__(32 * LmLayout<T, N, L, SCN, NOBS>::MAXW, 3) k_lm_warp(const __grid_constant__ KArgs<T> a) {
     typedef Ops<T> O;
     typedef typename O::R2 R2;
@@ -63,11 +67,13 @@ __global__ void __launch_bounds__(32 * LmLayout<T, N, L, SCN, NOBS>::MAXW, 3) k_
     constexpr unsigned FULL = 0xffffffffu;
     extern __shared__ __align__(128) unsigned char smem_raw[];
 
-    const bool f_collide = a.collide != 0, f_noise = a.u_noise > (T)0, f_vmax = a.has_vmax != 0, f_mass1 = a.mass_one != 0;
-    const bool has_step = a.step != nullptr, has_done = a.done != nullptr, has_indiv = a.indiv != nullptr;
-    const bool has_epr = a.ep_return != nullptr, has_epc = a.ep_coll != nullptr, has_stats = a.stats != nullptr;
-    const bool has_comm = a.comm != nullptr;
-    const int n_steps = a.n_steps;
+    const bool f_collide = STD ? true : (a.collide != 0), f_noise = a.u_noise > (T)0;   // (motor noise stays a run-time flag)
+    const bool f_vmax = STD ? false : (a.has_vmax != 0), f_mass1 = STD ? true : (a.mass_one != 0);
+    const bool has_step = STD ? true : (a.step != nullptr), has_done = STD ? true : (a.done != nullptr);
+    const bool has_indiv = STD ? true : (a.indiv != nullptr), has_epr = STD ? true : (a.ep_return != nullptr);
+    const bool has_epc = STD ? true : (a.ep_coll != nullptr), has_stats = STD ? true : (a.stats != nullptr);
+    const bool has_comm = STD ? false : (a.comm != nullptr);
+    const int n_steps = STD ? 1 : a.n_steps;
 
     const int lane = threadIdx.x & 31;
     const int wib = threadIdx.x >> 5;
@@ -86,7 +92,7 @@ __global__ void __launch_bounds__(32 * LmLayout<T, N, L, SCN, NOBS>::MAXW, 3) k_
     R2* s_pnew = reinterpret_cast<R2*>(wr + LY::off_pnew);
     R2* s_cen = reinterpret_cast<R2*>(wr + LY::off_cen);
     R2* s_vel = reinterpret_cast<R2*>(wr + LY::off_vel);
-    R2* s_lm = reinterpret_cast<R2*>(wr + LY::off_lm);
+    R2* s_lm2 = reinterpret_cast<R2*>(wr + LY::off_lm);
     R2* s_lmc = reinterpret_cast<R2*>(wr + LY::off_lmc);
     R2* s_mean = reinterpret_cast<R2*>(wr + LY::off_mean);
     Bits* s_max = reinterpret_cast<Bits*>(wr + LY::off_max);
@@ -98,11 +104,14 @@ __global__ void __launch_bounds__(32 * LmLayout<T, N, L, SCN, NOBS>::MAXW, 3) k_
     bool bulk_pending = false;
 
     // software pipeline over the spans of this (persistent) warp: the next span's state is in flight while this
-    // one is computed
+    // one is computed -- the per-agent arrays in registers, the landmarks (up to two items per lane) through
+    // cp.async straight into the other half of a double buffer: holding them in registers too made ptxas spill
+    // under the 80-register bound, and with ~2 KB of L1 left beside the shared memory every spill reload is an L2
+    // round trip (N = 4: long-scoreboard stalls 4.2 per issue, issue active 50 %, profiles/r02c_lm4_before).
     R2 p_n = zero, v_n = zero, u_n = zero;
-    R2 lm_n[NLR];
     T epr_n = (T)0;
     int stp_n = 0, epc_n = 0;
+    int buf = 0;                                                            // half of s_lm2 the NEXT fetch fills
     auto fetch = [&](int span) {
         const int fe0 = span * EPW;
         const int nv = min(EPW, a.E - fe0);
@@ -121,8 +130,12 @@ __global__ void __launch_bounds__(32 * LmLayout<T, N, L, SCN, NOBS>::MAXW, 3) k_
 #pragma unroll
         for (int r = 0; r < NLR; ++r) {
             const int q = lane + 32 * r;
-            lm_n[r] = (q < nv * L) ? a.lm[(size_t)fe0 * L + q] : zero;
+            if (q < nv * L)
+                asm volatile("cp.async.ca.shared.global [%0], [%1], %2;"
+                             :: "r"(smem_u32(s_lm2 + buf * NL + q)), "l"(a.lm + (size_t)fe0 * L + q), "n"(sizeof(R2)) : "memory");
         }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        buf ^= 1;
     };
     fetch(gw);
 
@@ -140,15 +153,12 @@ __global__ void __launch_bounds__(32 * LmLayout<T, N, L, SCN, NOBS>::MAXW, 3) k_
     R2* s_obs = reinterpret_cast<R2*>(wr + LY::off_obs + ((16u - obs_head) & 15u));
 
     R2 p = p_n, v = v_n, u = u_n;
-    R2 lmr[NLR];
-#pragma unroll
-    for (int r = 0; r < NLR; ++r) lmr[r] = lm_n[r];
     T epr = epr_n;
     int stp = stp_n, epc = epc_n;
+    R2* s_lm = s_lm2 + (buf ^ 1) * NL;                                      // filled by the fetch of the previous iteration
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncwarp();                                                           // every lane's copies landed; readers of the other half are done
     if (spans_left > 1) fetch(span + nwarps);
-    __syncwarp();                                                           // previous span's readers of s_lm are done
-#pragma unroll
-    for (int r = 0; r < NLR; ++r) if (lane + 32 * r < NL) s_lm[lane + 32 * r] = lmr[r];
 
     for (int ts = 0; ts < n_steps; ++ts) {
         if (lane < EPW) { s_max[lane] = 0; s_col[lane] = 0; }
