@@ -41,9 +41,7 @@ template <typename T, int N, int L, int SCN, int NOBS> struct LmLayout {
     static constexpr size_t off_cen = off_pnew + (size_t)2 * NA * sizeof(R2);
     static constexpr size_t off_vel = off_cen + (size_t)NA * sizeof(R2);
     static constexpr size_t off_lm = off_vel + (size_t)NA * sizeof(R2);      // 2 x [EPW][L] landmark positions (this span, next span)
-    static constexpr size_t off_lmc = off_lm + (size_t)2 * NL * sizeof(R2);  // [EPW][L] centred on their mean
-    static constexpr size_t off_mean = off_lmc + (size_t)NL * sizeof(R2);    // [EPW][2]: mean pos, mean landmark
-    static constexpr size_t off_max = off_mean + (size_t)2 * EPW * sizeof(R2);
+    static constexpr size_t off_max = off_lm + (size_t)2 * NL * sizeof(R2);
     static constexpr size_t off_col = off_max + (size_t)EPW * sizeof(Bits);
     static constexpr size_t off_stat = (off_col + (size_t)EPW * sizeof(int) + 7) & ~(size_t)7;   // 4 doubles
     static constexpr size_t raw = off_stat + 4 * sizeof(double);
@@ -93,8 +91,6 @@ __global__ void __launch_bounds__(32 * LmLayout<T, N, L, SCN, NOBS>::MAXW, 3) k_
     R2* s_cen = reinterpret_cast<R2*>(wr + LY::off_cen);
     R2* s_vel = reinterpret_cast<R2*>(wr + LY::off_vel);
     R2* s_lm2 = reinterpret_cast<R2*>(wr + LY::off_lm);
-    R2* s_lmc = reinterpret_cast<R2*>(wr + LY::off_lmc);
-    R2* s_mean = reinterpret_cast<R2*>(wr + LY::off_mean);
     Bits* s_max = reinterpret_cast<Bits*>(wr + LY::off_max);
     int* s_col = reinterpret_cast<int*>(wr + LY::off_col);
     double* s_stat = reinterpret_cast<double*>(wr + LY::off_stat);          // per-warp episode statistics (see fg_warp.cuh)
@@ -102,6 +98,7 @@ __global__ void __launch_bounds__(32 * LmLayout<T, N, L, SCN, NOBS>::MAXW, 3) k_
 
     const R2 zero = O::make((T)0, (T)0);
     bool bulk_pending = false;
+    const R2* zeroed = nullptr;                                             // image whose comm slots hold zeros
 
     // software pipeline over the spans of this (persistent) warp: the next span's state is in flight while this
     // one is computed -- the per-agent arrays in registers, the landmarks (up to two items per lane) through
@@ -238,46 +235,42 @@ __global__ void __launch_bounds__(32 * LmLayout<T, N, L, SCN, NOBS>::MAXW, 3) k_
         __syncwarp();
 
         // ============ Scenario.reward on the NEW state (formation_hd_partial_env.py:67-87; Q16) ============
-        // u - mean(u), v - mean(v): one lane per (env, {agents, landmarks}), summed in entity order like np.mean
-        if (lane < 2 * nval) {
-            const int qe = lane >> 1, which = lane & 1;
-            const R2* src = which ? (s_lm + qe * L) : (s_pnew + qe * 2 * N);
-            const int cnt = which ? L : N;
-            T sx = 0, sy = 0;
-            for (int j = 0; j < cnt; ++j) { R2 q = src[j]; sx = O::add(sx, q.x); sy = O::add(sy, q.y); }
-            s_mean[lane] = O::make(O::div(sx, (T)cnt), O::div(sy, (T)cnt));
+        // u - mean(u), v - mean(v) (:70-74): np.mean sums the rows in entity order.  Every lane of an env computes both
+        // means itself -- the positions from its env's lanes by shuffle, the landmarks from shared memory (every lane
+        // of an env reads the same addresses: broadcasts) -- so nothing is staged and no lane waits for another.
+        // (One lane per (env, mean) writing to shared memory, as fg_warp.cuh does, cost 5-way bank conflicts on the
+        // strided reads and two more warp barriers: profiles/r02d_lm4.)
+        T sx = 0, sy = 0, lx = 0, ly = 0;
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+            sx = O::add(sx, __shfl_sync(FULL, p.x, le * N + j));
+            sy = O::add(sy, __shfl_sync(FULL, p.y, le * N + j));
         }
-        __syncwarp();
-        const R2 mp = s_mean[2 * le];
+        const R2* eL = s_lm + le * L;
+#pragma unroll
+        for (int k = 0; k < L; ++k) { R2 l = eL[k]; lx = O::add(lx, l.x); ly = O::add(ly, l.y); }
+        const R2 mp = O::make(O::div_count(sx, N), O::div_count(sy, N));    // fp64: true division, as np.mean
+        const R2 ml = O::make(O::div_count(lx, L), O::div_count(ly, L));
         const R2 C = O::make(O::sub(p.x, mp.x), O::sub(p.y, mp.y));         // centred agent shape
         if (lane < NA) s_cen[lane] = C;
-#pragma unroll
-        for (int r = 0; r < NLR; ++r) {
-            const int q = lane + 32 * r;
-            if (q < nval * L) {
-                const R2 ml = s_mean[2 * (q / L) + 1];
-                const R2 l = s_lm[q];
-                s_lmc[q] = O::make(O::sub(l.x, ml.x), O::sub(l.y, ml.y));   // centred landmark shape
-            }
-        }
         __syncwarp();
 
         int col = 0;
         if (active) {
-            const R2* eV = s_lmc + le * L;
             const R2* eC = s_cen + le * N;
             const R2* eP = s_pnew + le * 2 * N + i;                         // eP[k] = agent (i + k) mod N
             T dmax = (T)INFINITY;
 #pragma unroll
-            for (int k = 0; k < L; ++k) {                                   // row i: min_k |C_i - V_k|^2
-                R2 Vk = eV[k];
-                dmax = fmin(dmax, O::sq2(O::sub(C.x, Vk.x), O::sub(C.y, Vk.y)));
+            for (int k = 0; k < L; ++k) {                                   // row i: min_k |C_i - V_k|^2, V_k = l_k - mean(l)
+                const R2 l = eL[k];
+                dmax = fmin(dmax, O::sq2(O::sub(C.x, O::sub(l.x, ml.x)), O::sub(C.y, O::sub(l.y, ml.y))));
             }
 #pragma unroll
             for (int k0 = 0; k0 < L; k0 += N) {                             // columns i, i + N, ...: min_j |C_j - V_k|^2
                 const int k = k0 + i;
                 if (k < L) {
-                    const R2 Vk = eV[k];
+                    const R2 l = eL[k];
+                    const R2 Vk = O::make(O::sub(l.x, ml.x), O::sub(l.y, ml.y));
                     T colmin = (T)INFINITY;
 #pragma unroll
                     for (int j = 0; j < N; ++j) {
@@ -375,6 +368,15 @@ __global__ void __launch_bounds__(32 * LmLayout<T, N, L, SCN, NOBS>::MAXW, 3) k_
                 bulk_pending = false;
                 __syncwarp();
             }
+            // comm of the others (silent agents: zeros): nothing else writes these slots and the warp's spans all use the
+            // same image (one 16-byte phase per warp), so they are written once per launch, not once per span
+            if (zeroed != s_obs) {                                          // warp-uniform
+                if (lane < NA) {
+#pragma unroll
+                    for (int m = 0; m < N - 1; ++m) s_obs[lane * IPR + 1 + L + NREL + m] = zero;
+                }
+                zeroed = s_obs;
+            }
             if (active) {
                 // [p_vel | landmark p_pos (L) | other_pos (NREL) | comm of the others (N-1 zeros)]
                 // (formation_hd_partial_env.py:40-65 / formation_hd_partial_range_env.py:40-54).  Own row per lane; an
@@ -407,12 +409,6 @@ __global__ void __launch_bounds__(32 * LmLayout<T, N, L, SCN, NOBS>::MAXW, 3) k_
                         dy = (dy < lo) ? lo : ((dy > hi) ? hi : dy);
                         row[1 + L + mm] = O::make(dx, dy);
                     }
-                }
-                const int rC = ROT ? lane % (N - 1) : 0;
-#pragma unroll
-                for (int m = 0; m < N - 1; ++m) {
-                    int mm = m + rC; mm -= (mm >= N - 1) ? (N - 1) : 0;
-                    row[1 + L + NREL + mm] = zero;                          // comm of the others (silent)
                 }
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // generic-proxy writes -> async proxy
