@@ -457,7 +457,8 @@ bool warp_path_ok(const fg::KArgs<T>& a, int scenario, const fg_params* p, const
 // formation_hd_partial_env / formation_hd_partial_range_env on the warp-autonomous kernel (fg_warp_lm.cuh)
 template <typename T>
 bool lm_warp_ok(const fg::KArgs<T>& a, int scenario, const fg_params* p, const fg_buffers* b) {
-    if (scenario != FG_SCENARIO_HD_PARTIAL && scenario != FG_SCENARIO_HD_PARTIAL_RANGE) return false;
+    if (scenario != FG_SCENARIO_HD_PARTIAL && scenario != FG_SCENARIO_HD_PARTIAL_RANGE &&
+        scenario != FG_SCENARIO_HD_OBSTACLE) return false;
     if (a.N < 3 || a.N > 9 || !b->landmarks || !b->obs) return false;
     if (p->agent_mass || p->agent_size_arr || p->agent_accel || p->agent_max_speed) return false;
     if (p->n_walls != 0 || !p->silent || b->contact_pos) return false;
@@ -520,15 +521,20 @@ int step_fused_impl(const fg_params* p, const fg_buffers* b, int scenario, int E
     if (random_actions < 0 || random_actions > 2) return fail(FG_ERR_ARG, "fg_step_fused: random_actions must be 0, 1 or 2%s");
     if (random_actions && !p->silent)
         return fail(FG_ERR_ARG, "fg_step_fused: random_actions supports silent agents only%s");
-    if (random_actions == 2 && (!b->act || scenario == FG_SCENARIO_HD_OBSTACLE))
-        return fail(FG_ERR_ARG, "fg_step_fused: random_actions == 2 records the drawn actions in b->act (non-null; not "
-                                "available for formation_hd_obs_env)%s");
+    if (random_actions == 2 && !b->act)
+        return fail(FG_ERR_ARG, "fg_step_fused: random_actions == 2 records the drawn actions in b->act (non-null)%s");
     if (scenario == FG_SCENARIO_HD && (!b->ideal_shape || !b->ideal_vel))
         return fail(FG_ERR_ARG, "fg_step_fused(hd): ideal_shape/ideal_vel must be non-null%s");
     if (scenario != FG_SCENARIO_HD && !b->landmarks)
         return fail(FG_ERR_ARG, "fg_step_fused: landmarks must be non-null for this scenario%s");
     a.n_steps = n_steps; a.random_actions = random_actions; a.auto_reset = auto_reset;
-    if (scenario == FG_SCENARIO_HD_OBSTACLE) return launch_obstacle<T, true>(a, stream);
+    if (scenario == FG_SCENARIO_HD_OBSTACLE) {
+        if (lm_warp_ok<T>(a, scenario, p, b)) {
+            rc = fgabi::launch_lm_warp(a, scenario, (cudaStream_t)stream);
+            if (rc <= 0) return rc;                                 // (1: no instantiation -> tile kernel)
+        }
+        return launch_obstacle<T, true>(a, stream);
+    }
     if (warp_path_ok<T>(a, scenario, p, b)) {
         cudaStream_t st = (cudaStream_t)stream;
         if (scenario == FG_SCENARIO_BASIC) return launch_warp<T, 3, fg::kScnBasic>(a, st);

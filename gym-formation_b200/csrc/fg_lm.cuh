@@ -96,6 +96,19 @@ int launch_lm_dispatch(const fg::KArgs<T>& a, int scenario, cudaStream_t st) {
             default: return 1;
         }
     }
+    // formation_hd_obs_env: make_world's 4 goal landmarks + 3 obstacles (formation_hd_obs_env.py:14)
+    if (scenario == FG_SCENARIO_HD_OBSTACLE && a.L == 7 && a.n_obst == 3 && a.n_walls == 0) {
+        switch (a.N) {
+            case 3: return launch_lm_n<T, 3, 7, fg::kScnObstacle, 3>(a, st);
+            case 4: return launch_lm_n<T, 4, 7, fg::kScnObstacle, 3>(a, st);
+            case 5: return launch_lm_n<T, 5, 7, fg::kScnObstacle, 3>(a, st);
+            case 6: return launch_lm_n<T, 6, 7, fg::kScnObstacle, 3>(a, st);
+            case 7: return launch_lm_n<T, 7, 7, fg::kScnObstacle, 3>(a, st);
+            case 8: return launch_lm_n<T, 8, 7, fg::kScnObstacle, 3>(a, st);
+            case 9: return launch_lm_n<T, 9, 7, fg::kScnObstacle, 3>(a, st);
+            default: return 1;
+        }
+    }
     return 1;
 }
 

@@ -103,6 +103,7 @@ __global__ void __launch_bounds__(kBlock, 2) k_step_obst(const __grid_constant__
                 if (a.random_actions) {
                     U4 r = philox(a.seed, ge, (uint32_t)i, tick0 + (uint32_t)ts, kAction);
                     u = O_::make(uniform_pm1<T>(r.x), uniform_pm1<T>(r.y));
+                    if (a.random_actions == 2) const_cast<R2*>(a.act)[g] = u;    // recorded for the caller (replay buffer)
                 }
                 T Fx = O_::mul(a.gain, O_::mul(u.x, a.sens));                // environment.py:216-221, core.py:232-236
                 T Fy = O_::mul(a.gain, O_::mul(u.y, a.sens));

@@ -17,11 +17,18 @@
 //     the landmarks) and the columns of landmarks i, i + N, ... (min over the agents).
 //   * row = [p_vel | landmark positions (absolute) | other_pos | comm zeros (N-1)]: other_pos are the NOBS agents after
 //     me in cyclic order (partial, :50-53) or all others clipped to +-obs_range (range, :49-52).
+//   * formation_hd_obs_env (formation_gym/envs/formation_hd_obs_env.py:14-149; train/README.md:43,53,171: 4 agents): the
+//     last NO landmarks are movable colliding obstacles.  Lane i < NO of an env also owns obstacle i: its contact forces
+//     against the agents and the other obstacles in the reference's entity order, its integration, the reward hook's
+//     velocity rule and its reset (semantics: fg_obstacle.cuh, whose tile kernel stays the fallback).  The reward is the
+//     goals' Hausdorff term minus 2 per collision with an agent or an obstacle; the obstacles enter the row relative to
+//     the agent.
 // Restrictions (host: lm_warp_ok in fg_abi_impl.cuh): uniform agent constants, no walls, silent agents, an
 // observation buffer; anything else takes the tile kernel, which implements the same semantics (and is what the fp64
 // goldens of the unmodified reference pin; tests compare the two kernels and each against the oracle).
 #pragma once
 #include "fg_kernels.cuh"
+#include "fg_obstacle.cuh"
 
 namespace fg {
 
@@ -32,6 +39,10 @@ template <typename T, int N, int L, int SCN, int NOBS> struct LmLayout {
     static constexpr int NA = EPW * N;                 // active lanes
     static constexpr int NL = EPW * L;                 // landmarks of a span
     static constexpr int NLR = (NL + 31) / 32;         // landmark items per lane
+    // formation_hd_obs_env: L = goal landmarks + obstacles (world.landmarks order), NOBS = the number of obstacles;
+    // its row [p_vel | goals (LG) | obstacles - p (NO) | other_pos (N-1) | comm (N-1)] has the range scenario's length
+    static constexpr int NO = (SCN == kScnObstacle) ? NOBS : 0;     // movable colliding obstacles (the last NO landmarks)
+    static constexpr int LG = L - NO;                               // goal landmarks
     static constexpr int NREL = (SCN == kScnPartial) ? NOBS : N - 1;
     static constexpr int IPR = 1 + L + NREL + (N - 1); // R2 items per observation row
     static constexpr int MAXW = 8;
@@ -41,12 +52,15 @@ template <typename T, int N, int L, int SCN, int NOBS> struct LmLayout {
     static constexpr size_t off_cen = off_pnew + (size_t)2 * NA * sizeof(R2);
     static constexpr size_t off_vel = off_cen + (size_t)NA * sizeof(R2);
     static constexpr size_t off_lm = off_vel + (size_t)NA * sizeof(R2);      // 2 x [EPW][L] landmark positions (this span, next span)
-    static constexpr size_t off_max = off_lm + (size_t)2 * NL * sizeof(R2);
+    static constexpr size_t off_ov = off_lm + (size_t)2 * NL * sizeof(R2);   // 2 x [EPW][NO] obstacle velocities (as off_lm)
+    static constexpr size_t off_on = off_ov + (size_t)2 * EPW * NO * sizeof(R2);   // [EPW][NO] obstacle positions after the step
+    static constexpr size_t off_max = off_on + (size_t)EPW * NO * sizeof(R2);
     static constexpr size_t off_col = off_max + (size_t)EPW * sizeof(Bits);
     static constexpr size_t off_stat = (off_col + (size_t)EPW * sizeof(int) + 7) & ~(size_t)7;   // 4 doubles
     static constexpr size_t raw = off_stat + 4 * sizeof(double);
     static constexpr size_t stride = (raw + 15) & ~(size_t)15;
-    static_assert(SCN == kScnPartial || SCN == kScnRange, "landmark scenarios");
+    static_assert(SCN == kScnPartial || SCN == kScnRange || SCN == kScnObstacle, "landmark scenarios");
+    static_assert(NO <= N && LG >= 1, "lane i of an env also owns obstacle i");
     static_assert(N >= 2 && N <= 16 && L >= 1 && NLR <= 4, "small worlds only");
     static_assert(SCN != kScnPartial || (NOBS >= 1 && NOBS <= N), "the cyclic neighbour window fits the doubled array");
 };
@@ -62,6 +76,8 @@ __global__ void __launch_bounds__(32 * LmLayout<T, N, L, SCN, NOBS>::MAXW, 3) k_
     typedef typename O::Bits Bits;
     typedef LmLayout<T, N, L, SCN, NOBS> LY;
     constexpr int EPW = LY::EPW, NA = LY::NA, NL = LY::NL, NLR = LY::NLR, IPR = LY::IPR, NREL = LY::NREL;
+    constexpr int NO = LY::NO, LG = LY::LG;
+    constexpr bool OBST = (SCN == kScnObstacle);
     constexpr unsigned FULL = 0xffffffffu;
     extern __shared__ __align__(128) unsigned char smem_raw[];
 
@@ -91,10 +107,21 @@ __global__ void __launch_bounds__(32 * LmLayout<T, N, L, SCN, NOBS>::MAXW, 3) k_
     R2* s_cen = reinterpret_cast<R2*>(wr + LY::off_cen);
     R2* s_vel = reinterpret_cast<R2*>(wr + LY::off_vel);
     R2* s_lm2 = reinterpret_cast<R2*>(wr + LY::off_lm);
+    R2* s_ov2 = reinterpret_cast<R2*>(wr + LY::off_ov);                     // obstacle velocities (formation_hd_obs_env)
+    R2* s_on = reinterpret_cast<R2*>(wr + LY::off_on);                      // obstacle positions after the step
     Bits* s_max = reinterpret_cast<Bits*>(wr + LY::off_max);
     int* s_col = reinterpret_cast<int*>(wr + LY::off_col);
     double* s_stat = reinterpret_cast<double*>(wr + LY::off_stat);          // per-warp episode statistics (see fg_warp.cuh)
     if (lane < 4) s_stat[lane] = 0.0;
+
+    // formation_hd_obs_env: contact geometry of the agent-obstacle and obstacle-obstacle pairs (core.py:307) and the mass
+    // ratios of core.py:314-318 -- launch constants
+    const T dmin_ao = OBST ? O::add(a.size, a.osize) : (T)0, dmin_oo = OBST ? O::add(a.osize, a.osize) : (T)0;
+    const T cut_ao = dmin_ao + a.kcut * a.margin, cut_oo = dmin_oo + a.kcut * a.margin;
+    const T cut2_ao = cut_ao * cut_ao, cut2_oo = cut_oo * cut_oo;
+    const T ratio_ao = OBST ? O::div(a.omass, a.mass) : (T)1;               // force on the agent: (m_b / m_a) * force
+    const T ratio_oa = OBST ? -O::div((T)1, ratio_ao) : (T)1;               // on the obstacle: -(m_a / m_b) * force
+    const T dmin_ao2_hi = dmin_ao * dmin_ao * (T)1.0001;                    // guarded square: candidates of the exact test
 
     const R2 zero = O::make((T)0, (T)0);
     bool bulk_pending = false;
@@ -131,6 +158,12 @@ __global__ void __launch_bounds__(32 * LmLayout<T, N, L, SCN, NOBS>::MAXW, 3) k_
                 asm volatile("cp.async.ca.shared.global [%0], [%1], %2;"
                              :: "r"(smem_u32(s_lm2 + buf * NL + q)), "l"(a.lm + (size_t)fe0 * L + q), "n"(sizeof(R2)) : "memory");
         }
+        if (OBST && a.lmv && lane < nv * NO) {                              // landmark_vel[E,L,2]: obstacle entries only
+            const int qe = lane / (NO > 0 ? NO : 1), k = lane - qe * NO;
+            asm volatile("cp.async.ca.shared.global [%0], [%1], %2;"
+                         :: "r"(smem_u32(s_ov2 + buf * (EPW * NO) + lane)), "l"(a.lmv + (size_t)(fe0 + qe) * L + LG + k),
+                            "n"(sizeof(R2)) : "memory");
+        }
         asm volatile("cp.async.commit_group;" ::: "memory");
         buf ^= 1;
     };
@@ -153,9 +186,14 @@ __global__ void __launch_bounds__(32 * LmLayout<T, N, L, SCN, NOBS>::MAXW, 3) k_
     T epr = epr_n;
     int stp = stp_n, epc = epc_n;
     R2* s_lm = s_lm2 + (buf ^ 1) * NL;                                      // filled by the fetch of the previous iteration
+    R2* s_ov = s_ov2 + (buf ^ 1) * (EPW * NO);
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncwarp();                                                           // every lane's copies landed; readers of the other half are done
     if (spans_left > 1) fetch(span + nwarps);
+    // formation_hd_obs_env: lane i < NO of an env also owns obstacle i (entity N + LG + i of the reference's pair loop)
+    const bool obst_lane = OBST && active && i < NO;
+    R2 ov = zero;                                                           // its velocity (NULL landmark_vel: at rest)
+    if (obst_lane && a.lmv) ov = s_ov[le * NO + i];
 
     for (int ts = 0; ts < n_steps; ++ts) {
         if (lane < EPW) { s_max[lane] = 0; s_col[lane] = 0; }
@@ -205,6 +243,22 @@ __global__ void __launch_bounds__(32 * LmLayout<T, N, L, SCN, NOBS>::MAXW, 3) k_
                     if (j < i) { Fx = O::add(-fx, Fx); Fy = O::add(-fy, Fy); }   // equal masses: ratio 1
                     else       { Fx = O::add(fx, Fx);  Fy = O::add(fy, Fy); }
                 }
+                if constexpr (OBST) {
+                    // agent (entity a) against every obstacle (entity b > a; goal landmarks do not collide,
+                    // core.py:292): force_a = (m_b / m_a) * force (core.py:314-318)
+                    const R2* envo = s_lm + le * L + LG;
+                    const T ratio = ratio_ao;
+#pragma unroll
+                    for (int k = 0; k < NO; ++k) {
+                        R2 q = envo[k];
+                        T dx = O::sub(p.x, q.x), dy = O::sub(p.y, q.y);
+                        if (!(dx * dx + dy * dy >= cut2_ao)) {
+                            T fx, fy;
+                            contact_force<T>(dx, dy, dmin_ao, a.margin, a.cforce, &fx, &fy);
+                            Fx = O::add(O::mul(ratio, fx), Fx); Fy = O::add(O::mul(ratio, fy), Fy);
+                        }
+                    }
+                }
             }
             // integrate_state (core.py:264-277)
             v.x = O::mul(v.x, a.keep); v.y = O::mul(v.y, a.keep);
@@ -229,6 +283,47 @@ __global__ void __launch_bounds__(32 * LmLayout<T, N, L, SCN, NOBS>::MAXW, 3) k_
                 if (has_comm) a.comm[g] = zero;                             // update_agent_state: silent -> c = 0
             }
         }
+        if constexpr (OBST) {
+            // the obstacles themselves (fg_obstacle.cuh): contributions in entity order -- agents (the obstacle is entity
+            // b: -(m_a / m_b) * force), earlier obstacles (b), later obstacles (a); no action force, damped and
+            // integrated like an agent, never speed-clamped (core.py:264-277)
+            if (obst_lane) {
+                const R2* envo = s_lm + le * L + LG;
+                const R2 po = envo[i];
+                T Fx = (T)0, Fy = (T)0;
+                if (f_collide) {
+                    const R2* envp = s_pold + le * N;
+                    const T c = ratio_oa;
+#pragma unroll
+                    for (int j = 0; j < N; ++j) {
+                        R2 pj = envp[j];
+                        T dx = O::sub(pj.x, po.x), dy = O::sub(pj.y, po.y);
+                        if (!(dx * dx + dy * dy >= cut2_ao)) {
+                            T fx, fy;
+                            contact_force<T>(dx, dy, dmin_ao, a.margin, a.cforce, &fx, &fy);
+                            Fx = O::add(O::mul(c, fx), Fx); Fy = O::add(O::mul(c, fy), Fy);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int m = 0; m < NO; ++m) {
+                    if (m == i) continue;
+                    R2 q2 = envo[m];
+                    T dx = (m < i) ? O::sub(q2.x, po.x) : O::sub(po.x, q2.x);
+                    T dy = (m < i) ? O::sub(q2.y, po.y) : O::sub(po.y, q2.y);
+                    if (!(dx * dx + dy * dy >= cut2_oo)) {
+                        T fx, fy;
+                        contact_force<T>(dx, dy, dmin_oo, a.margin, a.cforce, &fx, &fy);
+                        if (m < i) { Fx = O::add(-fx, Fx); Fy = O::add(-fy, Fy); }     // equal obstacle masses
+                        else       { Fx = O::add(fx, Fx);  Fy = O::add(fy, Fy); }
+                    }
+                }
+                ov.x = O::mul(ov.x, a.keep); ov.y = O::mul(ov.y, a.keep);
+                ov.x = O::add(ov.x, O::mul(O::div(Fx, a.omass), a.dt));
+                ov.y = O::add(ov.y, O::mul(O::div(Fy, a.omass), a.dt));
+                s_on[le * NO + i] = O::make(O::add(po.x, O::mul(ov.x, a.dt)), O::add(po.y, O::mul(ov.y, a.dt)));
+            }
+        }
         // any non-finite position in an env makes its centroid, hence the whole shape term, NaN
         const bool bad = !(fabs(p.x) < (T)INFINITY) || !(fabs(p.y) < (T)INFINITY);
         const bool env_bad = (__ballot_sync(FULL, active && bad) & envmask) != 0u;
@@ -248,9 +343,9 @@ __global__ void __launch_bounds__(32 * LmLayout<T, N, L, SCN, NOBS>::MAXW, 3) k_
         }
         const R2* eL = s_lm + le * L;
 #pragma unroll
-        for (int k = 0; k < L; ++k) { R2 l = eL[k]; lx = O::add(lx, l.x); ly = O::add(ly, l.y); }
+        for (int k = 0; k < LG; ++k) { R2 l = eL[k]; lx = O::add(lx, l.x); ly = O::add(ly, l.y); }   // (goal landmarks)
         const R2 mp = O::make(O::div_count(sx, N), O::div_count(sy, N));    // fp64: true division, as np.mean
-        const R2 ml = O::make(O::div_count(lx, L), O::div_count(ly, L));
+        const R2 ml = O::make(O::div_count(lx, LG), O::div_count(ly, LG));
         const R2 C = O::make(O::sub(p.x, mp.x), O::sub(p.y, mp.y));         // centred agent shape
         if (lane < NA) s_cen[lane] = C;
         __syncwarp();
@@ -261,14 +356,14 @@ __global__ void __launch_bounds__(32 * LmLayout<T, N, L, SCN, NOBS>::MAXW, 3) k_
             const R2* eP = s_pnew + le * 2 * N + i;                         // eP[k] = agent (i + k) mod N
             T dmax = (T)INFINITY;
 #pragma unroll
-            for (int k = 0; k < L; ++k) {                                   // row i: min_k |C_i - V_k|^2, V_k = l_k - mean(l)
+            for (int k = 0; k < LG; ++k) {                                  // row i: min_k |C_i - V_k|^2, V_k = l_k - mean(l)
                 const R2 l = eL[k];
                 dmax = fmin(dmax, O::sq2(O::sub(C.x, O::sub(l.x, ml.x)), O::sub(C.y, O::sub(l.y, ml.y))));
             }
 #pragma unroll
-            for (int k0 = 0; k0 < L; k0 += N) {                             // columns i, i + N, ...: min_j |C_j - V_k|^2
+            for (int k0 = 0; k0 < LG; k0 += N) {                            // columns i, i + N, ...: min_j |C_j - V_k|^2
                 const int k = k0 + i;
-                if (k < L) {
+                if (k < LG) {
                     const R2 l = eL[k];
                     const R2 Vk = O::make(O::sub(l.x, ml.x), O::sub(l.y, ml.y));
                     T colmin = (T)INFINITY;
@@ -295,6 +390,15 @@ __global__ void __launch_bounds__(32 * LmLayout<T, N, L, SCN, NOBS>::MAXW, 3) k_
                 R2 q = eP[k];
                 if (O::norm2(O::sub(q.x, p.x), O::sub(q.y, p.y)) < a.rthr) ++col;
             }
+            if constexpr (OBST) {                                           // ... and with every obstacle (formation_hd_obs_env.py:91-97)
+                const R2* envo = s_on + le * NO;
+#pragma unroll
+                for (int k = 0; k < NO; ++k) {
+                    R2 q = envo[k];
+                    T dx = O::sub(q.x, p.x), dy = O::sub(q.y, p.y);
+                    if (f_collide && dx * dx + dy * dy < dmin_ao2_hi && O::norm2(dx, dy) < dmin_ao) ++col;
+                }
+            }
             atomicMax(&s_max[le], O::bits(dmax));                           // d2 >= 0: bit order == value order
             if (col) atomicAdd(&s_col[le], col);
         }
@@ -306,11 +410,12 @@ __global__ void __launch_bounds__(32 * LmLayout<T, N, L, SCN, NOBS>::MAXW, 3) k_
         if (active) {
             T base = -O::sqrt_(O::from_bits(s_max[le]));                    // -max(dH(u,v), dH(v,u)); no velocity term
             if (env_bad) base = O::from_bits(~(Bits)0 >> 1);                // NaN, as the reference
+            constexpr int CPEN = OBST ? 2 : 1;                              // rew -= 1 (2: formation_hd_obs_env.py:93,97) per collision
             T r = base;
-            for (int c = 0; c < col; ++c) r = O::sub(r, (T)1);              // rew -= 1 per collision
+            for (int c = 0; c < col; ++c) r = O::sub(r, (T)CPEN);
             const int coltot = s_col[le];
-            // shared reward = sum_i r_i (environment.py:136): N*base - total collisions, in fp64
-            const double R = (double)N * (double)base - (double)coltot;
+            // shared reward = sum_i r_i (environment.py:136): N*base - CPEN * total collisions, in fp64
+            const double R = (double)N * (double)base - (double)CPEN * (double)coltot;
             a.reward[g] = (T)R;
             if (has_indiv) a.indiv[g] = r;
             if (has_done) a.done[g] = (uint8_t)(has_step ? (stp >= a.world_length) : 0);
@@ -331,6 +436,10 @@ __global__ void __launch_bounds__(32 * LmLayout<T, N, L, SCN, NOBS>::MAXW, 3) k_
             }
         }
 
+        // the reward hook's side effect (formation_hd_obs_env.py:85-88): every obstacle falls at (0, -1) while it is above
+        // the floor and rests below it -- its velocity for the next step
+        if (obst_lane) ov = O::make((T)0, (s_on[le * NO + i].y > a.ofloor) ? a.ofall : (T)0);
+
         // ======== VecEnv auto-reset (env_wrappers.py:14-18; reset_world formation_hd_partial_env.py:89-101)
         if (a.auto_reset && __any_sync(FULL, dn)) {
             const uint32_t tk = tick0 + (uint32_t)ts;
@@ -343,20 +452,29 @@ __global__ void __launch_bounds__(32 * LmLayout<T, N, L, SCN, NOBS>::MAXW, 3) k_
                 s_vel[lane] = v;
                 stp = 0;
 #pragma unroll
-                for (int k0 = 0; k0 < L; k0 += N) {                         // landmarks i, i + N, ... of my env
+                for (int k0 = 0; k0 < LG; k0 += N) {                        // landmarks i, i + N, ... of my env
                     const int k = k0 + i;
-                    if (k < L) {
+                    if (k < LG) {
                         U4 q = philox(a.seed, ge, (uint32_t)k, tk, kResetLandmark);
                         const R2 l = O::make(uniform_pm1<T>(q.x), uniform_pm1<T>(q.y));
                         s_lm[le * L + k] = l;
                         a.lm[(size_t)e * L + k] = l;
                     }
                 }
+                if (OBST && i < NO) {                                       // formation_hd_obs_env.py:108,116-119
+                    R2 po;
+                    obstacle_reset<T>(a.seed, ge, LG + i, i, NO, tk, &po, &ov, a.ofall);
+                    s_on[le * NO + i] = po;
+                }
                 if (ts == n_steps - 1) { a.pos[g] = p; a.vel[g] = v; }
             }
             __syncwarp();
         }
         if (active && i == 0 && has_step) a.step[e] = stp;
+        if (obst_lane && ts == n_steps - 1) {                               // the obstacles' new state
+            a.lm[(size_t)e * L + LG + i] = s_on[le * NO + i];
+            if (a.lmv) a.lmv[(size_t)e * L + LG + i] = ov;
+        }
 
         // ================= observation rows leave the SM as one bulk copy =======================
         // Filled LAST, from the shared state, which for an env that was just reset already holds the RESET state
@@ -392,7 +510,12 @@ __global__ void __launch_bounds__(32 * LmLayout<T, N, L, SCN, NOBS>::MAXW, 3) k_
 #pragma unroll
                 for (int k = 0; k < L; ++k) {
                     int kk = k + rL; kk -= (kk >= L) ? L : 0;
-                    row[1 + kk] = eL[kk];
+                    R2 l = eL[kk];                                          // landmark p_pos, absolute
+                    if (OBST && kk >= LG) {                                 // obstacles: NEW position relative to me (:58-59)
+                        const R2 o = s_on[le * NO + (kk - LG)];
+                        l = O::make(O::sub(o.x, p.x), O::sub(o.y, p.y));
+                    }
+                    row[1 + kk] = l;
                 }
                 const int rR = ROT ? lane % NREL : 0;
 #pragma unroll
@@ -401,12 +524,14 @@ __global__ void __launch_bounds__(32 * LmLayout<T, N, L, SCN, NOBS>::MAXW, 3) k_
                     if (SCN == kScnPartial) {                               // agents i+1 .. i+NOBS, cyclic (:50-53)
                         R2 q = eP[1 + mm];
                         row[1 + L + mm] = O::make(O::sub(q.x, p.x), O::sub(q.y, p.y));
-                    } else {                                                // all others, j != i ascending, clipped (:49-52)
+                    } else {                                                // all others, j != i ascending
                         R2 q = eA[mm + (mm >= i ? 1 : 0)];
                         T dx = O::sub(q.x, p.x), dy = O::sub(q.y, p.y);
-                        const T lo = -a.obs_range, hi = a.obs_range;        // np.clip keeps NaN
-                        dx = (dx < lo) ? lo : ((dx > hi) ? hi : dx);
-                        dy = (dy < lo) ? lo : ((dy > hi) ? hi : dy);
+                        if (SCN == kScnRange) {                             // clipped to the sensing range (:49-52)
+                            const T lo = -a.obs_range, hi = a.obs_range;    // np.clip keeps NaN
+                            dx = (dx < lo) ? lo : ((dx > hi) ? hi : dx);
+                            dy = (dy < lo) ? lo : ((dy > hi) ? hi : dy);
+                        }
                         row[1 + L + mm] = O::make(dx, dy);
                     }
                 }
@@ -436,6 +561,8 @@ __global__ void __launch_bounds__(32 * LmLayout<T, N, L, SCN, NOBS>::MAXW, 3) k_
             }
             bulk_pending = true;
         }
+        // next step of an in-kernel rollout: the obstacles' new positions become the old ones
+        if (OBST && n_steps > 1 && obst_lane) s_lm[le * L + LG + i] = s_on[le * NO + i];
     }
     if (--spans_left == 0) break;
   }  // spans

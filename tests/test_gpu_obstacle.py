@@ -125,9 +125,13 @@ def test_obstacle_reset_rollout_and_facade():
     assert np.all(ov[..., 0] == 0.0) and np.all(ov[..., 1] == -1.0)
     assert float(env.landmarks[:, :G].abs().max()) <= 1.0 and float(env.pos.abs().max()) <= 1.0
     # stepwise random policy == one in-kernel rollout (same Philox stream), across an auto-reset
+    # (fp32: both through the tile kernel -- single steps would otherwise take the warp kernel's STD instantiation,
+    # whose FMA contraction differs in the last bit)
+    from formation_gym import _native as nat_
     sd = env.state_dict()
-    for _ in range(7):
-        obs_a, rew_a, done_a, _ = env.step_random()
+    with nat_.options(no_std_kernel=1):
+        for _ in range(7):
+            obs_a, rew_a, done_a, _ = env.step_random()
     fin = {k: getattr(env, k).clone() for k in ("pos", "vel", "landmarks", "landmark_vel", "step_count")}
     obs_a = obs_a.clone()
     env.load_state_dict(sd)
@@ -195,3 +199,64 @@ def test_world_step_alone_on_obstacle_world():
     assert np.abs(np.stack([l.state.p_pos for l in w.landmarks[4:]]) - ro[0]).max() <= 1e-11
     assert np.abs(np.stack([l.state.p_vel for l in w.landmarks[4:]]) - rov[0]).max() <= 1e-10
     assert np.abs(rov[0] - np.array([0.0, -0.75])).max() > 1e-3      # contacts did change an obstacle's velocity
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# k_lm_warp<.., kScnObstacle> (fg_warp_lm.cuh): the warp-autonomous kernel the scenario takes at 3 .. 9 agents with
+# make_world's 4 goals + 3 obstacles, against the tile kernel of fg_obstacle.cuh (force_tile_kernel)
+from formation_gym import _native as nat  # noqa: E402
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64], ids=["f32", "f64"])
+@pytest.mark.parametrize("N", [3, 4, 5, 6, 7, 8, 9])
+def test_obstacle_warp_kernel_equals_tile_kernel(N, dtype):
+    """Episodes of 12 steps with auto-reset (the obstacles fall through the agents, which start inside [-1, 1]^2: contacts
+    agent-agent, agent-obstacle and obstacle-obstacle all occur), ragged last span, random policy recorded: the fp64
+    build is bit-identical, fp32 agrees to 1e-5 with the states re-synchronised every step."""
+    E = 517
+    mk = lambda: BatchedFormationEnv(SCN, E, N, episode_length=12, dtype=dtype, seed=23, auto_reset=True)  # noqa: E731
+    a, b = mk(), mk()
+    a.reset(); b.reset()
+    assert torch.equal(a.obs, b.obs) and torch.equal(a.landmarks, b.landmarks)
+    touched = 0
+    for t in range(30):
+        l0 = a.launches
+        oa, ra, da, ia = a.step_random(record_actions=True)
+        assert a.launches - l0 == 1
+        with nat.options(force_tile_kernel=1):
+            ob, rb, db, ib = b.step_random(record_actions=True)
+        assert torch.equal(a.actions, b.actions) and torch.equal(da, db)
+        pairs = ((oa, ob), (ra, rb), (a.pos, b.pos), (a.vel, b.vel), (a.landmarks, b.landmarks),
+                 (a.landmark_vel, b.landmark_vel), (ia["individual_reward"], ib["individual_reward"]),
+                 (a.ep_return, b.ep_return))
+        if dtype == torch.float64:
+            for k, (x, y) in enumerate(pairs):
+                assert torch.equal(x, y), (t, k)
+        else:
+            for k, (x, y) in enumerate(pairs):
+                assert float((x - y).abs().max()) <= 1e-5 * max(1.0, float(y.abs().max())), (t, k)
+            b.load_state_dict(a.state_dict())
+        assert torch.equal(a.step_count, b.step_count) and torch.equal(a.ep_collisions, b.ep_collisions)
+        touched += int((ia["individual_reward"] < ia["individual_reward"].amax(dim=1, keepdim=True) - 1.5).sum())
+    assert touched > 0                                               # some agent paid the -2 of a collision
+    assert torch.equal(a.stats[:1], b.stats[:1])
+
+
+def test_obstacle_warp_kernel_rollout_and_external_actions():
+    """n_steps > 1 in one launch (the obstacles' new positions feed the next step's contacts) and caller-owned action
+    buffers, fp64, against single tile-kernel steps."""
+    for N in (4, 5):
+        mk = lambda: BatchedFormationEnv(SCN, 700, N, episode_length=9, dtype=torch.float64, seed=4)  # noqa: E731
+        a, b = mk(), mk()
+        a.reset(); b.reset()
+        a.rollout_random(14)
+        for _ in range(14):
+            with nat.options(force_tile_kernel=1):
+                b.step_random()
+        for k in ("pos", "vel", "landmarks", "landmark_vel", "obs", "reward", "step_count", "ep_return"):
+            assert torch.equal(getattr(a, k), getattr(b, k)), (N, k)
+        act = torch.rand(700, N, 2, dtype=torch.float64, device="cuda") * 2 - 1
+        oa = a.step(act)[0].clone()
+        with nat.options(force_tile_kernel=1):
+            ob = b.step(act)[0]
+        assert torch.equal(oa, ob) and torch.equal(a.landmarks, b.landmarks)
