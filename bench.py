@@ -820,6 +820,15 @@ def also_configs(formation_gym, torch, device, dtype, peak, a):
         ("hd N=243 E=8192 state+reward only (no obs)", "formation_hd_env", 243, 8192, "noobs", 10, {}),
         ("hd N=81 E=8192", "formation_hd_env", 81, 8192, "step", 20, {}),
         ("basic N=3 L=3 E=1048576", "basic_formation_env", 3, 1048576, "step", 50, {}),
+        # SURVEY.md 8(f) rank 3, at the sizes the reference's training recipes use (train/README.md:40-53,167-173: 4 / 5
+        # agents, make_world's default landmark counts): fg::k_lm_warp (fg_warp_lm.cuh)
+        ("formation_hd_partial_env N=4 L=5 num_obs=3 E=262144 (train/README.md:51)", "formation_hd_partial_env", 4, 262144,
+         "step", 50, {}),
+        ("formation_hd_partial_env N=5 L=5 num_obs=3 E=262144 (train/README.md:40)", "formation_hd_partial_env", 5, 262144,
+         "step", 50, {}),
+        ("formation_hd_partial_range_env N=4 L=4 E=262144", "formation_hd_partial_range_env", 4, 262144, "step", 50, {}),
+        ("formation_hd_obs_env N=4, 4 goals + 3 obstacles, E=262144 (train/README.md:43,171)", "formation_hd_obs_env", 4,
+         262144, "step", 50, {}),
     ]
     for name, scen, N, E, mode, steps, kw in cfgs:
         try:

@@ -163,7 +163,8 @@ const char* fg_last_error(void);
 /* A/B switches for tests and profiling (never needed in production; defaults select the product kernels).  They are
  * process-global, read once from the environment variables FG_<NAME IN UPPER CASE> when the library is first used
  * (never on the launch path) and can be changed at run time here.  Names and ranges:
- *   force_tile_kernel 0/1  fg_step_fused always takes the generic tile kernel instead of the warp-autonomous one
+ *   force_tile_kernel 0/1  fg_step_fused always takes the generic tile kernels instead of the warp-autonomous ones
+ *                          (formation_hd_env / basic: k_hd_warp; partial, partial_range, obs_env: k_lm_warp)
  *   no_fast_pairs 0/1      tile kernel: scalar pair loops instead of the packed ones (N >= 32)
  *   force_fast_pairs 0/1   tile kernel: packed pair loops also for 32 <= N < 64 with observations
  *   no_cells 0/1           packed pair loops: O(N^2) group filters instead of the hashed cell lists
@@ -175,7 +176,8 @@ const char* fg_last_error(void);
  *   row_nbuf 1/2           per-row pieces: staging buffers per warp
  *   no_early_rows 0/1      long-row observation writer: rows leave after the reward pass
  *   no_tile_image 0/1      short-row observation writer: flat item loop instead of the tile image
- *   no_std_kernel 0/1      warp kernel: never the instantiation specialised for the standard configuration
+ *   no_std_kernel 0/1      warp kernels: never the instantiation specialised for the standard configuration (fp32
+ *                          k_lm_warp has no other: the partial / obstacle scenarios then take the tile kernels)
  *   l2_prefetch 0/1/2      warp kernel: prefetch.global.L2 of the state two spans ahead: never / when the state
  *                          arrays exceed ~1/3 of L2 (default) / always
  *   waves 1..64            warp kernel: grid = waves x one resident wave
@@ -214,8 +216,8 @@ int fg_obs_reward_f64(const fg_params* p, const fg_buffers* b, int scenario, int
  * n_steps > 1 runs a whole rollout inside the kernel with state held on chip; then actions are
  * drawn in-kernel from the random policy U(-1,1) (test.py:20) and b->act is ignored.
  * n_steps == 1 and random_actions == 0 is the plain step on caller-provided actions.
- * random_actions == 2: as 1, and the drawn actions are also WRITTEN to b->act [E,N,2] (the one case in which the
- * library writes that buffer) so that the caller has the (obs, action, reward) triple of the step -- the random
+ * random_actions == 2: as 1, and the drawn actions are also WRITTEN to b->act [E,N,2] (with fg_step_policy the one case
+ * in which the library writes that buffer) so that the caller has the (obs, action, reward) triple of the step -- the random
  * policy and the step in one launch instead of fg_random_actions + fg_step_fused. */
 int fg_step_fused(const fg_params* p, const fg_buffers* b, int scenario, int E, int N, int L,
                   int n_steps, int random_actions, int auto_reset,
