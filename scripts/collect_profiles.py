@@ -6,7 +6,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "scripts"))
 import ncu_csv_summary  # noqa: E402
 tag = sys.argv[1]
-short = {"formation_hd_env": "hd", "basic_formation_env": "basic"}
+short = {"formation_hd_partial_env": "partial", "formation_hd_obs_env": "obstacle", "formation_hd_env": "hd",
+         "basic_formation_env": "basic"}
 for raw in sorted(glob.glob(os.path.join(ROOT, "gpurun_out", tag + "_*.raw.csv"))):
     name = os.path.basename(raw)[:-8]
     for k, v in short.items():

@@ -8,7 +8,9 @@ bash scripts/gpu_prof.sh $TAG \
   "formation_hd_env 9 1048576 1 k_hd_warp none" "formation_hd_env 27 65536 1 k_hd_warp none" \
   "formation_hd_env 3 1048576 1 k_hd_warp none" "basic_formation_env 3 1048576 1 k_hd_warp none" \
   "formation_hd_env 243 1024 1 k_step none" "formation_hd_env 243 1024 0 k_step none" \
-  "formation_hd_env 243 8192 0 k_step none" "formation_hd_env 81 8192 1 k_step none" > gpurun_out/${TAG}_prof.log 2>&1
+  "formation_hd_env 243 8192 0 k_step none" "formation_hd_env 81 8192 1 k_step none" \
+  "formation_hd_partial_env 4 262144 1 k_lm_warp none" "formation_hd_partial_env 5 262144 1 k_lm_warp none" \
+  "formation_hd_obs_env 4 262144 1 k_lm_warp none" > gpurun_out/${TAG}_prof.log 2>&1
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:k_policy -s 2 -c 1 -o gpurun_out/${TAG}_policy9 -f \
   python scripts/run_policy.py 9 131072 > /dev/null 2>&1
 ncu -i gpurun_out/${TAG}_policy9.ncu-rep --page raw --csv > gpurun_out/${TAG}_policy9.raw.csv
