@@ -15,7 +15,7 @@ const OptionDesc kOptions[] = {
     {"nvtx", &Switches::nvtx, 0, 1},
     {"no_std_kernel", &Switches::no_std_kernel, 0, 1}, {"l2_prefetch", &Switches::l2_prefetch, 0, 2},
     {"row_chunks", &Switches::row_chunks, 0, 2}, {"row_min_n", &Switches::row_min_n, 3, 256},
-    {"row_chunk_max_log2", &Switches::row_chunk_max_log2, 1, 7},
+    {"row_chunk_max_log2", &Switches::row_chunk_max_log2, 1, 7}, {"pf_spans", &Switches::pf_spans, 2, 8},
 };
 }  // namespace
 

@@ -37,6 +37,7 @@ struct Switches {
     std::atomic<int> waves{1};              // warp kernel: grid = waves x one resident wave (>= 1)
     std::atomic<int> no_std_kernel{0};      // warp kernel: never the STD instantiation (standard configuration, flags compiled out)
     std::atomic<int> l2_prefetch{1};        // warp kernel: prefetch.global.L2 of the state two spans ahead: 0 never, 1 auto, 2 always
+    std::atomic<int> pf_spans{2};           // ... how many spans ahead (2 .. 8)
     std::atomic<int> row_chunks{1};         // OM == 2: chunked row writer (RC whole rows per image, one bulk store per chunk)
     std::atomic<int> row_chunk_max_log2{7}; // chunked row writer: at most 2^k rows per chunk
     std::atomic<int> row_min_n{10};         // OM == 2 (bulk-store row writers) from this agent count up
@@ -194,7 +195,7 @@ int fill_args(fg::KArgs<T>& a, const fg_params* p, const fg_buffers* b, int scen
         // 0.95 -> 0.88: each prefetch.global.L2 holds its warp for an L2 round trip.
         const int mode = fgabi::switches().l2_prefetch.load(std::memory_order_relaxed);       // 0 never, 1 auto, 2 always
         const double state_bytes = (double)E * (double)N * 4.0 * (double)sizeof(R2);
-        a.pf_dist = mode == 2 || (mode == 1 && state_bytes > 44e6) ? 1 : 0;
+        a.pf_dist = mode == 2 || (mode == 1 && state_bytes > 44e6) ? fgabi::switches().pf_spans.load(std::memory_order_relaxed) : 0;
     }
     a.seed = seed; a.tick = tick; a.env_offset = env_offset;
     // long hd rows of silent agents: static 2/3 of each row bulk-stored from one shared image

@@ -95,7 +95,8 @@ __global__ void __launch_bounds__(256) k_wr_stg(float4* dst, size_t n16) {
         __stcs(dst + q, v);
 }
 
-__global__ void __launch_bounds__(256) k_wr_bulk(unsigned char* dst, size_t bytes, unsigned chunk, int evict_first) {
+__global__ void __launch_bounds__(256) k_wr_bulk(unsigned char* dst, size_t bytes, unsigned chunk, int evict_first,
+                                                 int blocked) {
     extern __shared__ __align__(128) unsigned char sm[];
     for (unsigned q = threadIdx.x * 16; q < chunk; q += blockDim.x * 16)
         *reinterpret_cast<float4*>(sm + q) = make_float4(1.f, 2.f, 3.f, (float)q);
@@ -105,7 +106,12 @@ __global__ void __launch_bounds__(256) k_wr_bulk(unsigned char* dst, size_t byte
         uint64_t pol;
         asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
         const size_t nchunks = bytes / chunk;
-        for (size_t c = blockIdx.x; c < nchunks; c += gridDim.x) {
+        // cyclic: CTA b writes chunks b, b + grid, ... (all CTAs advance through one moving window of grid x chunk bytes);
+        // blocked: CTA b writes its own contiguous range of chunks (grid independent sequential streams)
+        const size_t per = (nchunks + gridDim.x - 1) / gridDim.x;
+        const size_t c0 = blocked ? blockIdx.x * per : blockIdx.x, c1 = blocked ? min(nchunks, c0 + per) : nchunks;
+        const size_t cs = blocked ? 1 : gridDim.x;
+        for (size_t c = c0; c < c1; c += cs) {
             if (evict_first)
                 asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;"
                              :: "l"(dst + c * chunk), "r"((uint32_t)__cvta_generic_to_shared(sm)), "r"(chunk), "l"(pol) : "memory");
@@ -151,7 +157,7 @@ extern "C" int fg_write_probe(int variant, void* dst, unsigned long long bytes, 
         if (chunk > 48 * 1024 &&
             cudaFuncSetAttribute(k_wr_bulk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chunk) != cudaSuccess)
             return FG_ERR_CUDA;
-        k_wr_bulk<<<ctas, 256, chunk, st>>>((unsigned char*)dst, (size_t)bytes, chunk, variant == 2);
+        k_wr_bulk<<<ctas, 256, chunk, st>>>((unsigned char*)dst, (size_t)bytes, chunk, variant >= 2, variant == 4);
     }
     return cudaGetLastError() == cudaSuccess ? FG_OK : FG_ERR_CUDA;
 }

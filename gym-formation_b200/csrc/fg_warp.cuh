@@ -53,7 +53,12 @@ template <typename T, int N, bool WOBS> struct WarpLayout {
     // re-reading the partner positions (measured: N = 3 91.1 -> 86.9 us per 1 M envs, N = 27 246 -> 241 us
     // per 65536).  FUSED into the reward loop (the p_j - p_i it already holds): fewest instructions, best
     // where the kernel is closest to issue-bound (N = 9: 55.0 us fused vs 58.5 us late per 131072 envs).
-    static constexpr bool LATE_FILL = (N != 9);   // N = 3, 9: three 8-warp CTAs per SM (<= 85 registers)
+    // (A/B build -DFG_LATE9=1, round 2 with the STD instantiation: late fill at N = 9 is now a tie -- 51.2 vs 52.2 us
+    // L2-resident, 529.5 vs 530.2 us per 1 M envs -- so neither variant is what holds the streaming regime at 4.85 TB/s.)
+#ifndef FG_LATE9
+#define FG_LATE9 0
+#endif
+    static constexpr bool LATE_FILL = (N != 9) || FG_LATE9;   // N = 3, 9: three 8-warp CTAs per SM (<= 85 registers)
     static constexpr int NA = EPW * N;             // active lanes
     static constexpr int IPR = 3 * N;              // R2 items per observation row (6N scalars)
     static constexpr int OBS_ITEMS = WOBS ? NA * IPR : 0;
@@ -194,7 +199,7 @@ __global__ void __launch_bounds__(32 * WarpLayout<T, N, WOBS>::MAXW, (SCN == kSc
         }
     };
     fetch(gw);
-    if (a.pf_dist > 0) l2_prefetch(gw + nwarps);
+    for (int d = 1; d < a.pf_dist; ++d) l2_prefetch(gw + d * nwarps);
 
   int spans_left = (nspans - gw + nwarps - 1) / nwarps;                     // >= 1
   for (int span = gw; ; span += nwarps) {
@@ -213,7 +218,7 @@ __global__ void __launch_bounds__(32 * WarpLayout<T, N, WOBS>::MAXW, (SCN == kSc
     T epr = epr_n;
     int stp = stp_n, epc = epc_n;
     if (spans_left > 1) fetch(span + nwarps);
-    if (a.pf_dist > 0 && spans_left > 2) l2_prefetch(span + 2 * nwarps);
+    if (a.pf_dist > 0 && spans_left > a.pf_dist) l2_prefetch(span + a.pf_dist * nwarps);
     __syncwarp();                                                           // previous span's readers of s_shp are done
     if (lane < NA) s_shp[lane] = S;
 

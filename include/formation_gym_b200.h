@@ -295,7 +295,8 @@ int fg_fp32_probe(int variant, int iters, int ctas, float* scratch, void* stream
 
 /* Diagnostics: write-only HBM stream over `bytes` of `dst` (what an observation writer can reach at
  * best).  variant 0: 16-byte streaming stores; 1: TMA bulk stores (cp.async.bulk) of `chunk` bytes from
- * shared memory; 2: the same with the L2 evict_first policy the step kernels use; 3: hd observation rows of
+ * shared memory; 2: the same with the L2 evict_first policy the step kernels use; 4: as 2, each CTA writing its own
+ * contiguous range of chunks instead of chunks b, b + ctas, ...; 3: hd observation rows of
  * `chunk` = N agents written with plain 8-byte streaming stores from registers (one warp per env, 128-thread CTAs). */
 int fg_write_probe(int variant, void* dst, unsigned long long bytes, unsigned chunk, int ctas, void* stream);
 
