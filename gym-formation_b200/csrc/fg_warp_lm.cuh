@@ -11,7 +11,8 @@
 // free-standing entities:
 //   * L landmarks per env, L != N in general (make_world's defaults: 5 for the partial scenario, 4 for the range
 //     one, whatever num_agents is -- formation_gym/__init__.py:11 passes only num_agents).  A span's landmarks are
-//     EPW * L consecutive items of lm[E,L,2]; lane q holds items q, q + 32, ...
+//     EPW * L consecutive items of lm[E,L,2]; lane q copies items q, q + 32, ... of the NEXT span into shared memory
+//     with cp.async while this span is computed.
 //   * reward = -max(dH(u, v), dH(v, u)) of the agents and the landmarks, each centred on its own mean
 //     (formation_hd_partial_env.py:67-75), minus one per collision; no velocity term.  Lane i owns row i (min over
 //     the landmarks) and the columns of landmarks i, i + N, ... (min over the agents).
@@ -131,7 +132,7 @@ __global__ void __launch_bounds__(32 * LmLayout<T, N, L, SCN, NOBS>::MAXW, 3) k_
     // one is computed -- the per-agent arrays in registers, the landmarks (up to two items per lane) through
     // cp.async straight into the other half of a double buffer: holding them in registers too made ptxas spill
     // under the 80-register bound, and with ~2 KB of L1 left beside the shared memory every spill reload is an L2
-    // round trip (N = 4: long-scoreboard stalls 4.2 per issue, issue active 50 %, profiles/r02c_lm4_before).
+    // round trip (N = 4: long-scoreboard stalls 4.2 per issue, issue active 50 %, profiles/r02c_lm4_before_ncu_summary.json).
     R2 p_n = zero, v_n = zero, u_n = zero;
     T epr_n = (T)0;
     int stp_n = 0, epc_n = 0;
@@ -334,7 +335,7 @@ __global__ void __launch_bounds__(32 * LmLayout<T, N, L, SCN, NOBS>::MAXW, 3) k_
         // means itself -- the positions from its env's lanes by shuffle, the landmarks from shared memory (every lane
         // of an env reads the same addresses: broadcasts) -- so nothing is staged and no lane waits for another.
         // (One lane per (env, mean) writing to shared memory, as fg_warp.cuh does, cost 5-way bank conflicts on the
-        // strided reads and two more warp barriers: profiles/r02d_lm4.)
+        // strided reads and two more warp barriers: profiles/r02d_lm4_ncu_summary.json.)
         T sx = 0, sy = 0, lx = 0, ly = 0;
 #pragma unroll
         for (int j = 0; j < N; ++j) {

@@ -180,6 +180,7 @@ const char* fg_last_error(void);
  *                          k_lm_warp has no other: the partial / obstacle scenarios then take the tile kernels)
  *   l2_prefetch 0/1/2      warp kernel: prefetch.global.L2 of the state two spans ahead: never / when the state
  *                          arrays exceed ~1/3 of L2 (default) / always
+ *   pf_spans 2..8          ... how many spans ahead (2)
  *   waves 1..64            warp kernel: grid = waves x one resident wave
  *   nvtx 0/1               NVTX ranges (domain-less, named after the entry point) around every launch
  * Unknown names / out-of-range values return FG_ERR_ARG. */
