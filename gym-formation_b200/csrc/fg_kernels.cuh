@@ -405,8 +405,11 @@ __global__ void __launch_bounds__(kBlock, (OM == 3 && SCN == kScnBasic) ? 5 : (O
         // 243 agents -- the burst fills the SM's TMA queue and the warps block on issuing; round 2 repeated it on
         // every second CTA only, so that the others compute meanwhile: 293 vs 244 us, still slower; delaying the
         // k-th resident CTA of an SM by k x 1.5 .. 8 us so that not all CTAs of the first wave are in their HBM-idle
-        // load + physics phase together: 263 .. 285 vs 252 us, slower too.  The launch costs a fixed ~27 us on top of
-        // 0.215 us per env (linear fit 592 .. 4096 envs): first-row latency plus the drain of the last CTAs.)
+        // load + physics phase together: 263 .. 285 vs 252 us, slower too.  The launch costs a fixed ~20-27 us on top of
+        // 0.215 us per env (linear fit 592 .. 4096 envs): first-row latency plus the drain of the last CTAs.  Splitting
+        // an env's rows over two CTAs that both run the physics would not shrink it: with every CTA writing only HALF
+        // of its rows (timing experiment) the fit is 24.4 us + 0.111 us per CTA, so 1024 envs as 2048 half-CTAs cost
+        // 245.6 us against 241.1 us now.)
         bool early = false;
         if constexpr (OM == 2 && sizeof(R2) == 8) {
             if (a.obs && a.row_early) {
