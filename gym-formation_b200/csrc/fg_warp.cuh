@@ -150,6 +150,14 @@ __global__ void __launch_bounds__(32 * WarpLayout<T, N, WOBS>::MAXW, (SCN == kSc
 
     const R2 zero = O::make((T)0, (T)0);
     bool bulk_pending = false;
+    // ZERO_ONCE: the comm slots of the row image (N - 1 zeros per row: silent agents) are written once per launch --
+    // nothing else writes them and every span of a warp uses the same image position (one 16-byte phase per warp, see
+    // the host).  Per N by measurement (same box, us per step, rewritten every span -> once): N = 4 30.4 -> 29.7,
+    // 6 59.9 -> 57.1, 7 34.7 -> 34.3, 8 45.6 -> 44.6, 25 230.0 -> 192.3; but 9 51.9 -> 53.1, 16 77.3 -> 83.5,
+    // 27 209.5 -> 236.5, 32 151.5 -> 158.0 (the fill is no longer the same instruction stream in every span and the
+    // schedule ptxas finds is worse), so those keep the stores.
+    constexpr bool ZERO_ONCE = (N >= 4 && N <= 8) || N == 25;
+    bool comm_zeroed = false;
 
     // Software pipeline over the spans of this (persistent) warp: the state of span s + nwarps is
     // requested from HBM before span s is computed, so the load latency hides behind ~800
@@ -383,8 +391,10 @@ __global__ void __launch_bounds__(32 * WarpLayout<T, N, WOBS>::MAXW, (SCN == kSc
                 }
             }
             if (FUSE) {
+                if (!ZERO_ONCE || !comm_zeroed) {
 #pragma unroll
-                for (int k = 0; k < N - 1; ++k) row[N + k] = zero;          // comm of the others (silent)
+                    for (int k = 0; k < N - 1; ++k) row[N + k] = zero;      // comm of the others (silent)
+                }
                 row[3 * N - 1] = iv;                                        // ideal_vel
             }
             // is_collision (formation_hd_env.py:71-74,119-121): exact test only for candidates
@@ -510,7 +520,11 @@ __global__ void __launch_bounds__(32 * WarpLayout<T, N, WOBS>::MAXW, (SCN == kSc
                         int mm = m + r1; mm -= (mm >= N - 1) ? (N - 1) : 0;
                         R2 q = eA[mm + (mm >= i ? 1 : 0)];                  // partner of slot mm: j != i ascending
                         row[1 + mm] = O::make(O::sub(q.x, p.x), O::sub(q.y, p.y));
-                        row[N + mm] = zero;                                 // comm of the others (silent)
+                        if (!ZERO_ONCE) row[N + mm] = zero;                 // comm of the others (silent)
+                    }
+                    if (ZERO_ONCE && !comm_zeroed) {
+#pragma unroll
+                        for (int m = 0; m < N - 1; ++m) row[N + m] = zero;
                     }
                     // (writing the static 2N items of all rows cooperatively -- lane l holding items l, l + 32 of the
                     // env's [comm | ideal_shape | ideal_vel] vector, ceil(2N / 32) conflict-free stores per row -- was
@@ -535,8 +549,10 @@ __global__ void __launch_bounds__(32 * WarpLayout<T, N, WOBS>::MAXW, (SCN == kSc
                     R2 q = eA[m + (m >= i ? 1 : 0)];
                     row[OFF + 1 + m] = O::make(O::sub(q.x, p.x), O::sub(q.y, p.y));   // other_pos (formation_hd_env.py:55)
                 }
+                if (!ZERO_ONCE || !comm_zeroed) {
 #pragma unroll
-                for (int k = 0; k < N - 1; ++k) row[OFF + N + k] = zero;    // comm of the others (silent)
+                    for (int k = 0; k < N - 1; ++k) row[OFF + N + k] = zero;   // comm of the others (silent)
+                }
                 if (SCN == kScnHD) {
 #pragma unroll
                     for (int k = 0; k < N; ++k) row[2 * N - 1 + k] = eS[k];
@@ -570,6 +586,7 @@ __global__ void __launch_bounds__(32 * WarpLayout<T, N, WOBS>::MAXW, (SCN == kSc
                 }
             }
             bulk_pending = true;
+            if (ZERO_ONCE) comm_zeroed = true;
         }
 
         // ====== device controller on the new state (formation_gym/__init__.py:49-98), under the bulk store ======
