@@ -501,6 +501,22 @@ __global__ void __launch_bounds__(32 * WarpLayout<T, N, WOBS>::MAXW, (SCN == kSc
                 bulk_pending = false;
                 __syncwarp();
             }
+            // COOP_SHAPE (N = 4, 6, 8): the ideal_shape segment of all rows of the span is written by consecutive lanes <->
+            // consecutive (row, k) items: the N rows of an env read the same N shape items (broadcasts) and a half-warp's
+            // stores cover whole bank windows, where "lane l writes item kk of its own row" has 2-way conflicts even with
+            // the rotated order (N = 4: 52 % of all shared-memory wavefronts were conflicts, the shape copy 13 % of the
+            // stall samples: profiles/r02f_hd_n4)
+            constexpr bool COOP_SHAPE = SCN == kScnHD && LY::LATE_FILL && (N == 4 || N == 6 || N == 8);
+            if constexpr (COOP_SHAPE) {
+#pragma unroll
+                for (int it = 0; it < (NA * N + 31) / 32; ++it) {
+                    const int q = it * 32 + lane;
+                    if (q < NA * N) {
+                        const int R = q / N, k = q - R * N;                 // row of the span, shape item
+                        s_obs[R * IPR + 2 * N - 1 + k] = s_shp[(R / N) * N + k];
+                    }
+                }
+            }
             if (LY::LATE_FILL ? active : dn) {                              // FUSED: only reset envs are rewritten
                 // [p_vel | p_j - p_i (j != i ascending) | comm zeros | ideal_shape.flatten() | ideal_vel]
                 // (formation_hd_env.py:52-59); own row per lane, odd row stride 3N -> conflict-free STS.64
@@ -529,10 +545,12 @@ __global__ void __launch_bounds__(32 * WarpLayout<T, N, WOBS>::MAXW, (SCN == kSc
                     // (writing the static 2N items of all rows cooperatively -- lane l holding items l, l + 32 of the
                     // env's [comm | ideal_shape | ideal_vel] vector, ceil(2N / 32) conflict-free stores per row -- was
                     // measured SLOWER at N = 27: 230.6 vs 209.1 us per 65536 envs; equal at N = 16, 25, 32)
+                    if constexpr (!COOP_SHAPE) {
 #pragma unroll
-                    for (int k = 0; k < N; ++k) {
-                        int kk = k + rN; kk -= (kk >= N) ? N : 0;
-                        row[2 * N - 1 + kk] = eS[kk];
+                        for (int k = 0; k < N; ++k) {
+                            int kk = k + rN; kk -= (kk >= N) ? N : 0;
+                            row[2 * N - 1 + kk] = eS[kk];
+                        }
                     }
                     row[3 * N - 1] = iv;
                 } else {
