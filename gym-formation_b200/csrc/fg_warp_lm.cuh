@@ -496,6 +496,23 @@ __global__ void __launch_bounds__(32 * LmLayout<T, N, L, SCN, NOBS>::MAXW, 3) k_
                 }
                 zeroed = s_obs;
             }
+            // EVEN row stride: the landmark segment of all rows of the span is written by consecutive lanes <-> consecutive
+            // (row, k) items -- the N rows of an env read the same L landmark items (broadcasts) and a half-warp's stores
+            // fall on consecutive banks; "lane l writes item kk of its own row" has 2-way conflicts even in rotated
+            // order (fg_warp.cuh, COOP_SHAPE: N = 4 29.6 -> 27.6 us there)
+            // (not for the obstacle scenario: its relative obstacle entries need the row's agent as well, and the unrolled
+            // loop then spills 72-112 bytes under the 80-register bound)
+            constexpr bool COOP_LM = (IPR % 2) == 0 && !OBST;
+            if constexpr (COOP_LM) {
+#pragma unroll
+                for (int it = 0; it < (NA * L + 31) / 32; ++it) {
+                    const int q = it * 32 + lane;
+                    if (q < NA * L) {
+                        const int R = q / L, k = q - R * L;                 // row of the span, landmark
+                        s_obs[R * IPR + 1 + k] = s_lm[(R / N) * L + k];     // landmark p_pos, absolute
+                    }
+                }
+            }
             if (active) {
                 // [p_vel | landmark p_pos (L) | other_pos (NREL) | comm of the others (N-1 zeros)]
                 // (formation_hd_partial_env.py:40-65 / formation_hd_partial_range_env.py:40-54).  Own row per lane; an
@@ -507,16 +524,18 @@ __global__ void __launch_bounds__(32 * LmLayout<T, N, L, SCN, NOBS>::MAXW, 3) k_
                 const R2* eP = s_pnew + le * 2 * N + i;                     // eP[k] = agent (i + k) mod N
                 const R2* eA = s_pnew + le * 2 * N;                         // eA[j] = agent j
                 row[0] = v;
-                const int rL = ROT ? lane % L : 0;
+                if constexpr (!COOP_LM) {
+                    const int rL = ROT ? lane % L : 0;
 #pragma unroll
-                for (int k = 0; k < L; ++k) {
-                    int kk = k + rL; kk -= (kk >= L) ? L : 0;
-                    R2 l = eL[kk];                                          // landmark p_pos, absolute
-                    if (OBST && kk >= LG) {                                 // obstacles: NEW position relative to me (:58-59)
-                        const R2 o = s_on[le * NO + (kk - LG)];
-                        l = O::make(O::sub(o.x, p.x), O::sub(o.y, p.y));
+                    for (int k = 0; k < L; ++k) {
+                        int kk = k + rL; kk -= (kk >= L) ? L : 0;
+                        R2 l = eL[kk];                                      // landmark p_pos, absolute
+                        if (OBST && kk >= LG) {                             // obstacles: NEW position relative to me (:58-59)
+                            const R2 o = s_on[le * NO + (kk - LG)];
+                            l = O::make(O::sub(o.x, p.x), O::sub(o.y, p.y));
+                        }
+                        row[1 + kk] = l;
                     }
-                    row[1 + kk] = l;
                 }
                 const int rR = ROT ? lane % NREL : 0;
 #pragma unroll
