@@ -813,6 +813,8 @@ def also_configs(formation_gym, torch, device, dtype, peak, a):
          "formation_hd_env", 3, 1048576, "bfs", 30, {}),
         ("hd N=3 E=1048576, device controller compiled INTO the step kernel (fg_step_policy: one launch per step)",
          "formation_hd_env", 3, 1048576, "bfs_fused", 30, {}),
+        ("hd N=4 E=262144 (the reference's most used training size: train/README.md:37,49,167)", "formation_hd_env", 4,
+         262144, "step", 50, {}),
         ("configs[2] hd N=27 E=65536", "formation_hd_env", 27, 65536, "step", 50, {}),
         ("configs[3] hd N=243 E=1024 (one GPU's share of 8192)", "formation_hd_env", 243, 1024, "step", 30, {}),
         ("configs[3] hd N=243 E=8192 (all 8192 envs on one GPU)", "formation_hd_env", 243, 8192, "step", 10, {}),

@@ -7,6 +7,7 @@ bash scripts/gpu_prof.sh $TAG \
   "formation_hd_env 9 131072 1 k_hd_warp all" "formation_hd_env 9 131072 1 k_hd_warp none" \
   "formation_hd_env 9 1048576 1 k_hd_warp none" "formation_hd_env 27 65536 1 k_hd_warp none" \
   "formation_hd_env 3 1048576 1 k_hd_warp none" "basic_formation_env 3 1048576 1 k_hd_warp none" \
+  "formation_hd_env 4 262144 1 k_hd_warp none" \
   "formation_hd_env 243 1024 1 k_step none" "formation_hd_env 243 1024 0 k_step none" \
   "formation_hd_env 243 8192 0 k_step none" "formation_hd_env 81 8192 1 k_step none" \
   "formation_hd_partial_env 4 262144 1 k_lm_warp none" "formation_hd_partial_env 5 262144 1 k_lm_warp none" \
