@@ -268,7 +268,8 @@ __global__ void __launch_bounds__(32 * WarpLayout<T, N, WOBS>::MAXW, (SCN == kSc
                 // (Round 2: the point differences of this loop and of the reward loop as ONE packed FMA each --
                 // fma.rn.f32x2 p * (-1, -1) + q, bit-identical to two FSUBs, 35 FFMA2 and 40 fewer SASS instructions at
                 // N = 9 -- is a tie on a box that holds 1965 MHz: N = 9 50.95 vs 50.85 us, N = 16 78.0 vs 75.8, N = 25
-                // 188.4 vs 192.0, N = 3 82.2 vs 81.6.  Not kept.)
+                // 188.4 vs 192.0, N = 3 82.2 vs 81.6; and after 1 s under load (clock under the power cap): N = 9 54.5 vs
+                // 54.4-54.8, N = 16 79.2 vs 71.6.  Not kept.)
                 // Pass 2: the near pairs in ascending j -- the order in which the reference's a<b
                 // double loop adds contributions to agent i.
                 const T dmin = O::add(a.size, a.size);                      // core.py:307

@@ -1,5 +1,7 @@
 """Quick timing of the fused step kernel alone (CUDA graph of 5 steps) for a list of configs.
-Usage: python scripts/quick_cfg.py "scen N E [obs] [opt=val,...|-] [envkw=val,...]" ..."""
+Usage: [FG_SETTLE=seconds] python scripts/quick_cfg.py "scen N E [obs] [opt=val,...|-] [envkw=val,...]" ...
+FG_SETTLE > 0 replays the graph for that long first, so that the timing runs at the clock the box holds under its
+power cap (as bench.py's timed region does) instead of the burst clock."""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "gym-formation_b200"))
@@ -20,6 +22,14 @@ for cfg in sys.argv[1:]:
         env.sample_actions()
         g = env.capture_steps(5, policy=lambda e_: None)
         g.replay(); torch.cuda.synchronize()
+        settle = float(os.environ.get("FG_SETTLE", "0"))
+        if settle > 0:
+            import time
+            t0 = time.perf_counter()
+            while time.perf_counter() - t0 < settle:
+                for _ in range(20):
+                    g.replay()
+                torch.cuda.synchronize()
         best = 1e9
         for rep in range(3):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
