@@ -181,3 +181,42 @@ def test_lm_warp_kernel_vs_oracle(scen, N, L, kw):
         assert np.all(np.abs(rew[:, 0, 0].double().cpu().numpy() - R) <= tol + 1e-6 * np.abs(R))
         assert np.array_equal(done[:, 0].cpu().numpy(), ref["done"])
         assert int((ref["indiv"] < ref["indiv"].max(axis=1, keepdims=True) - 0.5).sum()) > 0   # collisions were exercised
+
+
+@pytest.mark.parametrize("scen,N,kw", [
+    ("formation_hd_partial_env", 4, dict(u_noise=0.1)),
+    ("formation_hd_partial_env", 5, dict(max_speed=0.3, mass=2.0)),
+    ("formation_hd_partial_range_env", 4, dict(collide=False, accel=3.0)),
+    ("formation_hd_obs_env", 4, dict(u_noise=0.05, max_speed=0.6, obstacle_mass=2.5)),
+    ("formation_hd_obs_env", 5, dict(mass=0.5, accel=4.0)),
+])
+def test_lm_warp_kernel_nonstandard_worlds_equal_tile_kernel(scen, N, kw):
+    """The generic (fp64) instantiation's run-time paths the product configuration never takes -- Philox motor noise,
+    max_speed clamp, mass != 1, accel, agents that do not collide, heavier obstacles -- bit-identical to the tile kernels."""
+    mk = lambda: BatchedFormationEnv(scen, 301, N, episode_length=6, dtype=torch.float64, seed=29, **kw)  # noqa: E731
+    a, b = mk(), mk()
+    a.reset(); b.reset()
+    for t in range(9):
+        oa, ra, da, ia = a.step_random(record_actions=True)
+        with nat.options(force_tile_kernel=1):
+            ob, rb, db, ib = b.step_random(record_actions=True)
+        for k, (x, y) in enumerate(((oa, ob), (ra, rb), (a.pos, b.pos), (a.vel, b.vel), (a.landmarks, b.landmarks),
+                                    (ia["individual_reward"], ib["individual_reward"]), (a.actions, b.actions))):
+            assert torch.equal(x, y), (t, k)
+        assert torch.equal(da, db)
+
+
+def test_lm_warp_kernel_graph_replay_matches_eager():
+    """CUDA graph of fused random-policy steps (device tick: the Philox counter lives on the device) == the same steps
+    launched one by one, for the three landmark scenarios in fp32 (the STD instantiation both ways)."""
+    for scen, N in (("formation_hd_partial_env", 4), ("formation_hd_partial_range_env", 5), ("formation_hd_obs_env", 4)):
+        mk = lambda: BatchedFormationEnv(scen, 2050, N, episode_length=7, seed=31)  # noqa: E731
+        a, b = mk(), mk()
+        a.reset(); b.reset()
+        g = a.capture_steps(4, fused_random=True)                    # (runs one warm-up step itself)
+        g.replay(); g.replay()
+        torch.cuda.synchronize()
+        for _ in range(9):
+            b.step_random(record_actions=True)
+        for k in ("pos", "vel", "landmarks", "obs", "reward", "actions", "step_count", "ep_return"):
+            assert torch.equal(getattr(a, k), getattr(b, k)), (scen, k)
