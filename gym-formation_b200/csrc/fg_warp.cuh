@@ -46,6 +46,9 @@ template <typename T, int N, bool WOBS> struct WarpLayout {
     // shared memory caps the SM at 12 warps anyway: 4-warp CTAs let ptxas use up to 255 registers (with
     // 256-thread bounds it stopped at 128 and spilled two, and with ~2 KB of L1 left beside the shared
     // memory every spill reload went to L2 -- 34 % of all stall samples in profiles/r01c_warp27_before).
+    // (N = 9 as seven 4-warp CTAs per SM -- 72 registers, no spills, 28 instead of 24 warps -- is no faster: 51.3 vs
+    // 50.9 us at the burst clock, 55.7-56.2 vs 55.3-56.0 us after 1 s under load, 544 vs 521 us per 1 M envs.  Neither
+    // more warps nor fewer instructions move the power-capped number, so it is not SM-side latency that follows the clock.)
     static constexpr int MAXW = (N >= 16) ? 4 : 8;
     static constexpr int MINB = (N >= 16) ? 0 : 3;
     // Where the observation image is filled.  LATE (after rewards / auto-reset, from the shared state):
