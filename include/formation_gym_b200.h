@@ -314,6 +314,9 @@ int fg_write_probe(int variant, void* dst, unsigned long long bytes, unsigned ch
  *           rows where done_dev[row] != 0 (done [E,N] uint8 of the same step; NULL = no whole rows).
  *   mode 3: pack the dynamic prefixes into `staging_dev` [E*N, dyn_items], then one contiguous copy of that into
  *           `obs_host` (which then is a [E*N, dyn_items] staging array; diagnostic).
+ *   mode 4: as 2, but in whole 64-byte host cache lines (the lines a row's dynamic prefix -- or, where done_dev says so,
+ *           the whole row -- touches; the extra bytes are row items whose host copy already equals the device value).
+ *           obs_dev / obs_host 64-byte aligned, E*N*row_items*item_bytes a multiple of 16, else FG_ERR_ARG.
  * Asynchronous on `stream`; the caller synchronises before reading the host array. */
 int fg_obs_to_host(const void* obs_dev, void* obs_host, const uint8_t* done_dev, void* staging_dev, int E, int N,
                    int row_items, int dyn_items, int item_bytes, int mode, void* stream);

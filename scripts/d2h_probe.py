@@ -37,12 +37,15 @@ def run(mode, dst, reps=10, done_t=None):
 
 full_b, dyn_b = obs.numel() * 4, rows * dyn * 8
 for mode, name, dst, b in ((0, "full contiguous memcpy", host, full_b), (1, "2-D memcpy, dynamic prefix", host, dyn_b),
-                           (2, "zero-copy scatter kernel", host, dyn_b), (3, "pack + contiguous memcpy", stage_h, dyn_b)):
+                           (2, "zero-copy scatter kernel", host, dyn_b), (3, "pack + contiguous memcpy", stage_h, dyn_b),
+                           (4, "zero-copy kernel, whole 64-B lines", host, dyn_b)):
     t = run(mode, dst)
     print("mode %d %-32s %8.3f ms  %7.2f GB/s useful (%d MB)" % (mode, name, t * 1e3, b / t / 1e9, b >> 20), flush=True)
 # correctness of mode 1 / 2 (host array must equal the device tensor where written)
 host.zero_(); run(2, host, 1)
 ok2 = torch.equal(host[:, :, :2 * N], obs.cpu()[:, :, :2 * N]) and float(host[:, :, 2 * N:].abs().sum()) == 0.0
+host.copy_(obs.cpu()); host[:, :, :2 * N] = 0; run(4, host, 1)            # mode 4 relies on the static part being in place
+ok4 = torch.equal(host, obs.cpu())
 host.zero_(); run(1, host, 1)
 ok1 = torch.equal(host[:, :, :2 * N], obs.cpu()[:, :, :2 * N]) and float(host[:, :, 2 * N:].abs().sum()) == 0.0
 done[::7] = 1
@@ -50,7 +53,7 @@ host.zero_(); run(2, host, 1, done)
 oc = obs.cpu()
 ok2d = torch.equal(host[::7], oc[::7]) and torch.equal(host[1::7, :, :2 * N], oc[1::7, :, :2 * N]) and \
     float(host[1::7, :, 2 * N:].abs().sum()) == 0.0
-print("correct: mode1", ok1, "mode2", ok2, "mode2+done", ok2d)
+print("correct: mode1", ok1, "mode2", ok2, "mode2+done", ok2d, "mode4", ok4)
 # host-side scatter of the packed staging array (torch CPU, multi-threaded strided copy)
 hv = host.view(rows, 6 * N)
 t0 = time.perf_counter()

@@ -172,5 +172,15 @@ def test_obs_to_host_modes(N, E, dtype):
     packed = torch.empty(E * N, 2 * dyn, dtype=dtype).pin_memory()
     run(3, packed)
     assert torch.equal(packed, oc.view(E * N, 6 * N)[:, :2 * N])
+    # mode 4 (whole 64-byte host lines): relies on the static part of the host array already holding the device values
+    if (E * N * row_items * isz) % 16 == 0:
+        host.copy_(oc); host[:, :, :2 * N] = -3.0
+        run(4, host)
+        assert torch.equal(host, oc)
+        host.copy_(oc); host[:, :, :2 * N] = -3.0; host[::5] = -3.0
+        run(4, host, done)
+        assert torch.equal(host, oc)
+    else:
+        assert lib.fg_obs_to_host(obs.data_ptr(), host.data_ptr(), None, None, E, N, row_items, dyn, isz, 4, st) == -1
     assert lib.fg_obs_to_host(obs.data_ptr(), host.data_ptr(), None, None, E, N, row_items, row_items + 1, isz, 1, st) == -1
     assert lib.fg_obs_to_host(obs.data_ptr(), host.data_ptr(), None, None, E, N, row_items, dyn, 12, 1, st) == -1
