@@ -240,6 +240,10 @@ __global__ void __launch_bounds__(32 * WarpLayout<T, N, WOBS>::MAXW, (SCN == kSc
 
         // =============================== World.step (core.py:206-225) ===========================
         if (active) {
+            // (Round 2: an instantiation that draws the NEXT span's actions inside the reward / row-fill block -- the
+            // Philox chain interleaved with shared-memory waits instead of standing here in a block of its own -- is
+            // bit-identical and a tie: N = 9 57.4 vs 56.7 us, N = 27 220.7 vs 220.7, N = 3 93.8 vs 95.2, N = 16 74.0
+            // vs 74.8, same box after 1 s under load.  The draw is not on the critical path; not kept.)
             if (a.random_actions) {                                         // test.py:20
                 U4 r = philox(a.seed, ge, (uint32_t)i, tick0 + (uint32_t)ts, kAction);
                 u = O::make(uniform_pm1<T>(r.x), uniform_pm1<T>(r.y));
